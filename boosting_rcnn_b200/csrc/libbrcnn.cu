@@ -1,0 +1,582 @@
+// libbrcnn.so — C ABI (include/brcnn.h) over the sm_100a kernels.
+// Single translation unit: nvcc -gencode arch=compute_100a,code=sm_100a
+//   -fmad=false -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <atomic>
+#include <cstring>
+
+#include "../../include/brcnn.h"
+#include "boost_loss.cuh"
+#include "common.cuh"
+#include "nms_kernels.cuh"
+#include "rcnn_post.cuh"
+#include "roi_align.cuh"
+#include "roi_align_bwd.cuh"
+#include "rpn.cuh"
+
+namespace brcnn {
+static std::atomic<int64_t> g_launches{0};
+int64_t g_launch_count_add(int n) { return g_launches.fetch_add(n) + n; }
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+// --------------------------------------------------------------------------
+// generic nms operator kernels (single segment)
+// --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ordered_bits(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// max over all 4K coordinates -> out[0] (single CTA; handles negatives)
+__global__ void __launch_bounds__(1024)
+nms_maxcoord_kernel(const float* __restrict__ boxes, int K, float* out) {
+  __shared__ float s[32];
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < 4 * K; i += blockDim.x) m = fmaxf(m, boxes[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s[w]);
+    out[0] = m;
+  }
+}
+
+// rank by counting: rank_i = #{j : key_j > key_i}; scatter sorted arrays.
+__global__ void __launch_bounds__(256)
+nms_rank_scatter_kernel(const float* __restrict__ boxes,
+                        const float* __restrict__ scores,
+                        const int64_t* __restrict__ idxs, int K,
+                        const float* __restrict__ maxc,
+                        float4* __restrict__ sorted_boxes,
+                        u64* __restrict__ sorted_key, int32_t* __restrict__ order,
+                        int32_t* __restrict__ count) {
+  __shared__ u64 tile[256];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  u64 mine = 0;
+  if (i < K) mine = ((u64)ordered_bits(scores[i]) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)i);
+  int rank = 0;
+  for (int j0 = 0; j0 < K; j0 += 256) {
+    const int j = j0 + threadIdx.x;
+    __syncthreads();
+    tile[threadIdx.x] = (j < K)
+        ? (((u64)ordered_bits(scores[j]) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)j))
+        : 0ull;
+    __syncthreads();
+    const int m = min(256, K - j0);
+    for (int t = 0; t < m; ++t) rank += (tile[t] > mine);
+  }
+  if (i < K) {
+    float4 b = reinterpret_cast<const float4*>(boxes)[i];
+    if (idxs != nullptr) {
+      const float o = (float)idxs[i] * (maxc[0] + 1.0f);
+      b = add_seg_offset(b, o);
+    }
+    sorted_boxes[rank] = b;
+    sorted_key[rank] = mine;
+    order[rank] = i;
+  }
+  if (i == 0) count[0] = K;
+}
+
+__global__ void nms_finalize_kernel(const float* __restrict__ boxes,
+                                    const float* __restrict__ scores,
+                                    const int32_t* __restrict__ order,
+                                    const int32_t* __restrict__ kept_pos,
+                                    const int32_t* __restrict__ kept_count,
+                                    int64_t* __restrict__ keep,
+                                    float* __restrict__ dets,
+                                    int32_t* __restrict__ num_keep) {
+  const int n = kept_count[0];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) num_keep[0] = n;
+  if (j >= n) return;
+  const int src = order[kept_pos[j]];
+  keep[j] = src;
+  if (dets != nullptr) {
+    const float4 b = reinterpret_cast<const float4*>(boxes)[src];
+    float* o = dets + (size_t)j * 5;
+    o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w; o[4] = scores[src];
+  }
+}
+
+struct NmsWs {
+  size_t sorted_boxes, sorted_key, order, count, maxc, mask, kept_pos, kept_count, total;
+};
+static NmsWs nms_ws(int K) {
+  NmsWs w; size_t o = 0;
+  const size_t W = (K + 63) / 64;
+  w.sorted_boxes = o; o = align256(o + (size_t)K * 16);
+  w.sorted_key = o;   o = align256(o + (size_t)K * 8);
+  w.order = o;        o = align256(o + (size_t)K * 4);
+  w.count = o;        o = align256(o + 4);
+  w.maxc = o;         o = align256(o + 4);
+  w.mask = o;         o = align256(o + (size_t)K * W * 8);
+  w.kept_pos = o;     o = align256(o + (size_t)K * 4);
+  w.kept_count = o;   o = align256(o + 4);
+  w.total = o;
+  return w;
+}
+
+// --------------------------------------------------------------------------
+// RPN workspace layout
+// --------------------------------------------------------------------------
+struct RpnDerived {
+  int Kc, keep_cap, W;
+  int level_n[BRCNN_MAX_LEVELS], level_k[BRCNN_MAX_LEVELS];
+};
+static int rpn_derive(const brcnn_rpn_params* p, RpnDerived* d) {
+  if (!p || p->batch <= 0 || p->num_levels <= 0 || p->num_levels > BRCNN_MAX_LEVELS ||
+      p->num_anchors <= 0 || p->num_anchors > BRCNN_MAX_ANCHORS || p->max_per_img <= 0)
+    return BRCNN_ERR_ARG;
+  int Kc = 0;
+  for (int l = 0; l < p->num_levels; ++l) {
+    if (p->feat_h[l] <= 0 || p->feat_w[l] <= 0) return BRCNN_ERR_ARG;
+    const long long n = (long long)p->feat_h[l] * p->feat_w[l] * p->num_anchors;
+    if (n > 0x3fffffff) return BRCNN_ERR_UNSUPPORTED;
+    d->level_n[l] = (int)n;
+    d->level_k[l] = (p->nms_pre > 0 && n > p->nms_pre) ? p->nms_pre : (int)n;
+    if (d->level_k[l] > Kc) Kc = d->level_k[l];
+  }
+  d->Kc = Kc;
+  d->keep_cap = Kc < p->max_per_img ? Kc : p->max_per_img;
+  d->W = (Kc + 63) / 64;
+  return BRCNN_OK;
+}
+
+struct RpnWsInternal {
+  brcnn_rpn_ws_layout pub;
+  size_t mask, kept_key;
+};
+static int rpn_ws(const brcnn_rpn_params* p, RpnWsInternal* w) {
+  RpnDerived d;
+  int rc = rpn_derive(p, &d);
+  if (rc) return rc;
+  const size_t S = (size_t)p->batch * p->num_levels;
+  size_t o = 0;
+  w->pub.cand_cap = d.Kc;
+  w->pub.keep_cap = d.keep_cap;
+  w->pub.cand_boxes = o; o = align256(o + S * d.Kc * 16);
+  w->pub.cand_key = o;   o = align256(o + S * d.Kc * 8);
+  w->pub.cand_valid = o; o = align256(o + S * d.Kc);
+  w->pub.cand_count = o; o = align256(o + S * 4);
+  w->pub.img_maxc = o;   o = align256(o + (size_t)p->batch * 4);
+  w->pub.kept_pos = o;   o = align256(o + S * d.keep_cap * 4);
+  w->pub.kept_count = o; o = align256(o + S * 4);
+  w->kept_key = o;       o = align256(o + S * d.keep_cap * 8);
+  w->mask = o;           o = align256(o + S * d.Kc * d.W * 8);
+  w->pub.total_bytes = (int64_t)o;
+  return BRCNN_OK;
+}
+
+// --------------------------------------------------------------------------
+// RCNN workspace layout
+// --------------------------------------------------------------------------
+struct RcnnWsInternal {
+  brcnn_rcnn_ws_layout pub;
+  size_t seg_boxes, mask, kept_key;
+  int keep_cap, W;
+};
+static int rcnn_ws(const brcnn_rcnn_params* p, RcnnWsInternal* w) {
+  if (!p || p->batch <= 0 || p->rois_per_img <= 0 || p->num_classes <= 0 ||
+      p->max_per_img <= 0)
+    return BRCNN_ERR_ARG;
+  if (p->rois_per_img > 4096) return BRCNN_ERR_UNSUPPORTED;
+  const size_t B = p->batch, Rc = p->rois_per_img, C = p->num_classes;
+  const size_t nbox = p->reg_class_agnostic ? 1 : C;
+  w->keep_cap = (int)(Rc < (size_t)p->max_per_img ? Rc : (size_t)p->max_per_img);
+  w->W = (int)((Rc + 63) / 64);
+  size_t o = 0;
+  w->pub.scores = o;     o = align256(o + B * Rc * (C + 1) * 4);
+  w->pub.bboxes = o;     o = align256(o + B * Rc * nbox * 16);
+  w->pub.img_maxc = o;   o = align256(o + B * 4);
+  w->pub.seg_count = o;  o = align256(o + B * C * 4);
+  w->pub.seg_key = o;    o = align256(o + B * C * Rc * 8);
+  w->seg_boxes = o;      o = align256(o + B * C * Rc * 16);
+  w->pub.kept_pos = o;   o = align256(o + B * C * w->keep_cap * 4);
+  w->pub.kept_count = o; o = align256(o + B * C * 4);
+  w->kept_key = o;       o = align256(o + B * C * w->keep_cap * 8);
+  w->mask = o;           o = align256(o + B * C * Rc * w->W * 8);
+  w->pub.total_bytes = (int64_t)o;
+  return BRCNN_OK;
+}
+
+}  // namespace brcnn
+
+using namespace brcnn;
+
+extern "C" {
+
+const char* brcnn_version(void) { return "libbrcnn 0.1 sm_100a"; }
+int64_t brcnn_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------- RPN --------------------------------------
+int brcnn_rpn_workspace_layout(const brcnn_rpn_params* p, brcnn_rpn_ws_layout* out) {
+  RpnWsInternal w;
+  int rc = rpn_ws(p, &w);
+  if (rc) return rc;
+  if (out) *out = w.pub;
+  return BRCNN_OK;
+}
+
+size_t brcnn_rpn_workspace_bytes(const brcnn_rpn_params* p) {
+  RpnWsInternal w;
+  if (rpn_ws(p, &w)) return 0;
+  return (size_t)w.pub.total_bytes;
+}
+
+int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
+                         const float* const* cls_scores_host,
+                         const float* const* bbox_preds_host,
+                         const float* const* iou_preds_host,
+                         const float* base_anchors, const float* img_hw,
+                         float* proposals, int32_t* num_proposals,
+                         void* workspace, size_t workspace_bytes,
+                         brcnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RpnDerived d;
+  int rc = rpn_derive(p, &d);
+  if (rc) return rc;
+  RpnWsInternal w;
+  rc = rpn_ws(p, &w);
+  if (rc) return rc;
+  if (!cls_scores_host || !bbox_preds_host || !iou_preds_host || !base_anchors ||
+      !img_hw || !proposals || !num_proposals || !workspace)
+    return BRCNN_ERR_ARG;
+  if (workspace_bytes < (size_t)w.pub.total_bytes) return BRCNN_ERR_WORKSPACE;
+  if (p->batch > 65535) return BRCNN_ERR_UNSUPPORTED;
+
+  RpnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = p->num_anchors; a.L = p->num_levels; a.B = p->batch; a.Kc = d.Kc;
+  int idx_base = 0, slice_cap = 0;
+  for (int l = 0; l < p->num_levels; ++l) {
+    RpnLevel& lv = a.lv[l];
+    lv.cls = cls_scores_host[l]; lv.bbox = bbox_preds_host[l]; lv.iou = iou_preds_host[l];
+    if (!lv.cls || !lv.bbox || !lv.iou) return BRCNN_ERR_ARG;
+    lv.H = p->feat_h[l]; lv.W = p->feat_w[l];
+    lv.stride_w = p->stride_w[l]; lv.stride_h = p->stride_h[l];
+    lv.n = d.level_n[l]; lv.k = d.level_k[l]; lv.idx_base = idx_base;
+    idx_base += lv.n;
+    const int P = lv.H * lv.W;
+    const int pp = (P + RPN_CS - 1) / RPN_CS;
+    if (pp * a.A > slice_cap) slice_cap = pp * a.A;
+  }
+  a.kpow2 = next_pow2(d.Kc);
+  a.slice_cap = slice_cap;
+  for (int i = 0; i < 4; ++i) { a.means[i] = p->means[i]; a.stds[i] = p->stds[i]; }
+  a.max_ratio = p->max_ratio; a.min_size = p->min_bbox_size;
+  const size_t smem = (size_t)a.kpow2 * 8 + (size_t)slice_cap * 4;
+  if (smem > 220 * 1024) return BRCNN_ERR_UNSUPPORTED;
+
+  char* ws = (char*)workspace;
+  float4* cand_boxes = (float4*)(ws + w.pub.cand_boxes);
+  u64* cand_key = (u64*)(ws + w.pub.cand_key);
+  uint8_t* cand_valid = (uint8_t*)(ws + w.pub.cand_valid);
+  int32_t* cand_count = (int32_t*)(ws + w.pub.cand_count);
+  int* img_maxc = (int*)(ws + w.pub.img_maxc);
+  int32_t* kept_pos = (int32_t*)(ws + w.pub.kept_pos);
+  int32_t* kept_count = (int32_t*)(ws + w.pub.kept_count);
+  u64* kept_key = (u64*)(ws + w.kept_key);
+  u64* mask = (u64*)(ws + w.mask);
+
+  cudaError_t e = cudaMemsetAsync(img_maxc, 0, (size_t)p->batch * 4, stream);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(rpn_select_decode_kernel,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(RPN_CS, p->num_levels, p->batch);
+  rpn_select_decode_kernel<<<grid, RPN_THREADS, smem, stream>>>(
+      a, base_anchors, img_hw, cand_boxes, cand_key, cand_valid, cand_count, img_maxc);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+
+  const int S = p->batch * p->num_levels;
+  rc = launch_nms_segments(cand_boxes, cand_valid, cand_count, S, d.Kc,
+                           p->iou_threshold, 0.f, (const float*)img_maxc,
+                           p->num_levels, mask, cand_key, kept_pos, kept_key,
+                           kept_count, d.keep_cap, p->max_per_img, stream);
+  if (rc) return rc;
+
+  RpnMergeEpilogue ep{cand_boxes, proposals, d.Kc, p->max_per_img};
+  nms_merge_kernel<RpnMergeEpilogue><<<p->batch, 256, 0, stream>>>(
+      kept_pos, kept_key, kept_count, p->num_levels, d.keep_cap, p->max_per_img,
+      num_proposals, ep);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+// ------------------------------- NMS --------------------------------------
+size_t brcnn_nms_workspace_bytes(int32_t num_boxes) {
+  if (num_boxes <= 0) return 256;
+  return nms_ws(num_boxes).total;
+}
+
+int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* idxs,
+                      int32_t K, float iou_threshold, int32_t offset,
+                      int64_t* keep, float* dets, int32_t* num_keep,
+                      void* workspace, size_t workspace_bytes,
+                      brcnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (K < 0 || !num_keep || (offset != 0 && offset != 1)) return BRCNN_ERR_ARG;
+  if (K == 0) {
+    cudaError_t e = cudaMemsetAsync(num_keep, 0, 4, stream);
+    return e == cudaSuccess ? BRCNN_OK : (int)e;
+  }
+  if (!boxes || !scores || !keep || !workspace) return BRCNN_ERR_ARG;
+  if (K > 393216) return BRCNN_ERR_UNSUPPORTED;
+  NmsWs w = nms_ws(K);
+  if (workspace_bytes < w.total) return BRCNN_ERR_WORKSPACE;
+  char* ws = (char*)workspace;
+  float4* sboxes = (float4*)(ws + w.sorted_boxes);
+  u64* skey = (u64*)(ws + w.sorted_key);
+  int32_t* order = (int32_t*)(ws + w.order);
+  int32_t* count = (int32_t*)(ws + w.count);
+  float* maxc = (float*)(ws + w.maxc);
+  u64* mask = (u64*)(ws + w.mask);
+  int32_t* kept_pos = (int32_t*)(ws + w.kept_pos);
+  int32_t* kept_count = (int32_t*)(ws + w.kept_count);
+  if (idxs != nullptr) {
+    nms_maxcoord_kernel<<<1, 1024, 0, stream>>>(boxes, K, maxc);
+    g_launch_count_add(1);
+    BRCNN_CUDA_CHECK_LAST();
+  }
+  nms_rank_scatter_kernel<<<(K + 255) / 256, 256, 0, stream>>>(
+      boxes, scores, idxs, K, maxc, sboxes, skey, order, count);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  int rc = launch_nms_segments(sboxes, nullptr, count, 1, K, iou_threshold,
+                               (float)offset, nullptr, 1, mask, nullptr, kept_pos,
+                               nullptr, kept_count, K, K, stream);
+  if (rc) return rc;
+  nms_finalize_kernel<<<(K + 255) / 256, 256, 0, stream>>>(
+      boxes, scores, order, kept_pos, kept_count, keep, dets, num_keep);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+// ------------------------------- RoI --------------------------------------
+int brcnn_map_roi_levels(const float* rois, int32_t R, float finest_scale,
+                         int32_t num_levels, int64_t* target_lvls,
+                         brcnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (R < 0 || num_levels <= 0) return BRCNN_ERR_ARG;
+  if (R == 0) return BRCNN_OK;
+  if (!rois || !target_lvls) return BRCNN_ERR_ARG;
+  map_roi_levels_kernel<<<(R + 255) / 256, 256, 0, stream>>>(rois, R, finest_scale,
+                                                             num_levels, target_lvls);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+static int roi_args_from(const brcnn_roi_params* p, RoiArgs* a) {
+  if (!p || p->batch <= 0 || p->channels <= 0 || (p->channels & 3) ||
+      p->num_levels <= 0 || p->num_levels > BRCNN_MAX_LEVELS || p->pooled_h <= 0 ||
+      p->pooled_w <= 0)
+    return BRCNN_ERR_ARG;
+  memset(a, 0, sizeof(*a));
+  a->B = p->batch; a->C = p->channels; a->L = p->num_levels;
+  a->PH = p->pooled_h; a->PW = p->pooled_w;
+  a->sampling_ratio = p->sampling_ratio; a->aligned = p->aligned;
+  a->finest_scale = p->finest_scale;
+  for (int l = 0; l < p->num_levels; ++l) {
+    if (p->feat_h[l] <= 0 || p->feat_w[l] <= 0) return BRCNN_ERR_ARG;
+    a->H[l] = p->feat_h[l]; a->W[l] = p->feat_w[l]; a->scale[l] = p->spatial_scale[l];
+  }
+  return BRCNN_OK;
+}
+
+int brcnn_roi_extract_forward(const brcnn_roi_params* p,
+                              const float* const* feats_nhwc_host,
+                              const float* rois, int32_t R, float* out,
+                              int32_t* roi_levels, brcnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RoiArgs a;
+  int rc = roi_args_from(p, &a);
+  if (rc) return rc;
+  if (R < 0) return BRCNN_ERR_ARG;
+  if (R == 0) return BRCNN_OK;
+  if (!feats_nhwc_host || !rois || !out) return BRCNN_ERR_ARG;
+  for (int l = 0; l < a.L; ++l) {
+    if (!feats_nhwc_host[l]) return BRCNN_ERR_ARG;
+    a.feat[l] = feats_nhwc_host[l];
+  }
+  const int nbins = a.PH * a.PW;
+  // channel chunk: as many channels as fit ~56 KB of staging, multiple of 32
+  int chunk = a.C;
+  const int max_chunk = ((56 * 1024) / (nbins * 4)) & ~31;
+  if (max_chunk < 32) return BRCNN_ERR_UNSUPPORTED;
+  if (chunk > max_chunk) chunk = max_chunk;
+  a.chunk_c = chunk;
+  const int nchunks = (a.C + chunk - 1) / chunk;
+  const size_t smem = (size_t)chunk * nbins * 4;
+  cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(R, nchunks);
+  roi_align_fwd_kernel<<<grid, 256, smem, stream>>>(a, rois, R, out, roi_levels);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+size_t brcnn_roi_extract_backward_workspace_bytes(const brcnn_roi_params* p,
+                                                  int32_t R) {
+  RoiArgs a;
+  if (roi_args_from(p, &a) || R < 0) return 0;
+  return roi_bwd_ws(a, R).total;
+}
+
+int brcnn_roi_extract_backward(const brcnn_roi_params* p, const float* grad_out,
+                               const float* rois, int32_t R,
+                               float* const* grad_feats_nhwc_host, void* workspace,
+                               size_t workspace_bytes, brcnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RoiArgs a;
+  int rc = roi_args_from(p, &a);
+  if (rc) return rc;
+  if (R < 0 || !grad_feats_nhwc_host) return BRCNN_ERR_ARG;
+  if (R > 0 && (!grad_out || !rois)) return BRCNN_ERR_ARG;
+  return roi_bwd_launch(a, grad_out, rois, R, grad_feats_nhwc_host, workspace,
+                        workspace_bytes, stream);
+}
+
+static int transpose_launch(const float* in, float* out, int batch, int rows,
+                            int cols, cudaStream_t stream) {
+  if (batch <= 0 || rows <= 0 || cols <= 0 || !in || !out) return BRCNN_ERR_ARG;
+  if (batch > 65535 || (rows + 31) / 32 > 65535) return BRCNN_ERR_UNSUPPORTED;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
+  transpose_kernel<<<grid, 256, 0, stream>>>(in, out, rows, cols);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+int brcnn_nchw_to_nhwc(const float* in, float* out, int32_t batch, int32_t channels,
+                       int32_t hw, brcnn_stream_t stream) {
+  return transpose_launch(in, out, batch, channels, hw, (cudaStream_t)stream);
+}
+int brcnn_nhwc_to_nchw(const float* in, float* out, int32_t batch, int32_t channels,
+                       int32_t hw, brcnn_stream_t stream) {
+  return transpose_launch(in, out, batch, hw, channels, (cudaStream_t)stream);
+}
+
+// ------------------------------- loss -------------------------------------
+int brcnn_boost_loss(const brcnn_loss_params* p, const float* cls_score,
+                     const int64_t* labels, const float* label_weights,
+                     const float* prior, const float* bbox_pred,
+                     const float* bbox_targets, const float* bbox_weights,
+                     float* out_scalars, float* grad_cls_score,
+                     float* grad_bbox_pred, brcnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!p || p->num_rois < 0 || p->num_classes <= 0 || !out_scalars) return BRCNN_ERR_ARG;
+  if (p->num_rois > 0 && (!cls_score || !labels || !prior || !bbox_pred ||
+                          !bbox_targets || !bbox_weights || !grad_cls_score))
+    return BRCNN_ERR_ARG;
+  LossArgs a;
+  a.N = p->num_rois; a.C = p->num_classes; a.agnostic = p->reg_class_agnostic;
+  a.reg_norm_mean = p->reg_norm_mean; a.gamma = p->gamma; a.alpha = p->alpha;
+  a.wcls = p->loss_cls_weight; a.wbbox = p->loss_bbox_weight;
+  if (grad_bbox_pred != nullptr && a.N > 0) {
+    const size_t nb = (size_t)a.N * (a.agnostic ? 4 : 4 * a.C) * 4;
+    cudaError_t e = cudaMemsetAsync(grad_bbox_pred, 0, nb, stream);
+    if (e != cudaSuccess) return (int)e;
+  }
+  boost_loss_kernel<<<1, 1024, 0, stream>>>(a, cls_score, labels, label_weights, prior,
+                                            bbox_pred, bbox_targets, bbox_weights,
+                                            out_scalars, grad_cls_score, grad_bbox_pred);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+// ------------------------------- RCNN post --------------------------------
+int brcnn_rcnn_workspace_layout(const brcnn_rcnn_params* p, brcnn_rcnn_ws_layout* out) {
+  RcnnWsInternal w;
+  int rc = rcnn_ws(p, &w);
+  if (rc) return rc;
+  if (out) *out = w.pub;
+  return BRCNN_OK;
+}
+size_t brcnn_rcnn_workspace_bytes(const brcnn_rcnn_params* p) {
+  RcnnWsInternal w;
+  if (rcnn_ws(p, &w)) return 0;
+  return (size_t)w.pub.total_bytes;
+}
+
+int brcnn_rcnn_get_bboxes(const brcnn_rcnn_params* p, const float* rois,
+                          const float* prior, const int32_t* num_rois,
+                          const float* cls_score, const float* bbox_pred,
+                          const float* img_hw, const float* scale_factor,
+                          float* det_bboxes, int64_t* det_labels, int32_t* num_dets,
+                          void* workspace, size_t workspace_bytes,
+                          brcnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RcnnWsInternal w;
+  int rc = rcnn_ws(p, &w);
+  if (rc) return rc;
+  if (!rois || !num_rois || !cls_score || !bbox_pred || !img_hw || !det_bboxes ||
+      !det_labels || !num_dets || !workspace)
+    return BRCNN_ERR_ARG;
+  if (p->prob && !prior) return BRCNN_ERR_ARG;
+  if (p->rescale && !scale_factor) return BRCNN_ERR_ARG;
+  if (workspace_bytes < (size_t)w.pub.total_bytes) return BRCNN_ERR_WORKSPACE;
+  if (p->batch > 65535 || p->num_classes > 65535) return BRCNN_ERR_UNSUPPORTED;
+  RcnnArgs a;
+  a.B = p->batch; a.Rc = p->rois_per_img; a.C = p->num_classes;
+  a.agnostic = p->reg_class_agnostic; a.prob = p->prob; a.rescale = p->rescale;
+  for (int i = 0; i < 4; ++i) { a.means[i] = p->means[i]; a.stds[i] = p->stds[i]; }
+  a.max_ratio = p->max_ratio; a.score_thr = p->score_thr;
+  char* ws = (char*)workspace;
+  float* scores = (float*)(ws + w.pub.scores);
+  float4* bboxes = (float4*)(ws + w.pub.bboxes);
+  int* img_maxc = (int*)(ws + w.pub.img_maxc);
+  int32_t* seg_count = (int32_t*)(ws + w.pub.seg_count);
+  u64* seg_key = (u64*)(ws + w.pub.seg_key);
+  float4* seg_boxes = (float4*)(ws + w.seg_boxes);
+  int32_t* kept_pos = (int32_t*)(ws + w.pub.kept_pos);
+  int32_t* kept_count = (int32_t*)(ws + w.pub.kept_count);
+  u64* kept_key = (u64*)(ws + w.kept_key);
+  u64* mask = (u64*)(ws + w.mask);
+
+  cudaError_t e = cudaMemsetAsync(img_maxc, 0, (size_t)a.B * 4, stream);
+  if (e != cudaSuccess) return (int)e;
+  const int rows = a.B * a.Rc;
+  const size_t smem1 = (size_t)RCNN_FUSE_WARPS * (a.C + 1) * 4;
+  if (smem1 > 48 * 1024) return BRCNN_ERR_UNSUPPORTED;
+  rcnn_fuse_decode_kernel<<<(rows + RCNN_FUSE_WARPS - 1) / RCNN_FUSE_WARPS,
+                            RCNN_FUSE_WARPS * 32, smem1, stream>>>(
+      a, rois, prior, num_rois, cls_score, bbox_pred, img_hw, scale_factor, scores,
+      bboxes, img_maxc);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+
+  const int rpow2 = next_pow2(a.Rc);
+  dim3 grid2(a.C, a.B);
+  rcnn_class_sort_kernel<<<grid2, 256, (size_t)rpow2 * 8, stream>>>(
+      a, num_rois, scores, bboxes, rpow2, seg_key, seg_boxes, seg_count);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+
+  const int S = a.B * a.C;
+  rc = launch_nms_segments(seg_boxes, nullptr, seg_count, S, a.Rc, p->iou_threshold,
+                           0.f, (const float*)img_maxc, a.C, mask, seg_key, kept_pos,
+                           kept_key, kept_count, w.keep_cap, p->max_per_img, stream);
+  if (rc) return rc;
+
+  RcnnMergeEpilogue ep{bboxes, det_bboxes, det_labels, a.Rc, a.C,
+                       a.agnostic ? 1 : a.C, p->max_per_img};
+  nms_merge_kernel<RcnnMergeEpilogue><<<a.B, 256, 0, stream>>>(
+      kept_pos, kept_key, kept_count, a.C, w.keep_cap, p->max_per_img, num_dets, ep);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,444 @@
+"""Torch-facing operators over libbrcnn (C ABI, hand-written sm_100a kernels).
+
+Mirrors the slice of ``mmcv.ops`` the reference path uses
+(``batched_nms``, ``nms``, ``RoIAlign`` / ``roi_align`` — call sites
+mmdet/models/dense_heads/atss_rpn_head.py:6,756, mmdet/core/post_processing/
+bbox_nms.py:3,86, mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:
+54-59) plus the fused batch-level entry points the drop-in heads call.
+
+torch is plumbing here: it owns device memory and the current stream; every
+computation is a libbrcnn kernel.  CPU tensors are rejected (no fallback).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+from torch.nn.modules.utils import _pair
+
+from . import _lib
+from ._lib import (LossParams, RcnnParams, RcnnWsLayout, RoiParams, RpnParams,
+                   RpnWsLayout, check, ptr_array)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f'{name} must be a CUDA tensor: boosting_rcnn_b200 has no CPU path')
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def max_ratio_f32(wh_ratio_clip=16 / 1000):
+    """``np.abs(np.log(wh_ratio_clip))`` as torch.clamp applies it to fp32
+    (delta_xywh_bbox_coder.py:226,234-235)."""
+    return float(np.float32(np.abs(np.log(wh_ratio_clip))))
+
+
+# --------------------------------------------------------------------------
+# RPN proposals
+# --------------------------------------------------------------------------
+def make_rpn_params(batch, featmap_sizes, strides, num_anchors, nms_pre,
+                    max_per_img, iou_threshold, min_bbox_size,
+                    means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.),
+                    wh_ratio_clip=16 / 1000):
+    p = RpnParams()
+    p.batch, p.num_levels, p.num_anchors = batch, len(featmap_sizes), num_anchors
+    for l, ((h, w), s) in enumerate(zip(featmap_sizes, strides)):
+        sw, sh = _pair(s)
+        p.feat_h[l], p.feat_w[l] = int(h), int(w)
+        p.stride_w[l], p.stride_h[l] = int(sw), int(sh)
+    p.nms_pre, p.max_per_img = int(nms_pre), int(max_per_img)
+    p.iou_threshold, p.min_bbox_size = float(iou_threshold), float(min_bbox_size)
+    for i in range(4):
+        p.means[i], p.stds[i] = float(means[i]), float(stds[i])
+    p.max_ratio = max_ratio_f32(wh_ratio_clip)
+    return p
+
+
+def rpn_workspace_layout(p):
+    lay = RpnWsLayout()
+    check(_lib.load().brcnn_rpn_workspace_layout(p, lay), 'brcnn_rpn_workspace_layout')
+    return lay
+
+
+def rpn_get_bboxes(p, cls_scores, bbox_preds, iou_preds, base_anchors, img_hw,
+                   return_workspace=False):
+    """Batched ATSSRPNHead.get_bboxes.  Returns (proposals (B,M,5) zero padded,
+    num_proposals (B,) int32)."""
+    lib = _lib.load()
+    cls_scores = [_f32c(t, 'cls_scores') for t in cls_scores]
+    bbox_preds = [_f32c(t, 'bbox_preds') for t in bbox_preds]
+    iou_preds = [_f32c(t, 'iou_preds') for t in iou_preds]
+    base_anchors = _f32c(base_anchors, 'base_anchors')
+    img_hw = _f32c(img_hw, 'img_hw')
+    dev = cls_scores[0].device
+    B, L, A = p.batch, p.num_levels, p.num_anchors
+    for l in range(L):
+        assert tuple(cls_scores[l].shape) == (B, A, p.feat_h[l], p.feat_w[l]), cls_scores[l].shape
+        assert tuple(bbox_preds[l].shape) == (B, 4 * A, p.feat_h[l], p.feat_w[l])
+        assert tuple(iou_preds[l].shape) == (B, A, p.feat_h[l], p.feat_w[l])
+    assert tuple(base_anchors.shape) == (L, A, 4)
+    assert tuple(img_hw.shape) == (B, 2)
+    nbytes = lib.brcnn_rpn_workspace_bytes(p)
+    if nbytes == 0:
+        raise RuntimeError('brcnn_rpn_workspace_bytes: bad parameters')
+    ws = _ws(nbytes, dev)
+    proposals = torch.empty((B, p.max_per_img, 5), dtype=torch.float32, device=dev)
+    num = torch.empty((B,), dtype=torch.int32, device=dev)
+    rc = lib.brcnn_rpn_get_bboxes(
+        p, ptr_array([t.data_ptr() for t in cls_scores]),
+        ptr_array([t.data_ptr() for t in bbox_preds]),
+        ptr_array([t.data_ptr() for t in iou_preds]),
+        base_anchors.data_ptr(), img_hw.data_ptr(), proposals.data_ptr(),
+        num.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    check(rc, 'brcnn_rpn_get_bboxes')
+    if return_workspace:
+        return proposals, num, ws
+    return proposals, num
+
+
+# --------------------------------------------------------------------------
+# mmcv.ops.nms / batched_nms mirrors
+# --------------------------------------------------------------------------
+def _nms_raw(boxes, scores, idxs, iou_threshold, offset):
+    lib = _lib.load()
+    boxes = _f32c(boxes, 'boxes')
+    scores = _f32c(scores, 'scores')
+    K = boxes.size(0)
+    dev = boxes.device
+    keep = torch.empty((K,), dtype=torch.int64, device=dev)
+    dets = torch.empty((K, 5), dtype=torch.float32, device=dev)
+    num = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if K == 0:
+        return dets, keep
+    if idxs is not None:
+        idxs = idxs.to(torch.int64).contiguous()
+    ws = _ws(lib.brcnn_nms_workspace_bytes(K), dev)
+    rc = lib.brcnn_batched_nms(
+        boxes.data_ptr(), scores.data_ptr(),
+        idxs.data_ptr() if idxs is not None else None, K, float(iou_threshold),
+        int(offset), keep.data_ptr(), dets.data_ptr(), num.data_ptr(),
+        ws.data_ptr(), ws.numel(), _stream())
+    check(rc, 'brcnn_batched_nms')
+    n = int(num.item())  # the reference API returns variable-length tensors
+    return dets[:n], keep[:n]
+
+
+def nms(boxes, scores, iou_threshold, offset=0, score_threshold=0, max_num=-1):
+    """mmcv.ops.nms: returns (dets (k,5), inds (k,) int64), score descending."""
+    assert boxes.size(1) == 4 and boxes.size(0) == scores.size(0)
+    assert offset in (0, 1)
+    valid_inds = None
+    if score_threshold > 0:
+        valid_mask = scores > score_threshold
+        valid_inds = torch.nonzero(valid_mask, as_tuple=False).squeeze(dim=1)
+        boxes, scores = boxes[valid_mask], scores[valid_mask]
+    dets, inds = _nms_raw(boxes, scores, None, iou_threshold, offset)
+    if max_num > 0:
+        dets, inds = dets[:max_num], inds[:max_num]
+    if valid_inds is not None:
+        inds = valid_inds[inds]
+    return dets, inds
+
+
+def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
+    """mmcv.ops.batched_nms.  ``split_thr`` is accepted and
+    ignored: with the pinned (score desc, index asc) order the split and
+    unsplit paths return identical results."""
+    nms_cfg_ = dict(nms_cfg)
+    class_agnostic = nms_cfg_.pop('class_agnostic', class_agnostic)
+    nms_type = nms_cfg_.pop('type', 'nms')
+    if nms_type != 'nms':
+        raise NotImplementedError(f'nms type {nms_type!r} is outside the hot path')
+    nms_cfg_.pop('split_thr', None)
+    max_num = nms_cfg_.pop('max_num', -1)
+    iou_threshold = nms_cfg_.pop('iou_threshold')
+    dets, keep = _nms_raw(boxes, scores, None if class_agnostic else idxs,
+                          iou_threshold, 0)
+    if max_num > 0:
+        dets, keep = dets[:max_num], keep[:max_num]
+    return dets, keep
+
+
+# --------------------------------------------------------------------------
+# RoI extraction (level map + multi-level RoIAlign), autograd enabled
+# --------------------------------------------------------------------------
+def make_roi_params(batch, channels, featmap_sizes, spatial_scales, output_size,
+                    sampling_ratio=0, aligned=True, finest_scale=56):
+    p = RoiParams()
+    p.batch, p.channels, p.num_levels = int(batch), int(channels), len(featmap_sizes)
+    for l, ((h, w), s) in enumerate(zip(featmap_sizes, spatial_scales)):
+        p.feat_h[l], p.feat_w[l], p.spatial_scale[l] = int(h), int(w), float(s)
+    oh, ow = _pair(output_size)
+    p.pooled_h, p.pooled_w = int(oh), int(ow)
+    p.sampling_ratio, p.aligned = int(sampling_ratio), int(bool(aligned))
+    p.finest_scale = float(finest_scale)
+    return p
+
+
+def to_nhwc(x):
+    """(B,C,H,W) tensor -> NHWC-contiguous storage (returned as a (B,H,W,C)
+    tensor).  channels_last inputs are a free view; NCHW-contiguous ones go
+    through the library's transpose kernel."""
+    assert x.dim() == 4
+    if not x.is_cuda:
+        raise RuntimeError('to_nhwc: CUDA tensor required (no CPU path)')
+    if x.dtype != torch.float32:
+        x = x.float()
+    B, C, H, W = x.shape
+    xp = x.permute(0, 2, 3, 1)
+    if xp.is_contiguous():
+        return xp
+    x = x.contiguous()
+    out = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+    check(_lib.load().brcnn_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, C, H * W,
+                                         _stream()), 'brcnn_nchw_to_nhwc')
+    return out
+
+
+def nhwc_to_nchw(x):
+    """(B,H,W,C) contiguous -> (B,C,H,W) contiguous via the library kernel."""
+    B, H, W, C = x.shape
+    x = x.contiguous()
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    check(_lib.load().brcnn_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), B, C, H * W,
+                                         _stream()), 'brcnn_nhwc_to_nchw')
+    return out
+
+
+def map_roi_levels(rois, num_levels, finest_scale=56):
+    rois = _f32c(rois, 'rois')
+    out = torch.empty((rois.size(0),), dtype=torch.int64, device=rois.device)
+    check(_lib.load().brcnn_map_roi_levels(rois.data_ptr(), rois.size(0),
+                                           float(finest_scale), int(num_levels),
+                                           out.data_ptr(), _stream()),
+          'brcnn_map_roi_levels')
+    return out
+
+
+class _RoiExtractFunction(Function):
+    """feats are (B,C,H,W)-shaped tensors (any memory format)."""
+
+    @staticmethod
+    def forward(ctx, rois, spatial_scales, output_size, sampling_ratio, aligned,
+                finest_scale, *feats):
+        lib = _lib.load()
+        rois = _f32c(rois, 'rois')
+        assert rois.dim() == 2 and rois.size(1) == 5, 'RoI must be (idx, x1, y1, x2, y2)!'
+        B, C = feats[0].shape[:2]
+        sizes = [tuple(f.shape[-2:]) for f in feats]
+        p = make_roi_params(B, C, sizes, spatial_scales, output_size,
+                            sampling_ratio, aligned, finest_scale)
+        nhwc = [to_nhwc(f) for f in feats]
+        R = rois.size(0)
+        out = torch.empty((R, C, p.pooled_h, p.pooled_w), dtype=torch.float32,
+                          device=rois.device)
+        lvls = torch.empty((R,), dtype=torch.int32, device=rois.device)
+        check(lib.brcnn_roi_extract_forward(
+            p, ptr_array([t.data_ptr() for t in nhwc]), rois.data_ptr(), R,
+            out.data_ptr(), lvls.data_ptr(), _stream()), 'brcnn_roi_extract_forward')
+        ctx.save_for_backward(rois)
+        ctx.params = p
+        ctx.channels_last = [f.permute(0, 2, 3, 1).is_contiguous() for f in feats]
+        ctx.mark_non_differentiable(lvls)
+        return out, lvls
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_lvls):
+        lib = _lib.load()
+        (rois,) = ctx.saved_tensors
+        p = ctx.params
+        grad_out = _f32c(grad_out, 'grad_out')
+        dev = grad_out.device
+        R = rois.size(0)
+        grads = [torch.empty((p.batch, p.feat_h[l], p.feat_w[l], p.channels),
+                             dtype=torch.float32, device=dev)
+                 for l in range(p.num_levels)]
+        ws = _ws(lib.brcnn_roi_extract_backward_workspace_bytes(p, R), dev)
+        check(lib.brcnn_roi_extract_backward(
+            p, grad_out.data_ptr(), rois.data_ptr(), R,
+            ptr_array([g.data_ptr() for g in grads]), ws.data_ptr(), ws.numel(),
+            _stream()), 'brcnn_roi_extract_backward')
+        outs = []
+        for g, cl in zip(grads, ctx.channels_last):
+            # channels_last inputs get a channels_last gradient for free;
+            # NCHW-contiguous inputs get an NCHW-contiguous one.
+            outs.append(g.permute(0, 3, 1, 2) if cl else nhwc_to_nchw(g))
+        return (None, None, None, None, None, None, *outs)
+
+
+def roi_extract(feats, rois, spatial_scales, output_size=7, sampling_ratio=0,
+                aligned=True, finest_scale=56, return_levels=False):
+    """Fused SingleRoIExtractor.forward: level mapping + RoIAlign on every
+    level in one launch.  Returns (R,C,oh,ow) [and int32 levels]."""
+    out, lvls = _RoiExtractFunction.apply(rois, tuple(spatial_scales), output_size,
+                                          sampling_ratio, aligned, finest_scale,
+                                          *feats)
+    return (out, lvls) if return_levels else out
+
+
+def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0,
+              pool_mode='avg', aligned=True):
+    """mmcv.ops.roi_align on one feature map."""
+    if pool_mode != 'avg':
+        raise NotImplementedError("pool_mode='max' is outside the hot path")
+    return roi_extract([input], rois, [spatial_scale], output_size, sampling_ratio,
+                       aligned, finest_scale=56)
+
+
+class RoIAlign(nn.Module):
+    """mmcv.ops.RoIAlign(output_size, spatial_scale, sampling_ratio, pool_mode,
+    aligned, use_torchvision) with the same attributes (``output_size`` is read
+    by single_level_roi_extractor.py:60)."""
+
+    def __init__(self, output_size, spatial_scale=1.0, sampling_ratio=0,
+                 pool_mode='avg', aligned=True, use_torchvision=False):
+        super().__init__()
+        self.output_size = _pair(output_size)
+        self.spatial_scale = float(spatial_scale)
+        self.sampling_ratio = int(sampling_ratio)
+        self.pool_mode = pool_mode
+        self.aligned = aligned
+        self.use_torchvision = use_torchvision
+
+    def forward(self, input, rois):
+        return roi_align(input, rois, self.output_size, self.spatial_scale,
+                         self.sampling_ratio, self.pool_mode, self.aligned)
+
+    def __repr__(self):
+        return (f'{self.__class__.__name__}(output_size={self.output_size}, '
+                f'spatial_scale={self.spatial_scale}, '
+                f'sampling_ratio={self.sampling_ratio}, pool_mode={self.pool_mode}, '
+                f'aligned={self.aligned}, use_torchvision={self.use_torchvision})')
+
+
+# --------------------------------------------------------------------------
+# Boosting reweighted loss
+# --------------------------------------------------------------------------
+class _BoostLossFunction(Function):
+
+    @staticmethod
+    def forward(ctx, cls_score, bbox_pred, labels, label_weights, prior,
+                bbox_targets, bbox_weights, num_classes, reg_class_agnostic, gamma,
+                alpha, loss_cls_weight, loss_bbox_weight, reg_norm_mean):
+        lib = _lib.load()
+        cls_score = _f32c(cls_score, 'cls_score')
+        bbox_pred = _f32c(bbox_pred, 'bbox_pred')
+        prior = _f32c(prior, 'prior')
+        bbox_targets = _f32c(bbox_targets, 'bbox_targets')
+        bbox_weights = _f32c(bbox_weights, 'bbox_weights')
+        labels = labels.to(torch.int64).contiguous()
+        if label_weights is not None:
+            label_weights = _f32c(label_weights, 'label_weights')
+        N = cls_score.size(0)
+        assert cls_score.size(1) == num_classes + 1
+        p = LossParams(N, num_classes, int(reg_class_agnostic), float(gamma),
+                       float(alpha), float(loss_cls_weight), float(loss_bbox_weight),
+                       int(reg_norm_mean))
+        out = torch.empty((8,), dtype=torch.float32, device=cls_score.device)
+        g_cls = torch.empty_like(cls_score)
+        g_box = torch.empty_like(bbox_pred)
+        check(lib.brcnn_boost_loss(
+            p, cls_score.data_ptr(), labels.data_ptr(),
+            label_weights.data_ptr() if label_weights is not None else None,
+            prior.data_ptr(), bbox_pred.data_ptr(), bbox_targets.data_ptr(),
+            bbox_weights.data_ptr(), out.data_ptr(), g_cls.data_ptr(),
+            g_box.data_ptr(), _stream()), 'brcnn_boost_loss')
+        ctx.save_for_backward(g_cls, g_box)
+        loss_cls, loss_bbox, acc = out[0], out[1], out[2]
+        ctx.mark_non_differentiable(acc)
+        return loss_cls, loss_bbox, acc, out
+
+    @staticmethod
+    def backward(ctx, g_loss_cls, g_loss_bbox, _g_acc, _g_out):
+        g_cls, g_box = ctx.saved_tensors
+        gc = g_cls * g_loss_cls if g_loss_cls is not None else None
+        gb = g_box * g_loss_bbox if g_loss_bbox is not None else None
+        return (gc, gb) + (None,) * 12
+
+
+def boost_loss(cls_score, bbox_pred, labels, label_weights, prior, bbox_targets,
+               bbox_weights, num_classes, reg_class_agnostic=False, gamma=0.5,
+               alpha=0.0, loss_cls_weight=1.0, loss_bbox_weight=1.0,
+               reg_norm_mean=False):
+    """Fused ProbRoIHead boost loss.  Returns (loss_cls, loss_bbox, acc,
+    scalars[8]); loss_cls / loss_bbox carry gradients to cls_score / bbox_pred."""
+    return _BoostLossFunction.apply(
+        cls_score, bbox_pred, labels, label_weights, prior, bbox_targets,
+        bbox_weights, num_classes, reg_class_agnostic, gamma, alpha,
+        loss_cls_weight, loss_bbox_weight, reg_norm_mean)
+
+
+# --------------------------------------------------------------------------
+# Score fusion + decode + class-wise NMS
+# --------------------------------------------------------------------------
+def make_rcnn_params(batch, rois_per_img, num_classes, score_thr, iou_threshold,
+                     max_per_img, means=(0., 0., 0., 0.), stds=(.1, .1, .2, .2),
+                     reg_class_agnostic=False, prob=True, rescale=False,
+                     wh_ratio_clip=16 / 1000):
+    p = RcnnParams()
+    p.batch, p.rois_per_img, p.num_classes = int(batch), int(rois_per_img), int(num_classes)
+    p.reg_class_agnostic, p.prob, p.rescale = int(reg_class_agnostic), int(prob), int(rescale)
+    for i in range(4):
+        p.means[i], p.stds[i] = float(means[i]), float(stds[i])
+    p.max_ratio = max_ratio_f32(wh_ratio_clip)
+    p.score_thr, p.iou_threshold = float(score_thr), float(iou_threshold)
+    p.max_per_img = int(max_per_img)
+    return p
+
+
+def rcnn_workspace_layout(p):
+    lay = RcnnWsLayout()
+    check(_lib.load().brcnn_rcnn_workspace_layout(p, lay), 'brcnn_rcnn_workspace_layout')
+    return lay
+
+
+def rcnn_get_bboxes(p, rois, prior, num_rois, cls_score, bbox_pred, img_hw,
+                    scale_factor=None, return_workspace=False):
+    """Batched fusion + ProbConvFCBBoxHead.get_bboxes + multiclass_nms on the
+    padded RoI layout.  Returns (det_bboxes (B,M,5), det_labels (B,M) int64,
+    num_dets (B,) int32)."""
+    lib = _lib.load()
+    rois = _f32c(rois, 'rois')
+    cls_score = _f32c(cls_score, 'cls_score')
+    bbox_pred = _f32c(bbox_pred, 'bbox_pred')
+    img_hw = _f32c(img_hw, 'img_hw')
+    dev = rois.device
+    rows = p.batch * p.rois_per_img
+    assert rois.shape == (rows, 5) and cls_score.shape == (rows, p.num_classes + 1)
+    assert bbox_pred.shape == (rows, 4 if p.reg_class_agnostic else 4 * p.num_classes)
+    if prior is not None:
+        prior = _f32c(prior, 'prior')
+        assert prior.numel() == rows
+    if scale_factor is not None:
+        scale_factor = _f32c(scale_factor, 'scale_factor')
+        assert scale_factor.shape == (p.batch, 4)
+    num_rois = num_rois.to(torch.int32).contiguous()
+    nbytes = lib.brcnn_rcnn_workspace_bytes(p)
+    if nbytes == 0:
+        raise RuntimeError('brcnn_rcnn_workspace_bytes: bad parameters')
+    ws = _ws(nbytes, dev)
+    det = torch.empty((p.batch, p.max_per_img, 5), dtype=torch.float32, device=dev)
+    lab = torch.empty((p.batch, p.max_per_img), dtype=torch.int64, device=dev)
+    num = torch.empty((p.batch,), dtype=torch.int32, device=dev)
+    check(lib.brcnn_rcnn_get_bboxes(
+        p, rois.data_ptr(), prior.data_ptr() if prior is not None else None,
+        num_rois.data_ptr(), cls_score.data_ptr(), bbox_pred.data_ptr(),
+        img_hw.data_ptr(),
+        scale_factor.data_ptr() if scale_factor is not None else None,
+        det.data_ptr(), lab.data_ptr(), num.data_ptr(), ws.data_ptr(), ws.numel(),
+        _stream()), 'brcnn_rcnn_get_bboxes')
+    if return_workspace:
+        return det, lab, num, ws
+    return det, lab, num

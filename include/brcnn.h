@@ -1,0 +1,257 @@
+/*
+ * libbrcnn — C ABI of the B200-native (sm_100a) Boosting R-CNN proposal-to-RoI
+ * hot path.  This is the drop-in boundary: plain pointers and sizes, no torch
+ * types.  Every entry point replaces a piece of the reference
+ * (mousecpn/Boosting-R-CNN = mmdet 2.17 + mmcv-full 1.4.0); the replaced
+ * interface is cited as file:line relative to the reference tree, or as the
+ * mmcv `_ext` symbol it stands in for (mmcv source is not vendored in the
+ * reference).
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers unless the name ends in _host or
+ *     the comment says "host array"; the caller owns every buffer;
+ *   - nothing is allocated, nothing synchronises, every launch goes to
+ *     `stream` (graph-capturable); scratch lives in the caller's `workspace`
+ *     (size from the matching *_workspace_bytes query, 256-byte aligned);
+ *   - return value: 0 = ok, <0 = argument/size error (BRCNN_ERR_*), >0 = the
+ *     cudaError_t of a failed launch;
+ *   - fp32 data, int32 counts, int64 where the reference returns torch.long;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails.
+ */
+#ifndef BRCNN_H_
+#define BRCNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRCNN_OK 0
+#define BRCNN_ERR_ARG (-1)
+#define BRCNN_ERR_WORKSPACE (-2)
+#define BRCNN_ERR_UNSUPPORTED (-3)
+
+#define BRCNN_MAX_LEVELS 8
+#define BRCNN_MAX_ANCHORS 32
+
+typedef void* brcnn_stream_t; /* a cudaStream_t */
+
+/* library / build identification: "libbrcnn <ver> sm_100a" */
+const char* brcnn_version(void);
+/* number of kernels launched by this library since load (all streams) */
+int64_t brcnn_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * (1) RPN proposal generation
+ * replaces ATSSRPNHead.get_bboxes / _get_bboxes_single
+ *   (mmdet/models/dense_heads/atss_rpn_head.py:466-503, 688-760),
+ *   AnchorGenerator.single_level_grid_anchors (anchor_generator.py:338-381),
+ *   delta2bbox (delta_xywh_bbox_coder.py:144-272) and
+ *   mmcv.ops.batched_nms with ids = pyramid level (atss_rpn_head.py:756).
+ * ---------------------------------------------------------------------- */
+typedef struct brcnn_rpn_params {
+  int32_t batch;                       /* B images                           */
+  int32_t num_levels;                  /* L pyramid levels                   */
+  int32_t num_anchors;                 /* A base anchors per location        */
+  int32_t feat_h[BRCNN_MAX_LEVELS];    /* H_l                                */
+  int32_t feat_w[BRCNN_MAX_LEVELS];    /* W_l                                */
+  int32_t stride_w[BRCNN_MAX_LEVELS];  /* anchor stride (w,h)                */
+  int32_t stride_h[BRCNN_MAX_LEVELS];
+  int32_t nms_pre;                     /* cfg.nms_pre (<=0: keep all)        */
+  int32_t max_per_img;                 /* cfg.max_per_img                    */
+  float iou_threshold;                 /* cfg.nms.iou_threshold              */
+  float min_bbox_size;                 /* cfg.min_bbox_size (<0: no filter)  */
+  float means[4];                      /* bbox_coder.target_means            */
+  float stds[4];                       /* bbox_coder.target_stds             */
+  float max_ratio;                     /* |ln(wh_ratio_clip)| as fp32        */
+} brcnn_rpn_params;
+
+/* byte offsets (into workspace) of the intermediate arrays, for parity tests.
+ * Kc = per-level candidate capacity = min(nms_pre, max_l H_l*W_l*A).       */
+typedef struct brcnn_rpn_ws_layout {
+  int64_t cand_cap;     /* Kc                                                */
+  int64_t keep_cap;     /* per-segment kept-list capacity                    */
+  int64_t cand_boxes;   /* float  [B][L][Kc][4]  decoded + clipped           */
+  int64_t cand_key;     /* uint64 [B][L][Kc]  score_bits<<32 | ~anchor_idx   */
+  int64_t cand_valid;   /* uint8  [B][L][Kc]  passes the min-size filter     */
+  int64_t cand_count;   /* int32  [B][L]                                     */
+  int64_t img_maxc;     /* float  [B]  boxes.max() over valid candidates     */
+  int64_t kept_pos;     /* int32  [B][L][keep_cap] candidate rank of keeps   */
+  int64_t kept_count;   /* int32  [B][L]                                     */
+  int64_t total_bytes;
+} brcnn_rpn_ws_layout;
+
+int brcnn_rpn_workspace_layout(const brcnn_rpn_params* p, brcnn_rpn_ws_layout* out);
+size_t brcnn_rpn_workspace_bytes(const brcnn_rpn_params* p);
+
+int brcnn_rpn_get_bboxes(
+    const brcnn_rpn_params* p,
+    const float* const* cls_scores_host, /* host array[L] of (B,A,H_l,W_l)   */
+    const float* const* bbox_preds_host, /* host array[L] of (B,4A,H_l,W_l)  */
+    const float* const* iou_preds_host,  /* host array[L] of (B,A,H_l,W_l)   */
+    const float* base_anchors,           /* (L,A,4)                          */
+    const float* img_hw,                 /* (B,2) img_shape[:2] = (h,w)      */
+    float* proposals,                    /* (B,max_per_img,5) x1,y1,x2,y2,s  */
+    int32_t* num_proposals,              /* (B)                              */
+    void* workspace, size_t workspace_bytes, brcnn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (2) NMS operators — stand-ins for mmcv `_ext.nms` and the Python wrappers
+ * mmcv.ops.nms / mmcv.ops.batched_nms (call sites atss_rpn_head.py:756,
+ * mmdet/core/post_processing/bbox_nms.py:86).  Order: score descending,
+ * ties by lower input index; suppression test inter/(a+b-inter) > thr.
+ * ---------------------------------------------------------------------- */
+size_t brcnn_nms_workspace_bytes(int32_t num_boxes);
+
+/* idxs may be NULL (plain / class-agnostic nms).  keep: int64[num_boxes]
+ * (first *num_keep entries valid, score-descending), dets: optional
+ * float[num_boxes][5] rows cat(boxes[keep], scores[keep]).                 */
+int brcnn_batched_nms(const float* boxes, const float* scores,
+                      const int64_t* idxs, int32_t num_boxes,
+                      float iou_threshold, int32_t offset, int64_t* keep,
+                      float* dets, int32_t* num_keep, void* workspace,
+                      size_t workspace_bytes, brcnn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (3) RoI feature extraction
+ * replaces SingleRoIExtractor.map_roi_levels / forward
+ *   (mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:36-115)
+ * and mmcv `_ext.roi_align_forward` / `roi_align_backward`
+ *   (built at base_roi_extractor.py:54-59), pool_mode = avg.
+ * Feature maps are NHWC (channels_last) fp32: (B, H_l, W_l, C).
+ * ---------------------------------------------------------------------- */
+typedef struct brcnn_roi_params {
+  int32_t batch;
+  int32_t channels;                      /* C, multiple of 4                 */
+  int32_t num_levels;
+  int32_t feat_h[BRCNN_MAX_LEVELS];
+  int32_t feat_w[BRCNN_MAX_LEVELS];
+  float spatial_scale[BRCNN_MAX_LEVELS]; /* 1/stride                         */
+  int32_t pooled_h, pooled_w;            /* roi_layer.output_size            */
+  int32_t sampling_ratio;                /* 0 = adaptive ceil(roi/pooled)    */
+  int32_t aligned;                       /* mmcv default 1                   */
+  float finest_scale;                    /* 56                               */
+} brcnn_roi_params;
+
+/* target_lvls of map_roi_levels: int64[R] */
+int brcnn_map_roi_levels(const float* rois, int32_t num_rois,
+                         float finest_scale, int32_t num_levels,
+                         int64_t* target_lvls, brcnn_stream_t stream);
+
+/* rois: (R,5) [batch_idx, x1,y1,x2,y2]; rows with batch_idx < 0 are padding
+ * and produce zeros.  out: (R, C, pooled_h, pooled_w) NCHW-contiguous, the
+ * layout ConvFCBBoxHead flattens (convfc_bbox_head.py:164).
+ * roi_levels: optional int32[R] (level used for each RoI).                 */
+int brcnn_roi_extract_forward(const brcnn_roi_params* p,
+                              const float* const* feats_nhwc_host,
+                              const float* rois, int32_t num_rois, float* out,
+                              int32_t* roi_levels, brcnn_stream_t stream);
+
+size_t brcnn_roi_extract_backward_workspace_bytes(const brcnn_roi_params* p,
+                                                  int32_t num_rois);
+/* grad_feats_nhwc: host array[L] of (B,H_l,W_l,C) buffers; every element is
+ * written exactly once (levels without RoIs get zeros), no float atomics,
+ * bit-reproducible run to run.                                             */
+int brcnn_roi_extract_backward(const brcnn_roi_params* p,
+                               const float* grad_out, const float* rois,
+                               int32_t num_rois,
+                               float* const* grad_feats_nhwc_host,
+                               void* workspace, size_t workspace_bytes,
+                               brcnn_stream_t stream);
+
+/* layout helpers for callers that hold NCHW maps (the reference neck's
+ * default): (B,C,H,W) <-> (B,H,W,C), fp32                                   */
+int brcnn_nchw_to_nhwc(const float* in, float* out, int32_t batch,
+                       int32_t channels, int32_t hw, brcnn_stream_t stream);
+int brcnn_nhwc_to_nchw(const float* in, float* out, int32_t batch,
+                       int32_t channels, int32_t hw, brcnn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (4) Boosting reweighted R-CNN loss, forward + gradient in one pass
+ * replaces ProbRoIHead._bbox_forward_train_boost / norm_loss
+ *   (mmdet/models/roi_heads/prob_roi_head.py:107-154),
+ *   ProbConvFCBBoxHead.loss (bbox_heads/convfc_bbox_head.py:332-418),
+ *   cross_entropy (losses/cross_entropy_loss.py:10-50), weight_reduce_loss
+ *   (losses/utils.py:28-55), L1Loss (losses/smooth_l1_loss.py:35-52) and
+ *   accuracy (losses/accuracy.py:6-51).
+ * ---------------------------------------------------------------------- */
+typedef struct brcnn_loss_params {
+  int32_t num_rois;            /* N sampled RoIs                             */
+  int32_t num_classes;         /* C foreground classes; bg label == C        */
+  int32_t reg_class_agnostic;  /* bbox_pred (N,4) instead of (N,4C)          */
+  float gamma;                 /* ProbRoIHead.gamma: w = (1-prior)^gamma     */
+  float alpha;                 /* ProbRoIHead.alpha (0 = off)                */
+  float loss_cls_weight;       /* CrossEntropyLoss.loss_weight               */
+  float loss_bbox_weight;      /* L1Loss.loss_weight                         */
+  int32_t reg_norm_mean;       /* reg_norm == 'mean'                         */
+} brcnn_loss_params;
+
+/* out_scalars: float[8] = {loss_cls, loss_bbox, acc, sum_l, sum_wl, n_pos,
+ *                          weight_scale s, 0}
+ * grad_cls_score (N,C+1) and grad_bbox_pred (N,4C | N,4) are d(loss_cls)/d.
+ * and d(loss_bbox)/d. for an upstream gradient of 1.                       */
+int brcnn_boost_loss(const brcnn_loss_params* p, const float* cls_score,
+                     const int64_t* labels, const float* label_weights,
+                     const float* prior, const float* bbox_pred,
+                     const float* bbox_targets, const float* bbox_weights,
+                     float* out_scalars, float* grad_cls_score,
+                     float* grad_bbox_pred, brcnn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (5) Probabilistic score fusion + per-class decode + class-wise NMS
+ * replaces ProbRoIHead.simple_test_bboxes fusion (prob_roi_head.py:232-240),
+ *   ProbConvFCBBoxHead.get_bboxes (convfc_bbox_head.py:294-330) and
+ *   multiclass_nms (mmdet/core/post_processing/bbox_nms.py:8-95).
+ * RoIs are in the padded layout of brcnn_rpn_get_bboxes: image b owns rows
+ * [b*rois_per_img, b*rois_per_img + num_rois[b]).
+ * ---------------------------------------------------------------------- */
+typedef struct brcnn_rcnn_params {
+  int32_t batch;
+  int32_t rois_per_img;        /* row capacity per image                     */
+  int32_t num_classes;         /* C                                          */
+  int32_t reg_class_agnostic;
+  int32_t prob;                /* ProbRoIHead.prob: sqrt(softmax*prior)      */
+  int32_t rescale;             /* divide boxes by scale_factor               */
+  float means[4];
+  float stds[4];
+  float max_ratio;
+  float score_thr;             /* test_cfg.rcnn.score_thr                    */
+  float iou_threshold;         /* test_cfg.rcnn.nms.iou_threshold            */
+  int32_t max_per_img;         /* test_cfg.rcnn.max_per_img                  */
+} brcnn_rcnn_params;
+
+typedef struct brcnn_rcnn_ws_layout {
+  int64_t scores;      /* float  [B*Rc][C+1]  fused scores                   */
+  int64_t bboxes;      /* float  [B*Rc][C][4] decoded (+rescaled) boxes      */
+  int64_t img_maxc;    /* float  [B]                                         */
+  int64_t seg_count;   /* int32  [B][C]  candidates above score_thr          */
+  int64_t seg_key;     /* uint64 [B][C][Rc] sorted score_bits<<32|~flat_idx  */
+  int64_t kept_pos;    /* int32  [B][C][Rc]                                  */
+  int64_t kept_count;  /* int32  [B][C]                                      */
+  int64_t total_bytes;
+} brcnn_rcnn_ws_layout;
+
+int brcnn_rcnn_workspace_layout(const brcnn_rcnn_params* p, brcnn_rcnn_ws_layout* out);
+size_t brcnn_rcnn_workspace_bytes(const brcnn_rcnn_params* p);
+
+int brcnn_rcnn_get_bboxes(
+    const brcnn_rcnn_params* p,
+    const float* rois,          /* (B*Rc,5) [b,x1,y1,x2,y2]                   */
+    const float* prior,         /* (B*Rc) proposal score (proposals[:, -1])   */
+    const int32_t* num_rois,    /* (B)                                        */
+    const float* cls_score,     /* (B*Rc, C+1) logits                         */
+    const float* bbox_pred,     /* (B*Rc, 4C | 4)                             */
+    const float* img_hw,        /* (B,2)                                      */
+    const float* scale_factor,  /* (B,4)                                      */
+    float* det_bboxes,          /* (B,max_per_img,5)                          */
+    int64_t* det_labels,        /* (B,max_per_img)                            */
+    int32_t* num_dets,          /* (B)                                        */
+    void* workspace, size_t workspace_bytes, brcnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRCNN_H_ */

@@ -1,0 +1,62 @@
+"""Seeded synthetic inputs shared by the parity tests, smoke() and bench.py
+(SURVEY.md §8d).  numpy on the host; callers move them to the GPU."""
+import math
+
+import numpy as np
+
+STRIDES = (8, 16, 32, 64, 128)
+
+
+def featmap_sizes(pad_h, pad_w, strides=STRIDES):
+    return [(math.ceil(pad_h / s), math.ceil(pad_w / s)) for s in strides]
+
+
+def rpn_outputs(batch, sizes, num_anchors, seed=0, cls_std=1.5, box_std=0.3,
+                duplicate_frac=0.0):
+    """cls/iou ~ N(0, cls_std), bbox ~ N(0, box_std); optional exact duplicates
+    (quantised logits) to exercise the tie-break."""
+    rng = np.random.RandomState(seed)
+    cls, box, iou = [], [], []
+    for (h, w) in sizes:
+        c = rng.normal(0, cls_std, (batch, num_anchors, h, w)).astype(np.float32)
+        u = rng.normal(0, cls_std, (batch, num_anchors, h, w)).astype(np.float32)
+        if duplicate_frac > 0:
+            m = rng.rand(*c.shape) < duplicate_frac
+            c[m] = np.round(c[m] * 4) / 4
+            u[m] = np.round(u[m] * 4) / 4
+        cls.append(c)
+        iou.append(u)
+        box.append(rng.normal(0, box_std, (batch, 4 * num_anchors, h, w)).astype(np.float32))
+    return cls, box, iou
+
+
+def fpn_feats(batch, channels, sizes, seed=0):
+    rng = np.random.RandomState(seed)
+    return [rng.normal(0, 1, (batch, channels, h, w)).astype(np.float32) for (h, w) in sizes]
+
+
+def random_rois(batch, n_per_img, img_h, img_w, seed=0, min_size=2.0, max_size=None,
+                clustered=False):
+    """(batch*n, 5) [b, x1, y1, x2, y2]; log-uniform sizes spanning all levels."""
+    rng = np.random.RandomState(seed)
+    max_size = max_size or max(img_h, img_w)
+    rois = []
+    for b in range(batch):
+        if clustered:
+            seeds = rng.rand(max(n_per_img // 10, 1), 2) * [img_w, img_h]
+            ctr = seeds[rng.randint(0, len(seeds), n_per_img)] + rng.normal(0, 4, (n_per_img, 2))
+        else:
+            ctr = rng.rand(n_per_img, 2) * [img_w, img_h]
+        wh = np.exp(rng.uniform(np.log(min_size), np.log(max_size), (n_per_img, 2)))
+        x1 = np.clip(ctr[:, 0] - wh[:, 0] / 2, 0, img_w)
+        x2 = np.clip(ctr[:, 0] + wh[:, 0] / 2, 0, img_w)
+        y1 = np.clip(ctr[:, 1] - wh[:, 1] / 2, 0, img_h)
+        y2 = np.clip(ctr[:, 1] + wh[:, 1] / 2, 0, img_h)
+        rois.append(np.stack([np.full(n_per_img, b), x1, y1, x2, y2], 1))
+    return np.concatenate(rois, 0).astype(np.float32)
+
+
+def random_boxes(n, img_h, img_w, seed=0, clustered=False):
+    r = random_rois(1, n, img_h, img_w, seed=seed, min_size=8, max_size=400,
+                    clustered=clustered)
+    return r[:, 1:].copy()

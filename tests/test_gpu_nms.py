@@ -1,0 +1,84 @@
+"""GPU parity: mmcv-style nms / batched_nms operators vs the oracle's restated
+mmcv nms_cpu + batched_nms (keep lists bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from boosting_rcnn_b200 import ops
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _scores(n, seed, dup=False):
+    rng = np.random.RandomState(seed)
+    s = rng.rand(n).astype(np.float32)
+    if dup:
+        s = np.round(s * 50) / 50
+    return s.astype(np.float32)
+
+
+@pytest.mark.parametrize('n,clustered,dup', [(1, False, False), (63, False, False),
+                                             (64, True, False), (65, True, True),
+                                             (1000, True, True), (4693, False, False),
+                                             (5000, True, True)])
+def test_nms_matches_oracle(cuda, n, clustered, dup):
+    boxes = synth.random_boxes(n, 800, 1333, seed=n, clustered=clustered)
+    scores = _scores(n, n + 1, dup)
+    dets, keep = ops.nms(torch.from_numpy(boxes).to(cuda), torch.from_numpy(scores).to(cuda), 0.7)
+    ref = oracle.nms_cpu(boxes, scores, 0.7)
+    np.testing.assert_array_equal(keep.cpu().numpy(), ref)
+    np.testing.assert_array_equal(dets.cpu().numpy()[:, :4], boxes[ref])
+    np.testing.assert_array_equal(dets.cpu().numpy()[:, 4], scores[ref])
+
+
+def test_nms_offset_one_and_thresholds(cuda):
+    boxes = synth.random_boxes(700, 600, 1000, seed=3, clustered=True)
+    scores = _scores(700, 4)
+    for thr in (0.3, 0.5, 0.7):
+        for off in (0, 1):
+            _, keep = ops.nms(torch.from_numpy(boxes).to(cuda), torch.from_numpy(scores).to(cuda), thr, offset=off)
+            np.testing.assert_array_equal(keep.cpu().numpy(), oracle.nms_cpu(boxes, scores, thr, off))
+
+
+def test_nms_score_threshold_and_max_num(cuda):
+    boxes = synth.random_boxes(500, 600, 1000, seed=5, clustered=True)
+    scores = _scores(500, 6)
+    dets, keep = ops.nms(torch.from_numpy(boxes).to(cuda), torch.from_numpy(scores).to(cuda), 0.5,
+                         score_threshold=0.3, max_num=20)
+    m = scores > 0.3
+    ref = np.nonzero(m)[0][oracle.nms_cpu(boxes[m], scores[m], 0.5)][:20]
+    np.testing.assert_array_equal(keep.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize('n,nid', [(300, 5), (4693, 5), (12000, 80)])
+def test_batched_nms_matches_oracle(cuda, n, nid):
+    # n=12000 takes mmcv's split path (split_thr=10000) in the oracle
+    boxes = synth.random_boxes(n, 800, 1333, seed=n + 7, clustered=True)
+    scores = _scores(n, n + 8, dup=True)
+    ids = np.random.RandomState(n).randint(0, nid, n).astype(np.int64)
+    dets, keep = ops.batched_nms(torch.from_numpy(boxes).to(cuda), torch.from_numpy(scores).to(cuda),
+                                 torch.from_numpy(ids).to(cuda), dict(type='nms', iou_threshold=0.7))
+    rdets, rkeep = oracle.batched_nms(boxes, scores, ids, 0.7)
+    np.testing.assert_array_equal(keep.cpu().numpy(), rkeep)
+    np.testing.assert_array_equal(dets.cpu().numpy().view(np.uint32), rdets.view(np.uint32))
+
+
+def test_batched_nms_class_agnostic_and_empty(cuda):
+    boxes = synth.random_boxes(200, 300, 300, seed=1, clustered=True)
+    scores = _scores(200, 2)
+    ids = np.random.RandomState(0).randint(0, 3, 200).astype(np.int64)
+    _, keep = ops.batched_nms(torch.from_numpy(boxes).to(cuda), torch.from_numpy(scores).to(cuda),
+                              torch.from_numpy(ids).to(cuda),
+                              dict(type='nms', iou_threshold=0.5, class_agnostic=True))
+    np.testing.assert_array_equal(keep.cpu().numpy(), oracle.nms_cpu(boxes, scores, 0.5))
+    dets, keep = ops.batched_nms(torch.zeros((0, 4), device=cuda), torch.zeros((0,), device=cuda),
+                                 torch.zeros((0,), dtype=torch.long, device=cuda),
+                                 dict(type='nms', iou_threshold=0.5))
+    assert dets.shape == (0, 5) and keep.shape == (0,)
+
+
+def test_nms_rejects_cpu_tensors():
+    with pytest.raises(RuntimeError):
+        ops.nms(torch.zeros((4, 4)), torch.zeros((4,)), 0.5)

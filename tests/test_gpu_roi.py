@@ -1,0 +1,135 @@
+"""GPU parity: fused level-map + multi-level RoIAlign forward/backward vs the
+oracle's restated mmcv roi_align + SingleRoIExtractor.  Bar: level ids
+bit-exact; features and gradients <= 1e-5 relative (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from boosting_rcnn_b200 import ops
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _close(a, b, what):
+    scale = max(float(np.abs(b).max()), 1e-6)
+    err = float(np.abs(a - b).max())
+    assert err <= RTOL * scale, f'{what}: max abs err {err:.3e} vs scale {scale:.3e}'
+
+
+def _case(dev, batch, pad_hw, C, n_per_img, seed, clustered=False, channels_last=False,
+          extra_rois=None):
+    sizes = synth.featmap_sizes(*pad_hw)
+    scales = [1.0 / s for s in synth.STRIDES]
+    feats = synth.fpn_feats(batch, C, sizes, seed=seed)
+    rois = synth.random_rois(batch, n_per_img, pad_hw[0], pad_hw[1], seed=seed + 1,
+                             clustered=clustered)
+    if extra_rois is not None:
+        rois = np.concatenate([rois, extra_rois], 0).astype(np.float32)
+    tf = [torch.from_numpy(f).to(dev) for f in feats]
+    if channels_last:
+        tf = [f.contiguous(memory_format=torch.channels_last) for f in tf]
+    tf = [f.requires_grad_(True) for f in tf]
+    out, lv = ops.roi_extract(tf, torch.from_numpy(rois).to(dev), scales, 7, 0, True, 56,
+                              return_levels=True)
+    ref, rlv = oracle.roi_extract_forward(feats, rois, scales)
+    np.testing.assert_array_equal(lv.cpu().numpy().astype(np.int64), rlv)
+    _close(out.detach().cpu().numpy(), ref, 'roi features')
+    return tf, feats, rois, scales, out
+
+
+def test_roi_forward_small(cuda):
+    _case(cuda, 2, (256, 320), 64, 50, seed=0)
+
+
+def test_roi_forward_channels_last_input(cuda):
+    _case(cuda, 2, (256, 320), 256, 40, seed=1, channels_last=True)
+
+
+def test_roi_forward_edge_rois(cuda):
+    # degenerate, out-of-image, huge and level-threshold-straddling RoIs
+    ex = []
+    for s in (112.0, 224.0, 448.0, 896.0):
+        for d in (-1e-3, 0.0, 1e-3):
+            ex.append([0, 10, 10, 10 + s + d, 10 + s + d])
+    ex += [[1, 5, 5, 5, 5], [1, 0, 0, 320, 256], [0, 300, 250, 330, 270], [1, 100, 50, 90, 40],
+           [0, 2, 2, 318, 6], [1, -20, -20, 10, 10]]
+    _case(cuda, 2, (256, 320), 32, 10, seed=2, extra_rois=np.array(ex, dtype=np.float32))
+
+
+def test_roi_forward_full_size_utdac(cuda):
+    # configs[1] geometry: 1344x800 maps, 256 channels, 256 RoIs / image
+    _case(cuda, 2, (800, 1344), 256, 256, seed=3, clustered=True)
+
+
+def test_roi_levels_operator(cuda):
+    rois = synth.random_rois(1, 2000, 800, 1333, seed=9)
+    lv = ops.map_roi_levels(torch.from_numpy(rois).to(cuda), 5, 56)
+    np.testing.assert_array_equal(lv.cpu().numpy(), oracle.map_roi_levels(rois, 5, 56))
+    assert lv.dtype == torch.int64
+
+
+def test_roi_padding_rows_are_zero(cuda):
+    sizes = synth.featmap_sizes(128, 128)
+    feats = [torch.from_numpy(f).to(cuda) for f in synth.fpn_feats(1, 16, sizes, 0)]
+    rois = torch.tensor([[0, 4, 4, 60, 60], [-1, 0, 0, 0, 0]], dtype=torch.float32, device=cuda)
+    out, lv = ops.roi_extract(feats, rois, [1 / s for s in synth.STRIDES], return_levels=True)
+    assert out[1].abs().max().item() == 0 and lv[1].item() == -1 and out[0].abs().max().item() > 0
+
+
+@pytest.mark.parametrize('channels_last', [False, True])
+def test_roi_backward(cuda, channels_last):
+    tf, feats, rois, scales, out = _case(cuda, 2, (256, 320), 64, 120, seed=4, clustered=True,
+                                         channels_last=channels_last)
+    g = np.random.RandomState(5).normal(0, 1, out.shape).astype(np.float32)
+    out.backward(torch.from_numpy(g).to(cuda))
+    ref = oracle.roi_extract_backward(g, rois, [f.shape for f in feats], scales)
+    for l, (t, r) in enumerate(zip(tf, ref)):
+        assert t.grad is not None and t.grad.shape == r.shape  # every level gets a grad
+        _close(t.grad.cpu().numpy(), r, f'grad level {l}')
+
+
+def test_roi_backward_full_size_train_cfg(cuda):
+    # configs[2] geometry: 2 images, 512 RoIs each, 256 channels, clustered
+    tf, feats, rois, scales, out = _case(cuda, 2, (800, 1344), 256, 512, seed=6, clustered=True)
+    g = np.random.RandomState(7).normal(0, 1, out.shape).astype(np.float32)
+    out.backward(torch.from_numpy(g).to(cuda))
+    ref = oracle.roi_extract_backward(g, rois, [f.shape for f in feats], scales)
+    for l, (t, r) in enumerate(zip(tf, ref)):
+        _close(t.grad.cpu().numpy(), r, f'grad level {l}')
+
+
+def test_roi_backward_deterministic(cuda):
+    res = []
+    for _ in range(2):
+        tf, feats, rois, scales, out = _case(cuda, 1, (256, 320), 64, 400, seed=8, clustered=True)
+        g = np.random.RandomState(9).normal(0, 1, out.shape).astype(np.float32)
+        out.backward(torch.from_numpy(g).to(cuda))
+        res.append([t.grad.cpu().numpy() for t in tf])
+    for a, b in zip(*res):
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_roi_align_module_single_level(cuda):
+    feat = synth.fpn_feats(2, 32, [(50, 84)], seed=10)[0]
+    rois = synth.random_rois(2, 30, 800, 1344, seed=11)
+    layer = ops.RoIAlign(7, spatial_scale=1 / 16, sampling_ratio=0)
+    assert layer.output_size == (7, 7)
+    out = layer(torch.from_numpy(feat).to(cuda), torch.from_numpy(rois).to(cuda))
+    ref = oracle.roi_align_forward(feat, rois, 7, 1 / 16)
+    _close(out.cpu().numpy(), ref, 'single-level roi_align')
+    out2 = ops.roi_align(torch.from_numpy(feat).to(cuda), torch.from_numpy(rois).to(cuda), 7, 1 / 16,
+                         sampling_ratio=2)
+    _close(out2.cpu().numpy(), oracle.roi_align_forward(feat, rois, 7, 1 / 16, sampling_ratio=2),
+           'sampling_ratio=2')
+
+
+def test_layout_helpers_roundtrip(cuda):
+    x = torch.randn(3, 20, 13, 21, device=cuda)
+    y = ops.to_nhwc(x)
+    assert y.shape == (3, 13, 21, 20) and y.is_contiguous()
+    assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(ops.nhwc_to_nchw(y), x)
