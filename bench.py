@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py — RoI-path images/s of the Boosting R-CNN proposal-to-RoI hot path.
+
+Workload (BASELINE.json configs[1]): boosting_rcnn_r50_pafpn_1x_utdac inference,
+16 synthetic 1333x800 images per GPU, random-init head weights.  One "step" =
+RPN conv outputs + FPN maps  ->  proposals (score, top-k, decode, NMS)
+-> RoI features (level map + RoIAlign) -> 2-fc head (torch/cuBLAS, fp32)
+-> score fusion + per-class decode + class NMS -> detections, for the batch.
+
+  python bench.py [--gpus N --steps K --warmup W]      # this repo (sm_100a kernels)
+  python bench.py --impl reference [...]               # CPU reference arm (oracle)
+
+Prints ONE JSON line (see README/DESIGN.md for the keys).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'tests')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+STRIDES = (8, 16, 32, 64, 128)
+WORKLOAD = 'boosting_rcnn_r50_pafpn_1x_utdac inference, 16 synthetic 1333x800 images per GPU'
+SCALE_FACTOR = (1.6662, 1.6667, 1.6662, 1.6667)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=16, help='images per GPU per step')
+    ap.add_argument('--cfg', default='utdac', choices=['utdac', 'coco', 'voc'])
+    ap.add_argument('--cpu-images', type=int, default=0,
+                    help='images in the CPU-baseline sample (0: one per host thread, <= 16)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------
+# synthetic inputs, generated on the host, seeded per rank
+# ----------------------------------------------------------------------------
+def make_inputs(batch, pad_hw, num_anchors, channels, seed, pin):
+    g = torch.Generator().manual_seed(seed)
+    sizes = [(-(-pad_hw[0] // s), -(-pad_hw[1] // s)) for s in STRIDES]
+
+    def rnd(shape, std):
+        t = torch.empty(shape, dtype=torch.float32)
+        t.normal_(0, std, generator=g)
+        return t.pin_memory() if pin else t
+
+    feats = [rnd((batch, channels, h, w), 1.0) for (h, w) in sizes]
+    cls = [rnd((batch, num_anchors, h, w), 1.5) for (h, w) in sizes]
+    box = [rnd((batch, 4 * num_anchors, h, w), 0.3) for (h, w) in sizes]
+    iou = [rnd((batch, num_anchors, h, w), 1.5) for (h, w) in sizes]
+    return sizes, feats, cls, box, iou
+
+
+def img_metas_for(batch, geom):
+    return [dict(img_shape=geom['img_shape'], pad_shape=geom['pad_shape'],
+                 scale_factor=np.array(SCALE_FACTOR, dtype=np.float32)) for _ in range(batch)]
+
+
+# ----------------------------------------------------------------------------
+# CPU reference arm: the oracle (restated mmdet + mmcv CPU ops) on host cores
+# ----------------------------------------------------------------------------
+class CpuReference:
+    """Same step on the host: oracle C restatement per image, one image per
+    thread (ctypes releases the GIL), the 2-fc head on torch CPU."""
+
+    def __init__(self, rpn_head, roi_head, model, geom, threads):
+        from oracle import oracle
+        self.o = oracle
+        oracle.lib()
+        self.base = rpn_head.anchor_generator.base_anchor_table().numpy()
+        self.test_rpn = model['test_cfg']['rpn']
+        self.test_rcnn = model['test_cfg']['rcnn']
+        self.geom = geom
+        self.nc = roi_head.bbox_head.num_classes
+        self.head = roi_head.bbox_head
+        self.cpu_head = None
+        self.threads = threads
+
+    def _head_cpu(self):
+        if self.cpu_head is None:
+            import copy
+            self.cpu_head = copy.deepcopy(self.head).cpu().eval()
+        return self.cpu_head
+
+    def one_image(self, feats, cls, box, iou):
+        o = self.o
+        hw = self.geom['img_shape'][:2]
+        props = o.rpn_get_bboxes_single(cls, box, iou, self.base, STRIDES, hw,
+                                        self.test_rpn['nms_pre'], self.test_rpn['max_per_img'],
+                                        self.test_rpn['nms']['iou_threshold'],
+                                        self.test_rpn['min_bbox_size'])
+        n = props.shape[0]
+        rois = np.concatenate([np.zeros((n, 1), np.float32), props[:, :4]], 1)
+        rf, _ = o.roi_extract_forward([f[None] for f in feats], rois, [1.0 / s for s in STRIDES])
+        with torch.no_grad():
+            torch.set_num_threads(1)
+            cs, bp = self._head_cpu()(torch.from_numpy(rf))
+        fused = o.fuse_scores(cs.numpy(), props[:, 4])
+        return o.rcnn_get_bboxes_single(rois, fused, bp.numpy(), hw, SCALE_FACTOR, self.nc,
+                                        self.test_rcnn['score_thr'],
+                                        self.test_rcnn['nms']['iou_threshold'],
+                                        self.test_rcnn['max_per_img'], rescale=True)
+
+    def run(self, feats, cls, box, iou, n_images):
+        from concurrent.futures import ThreadPoolExecutor
+        self._head_cpu()
+        fn = [[f[b].numpy() for f in feats] for b in range(n_images)]
+        cn = [[c[b].numpy() for c in cls] for b in range(n_images)]
+        bn = [[c[b].numpy() for c in box] for b in range(n_images)]
+        un = [[c[b].numpy() for c in iou] for b in range(n_images)]
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=self.threads) as ex:
+            res = list(ex.map(lambda i: self.one_image(fn[i], cn[i], bn[i], un[i]), range(n_images)))
+        return time.perf_counter() - t0, res
+
+
+# ----------------------------------------------------------------------------
+# clocks sampling during the timed region (B200_PROFILING.md)
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--id={gpu_index}', f'--query-gpu={self.Q}',
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(',')]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=max(mx) if mx else None, samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+def roi_footprint_bytes(rois, sizes, channels, finest=56.0):
+    """Algorithmic feature bytes of RoIAlign: per RoI the
+    (floor..ceil)+tap footprint on its level, x C x 4 B."""
+    r = rois[rois[:, 0] >= 0]
+    w, h = r[:, 3] - r[:, 1], r[:, 4] - r[:, 2]
+    scale = np.sqrt(w * h)
+    lvl = np.clip(np.floor(np.log2(scale / finest + 1e-6)), 0, len(sizes) - 1).astype(int)
+    tot = 0
+    for l, (H, W) in enumerate(sizes):
+        m = lvl == l
+        s = 1.0 / STRIDES[l]
+        fw = np.minimum(np.ceil(r[m, 3] * s) - np.floor(r[m, 1] * s) + 2, W)
+        fh = np.minimum(np.ceil(r[m, 4] * s) - np.floor(r[m, 2] * s) + 2, H)
+        tot += float((fw * fh).sum()) * channels * 4
+    return tot
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if world > 1 and args.impl == 'reference' and rank != 0:
+        return 0  # the CPU arm runs on rank 0 only
+
+    from boosting_rcnn_b200 import configs
+    geom = configs.IMAGE_GEOMETRY[args.cfg]
+    pad_hw = geom['pad_shape'][:2]
+    B = args.batch
+    torch.manual_seed(0)
+    rpn_head, roi_head, model = configs.build_hot_path(args.cfg)
+    A, C = rpn_head.num_anchors, roi_head.bbox_roi_extractor.out_channels
+    threads = os.cpu_count() or 1
+    base_cfg = dict(workload=WORKLOAD if args.cfg == 'utdac' else f'{args.cfg} inference',
+                    images_per_gpu=B, rpn=model['test_cfg']['rpn'], rcnn=model['test_cfg']['rcnn'],
+                    head='2-fc shared head on torch/cuBLAS fp32 (TF32 off)',
+                    l2_policy='per-step inputs (>=440 MB/GPU) exceed the 126 MB L2',
+                    parallelism=f'image-sharded x{world}, no data-path collective')
+
+    # ------------------------------------------------------------------ CPU arm
+    if args.impl == 'reference':
+        n_img = args.cpu_images or min(threads, B)
+        sizes, feats, cls, box, iou = make_inputs(n_img, pad_hw, A, C, seed=1234, pin=False)
+        ref = CpuReference(rpn_head, roi_head, model, geom, threads)
+        for _ in range(max(args.warmup, 0)):
+            ref.run(feats, cls, box, iou, min(n_img, threads))
+        t = 0.0
+        for _ in range(args.steps):
+            dt, _ = ref.run(feats, cls, box, iou, n_img)
+            t += dt
+        val = n_img * args.steps / t
+        sample = f'{n_img} images/step x {args.steps} steps, one image per thread'
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'RoI-path images/s @1333x800', 'value': val,
+            'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': base_cfg,
+            'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                             'sample': sample},
+            'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0}}))
+        return 0
+
+    # ------------------------------------------------------------------ GPU arm
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    from boosting_rcnn_b200 import _lib, ops
+    from boosting_rcnn_b200.registry import ConfigDict
+    from boosting_rcnn_b200.roi_head import padded_rois
+    lib = _lib.load()
+    rpn_head, roi_head = rpn_head.to(dev).eval(), roi_head.to(dev).eval()
+    sizes, h_feats, h_cls, h_box, h_iou = make_inputs(B, pad_hw, A, C, seed=1234 + rank, pin=True)
+    metas = img_metas_for(B, geom)
+    to_dev = lambda ts: [t.to(dev, non_blocking=True) for t in ts]
+    d_feats, d_cls, d_box, d_iou = to_dev(h_feats), to_dev(h_cls), to_dev(h_box), to_dev(h_iou)
+    d_feats_cl = [f.contiguous(memory_format=torch.channels_last) for f in d_feats]
+    torch.cuda.synchronize()
+    test_rcnn = model['test_cfg']['rcnn']
+
+    @torch.no_grad()
+    def step(feats, cls, box, iou):
+        props = rpn_head.get_bboxes_padded(cls, box, iou, metas)
+        return roi_head.simple_test_bboxes_padded(feats, metas, props, test_rcnn, rescale=True)
+
+    @torch.no_grad()
+    def step_e2e():
+        det, lab, num = step(to_dev(h_feats), to_dev(h_cls), to_dev(h_box), to_dev(h_iou))
+        return det.cpu(), lab.cpu(), num.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.brcnn_launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.brcnn_launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    W, K = max(args.warmup, 3), args.steps
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, launches = timed(lambda: step(d_feats, d_cls, d_box, d_iou), K, W)
+    clocks = sampler.stop() if sampler else None
+    ms_cl, _ = timed(lambda: step(d_feats_cl, d_cls, d_box, d_iou), K, W)
+    ms_e2e, _ = timed(step_e2e, max(K // 3, 3), 3)
+    k_e2e = max(K // 3, 3)
+
+    # -------------------------------------------------- per-stage device times
+    stage_ms, roof = {}, None
+    if rank == 0:
+        with torch.no_grad():
+            props = rpn_head.get_bboxes_padded(d_cls, d_box, d_iou, metas)
+            rois = padded_rois(props)
+            scales = [1.0 / s for s in STRIDES]
+            nhwc = [ops.to_nhwc(f) for f in d_feats]
+            feats_cl = [t.permute(0, 3, 1, 2) for t in nhwc]
+            rf = ops.roi_extract(feats_cl, rois, scales, 7)
+            cs, bp = roi_head.bbox_head(rf)
+            hw, sf = roi_head._img_consts(metas, dev)
+            rp = roi_head.bbox_head.rcnn_params(B, props.boxes.size(1), ConfigDict(test_rcnn), True, True)
+            prior = props.boxes[..., 4].reshape(-1).contiguous()
+            stages = {
+                'rpn_get_bboxes': lambda: rpn_head.get_bboxes_padded(d_cls, d_box, d_iou, metas),
+                'nchw_to_nhwc_x5': lambda: [ops.to_nhwc(f) for f in d_feats],
+                'roi_align_fwd': lambda: ops.roi_extract(feats_cl, rois, scales, 7),
+                'fc_head_cublas': lambda: roi_head.bbox_head(rf),
+                'rcnn_get_bboxes': lambda: ops.rcnn_get_bboxes(rp, rois, prior, props.num, cs, bp,
+                                                               hw, sf),
+            }
+            for name, fn in stages.items():
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                evs = []
+                for _ in range(10):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    fn()
+                    b.record()
+                    evs.append((a, b))
+                torch.cuda.synchronize()
+                stage_ms[name] = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        else:
+            peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+        rois_h = rois.cpu().numpy()
+        n_live = int((rois_h[:, 0] >= 0).sum())
+        feat_bytes = sum(f.numel() * 4 for f in d_feats)
+        out_bytes = rois_h.shape[0] * C * 49 * 4
+        fp = roi_footprint_bytes(rois_h, sizes, C)
+        kernels = {
+            'roi_align_fwd_kernel': (out_bytes + min(fp, feat_bytes), stage_ms['roi_align_fwd']),
+            'transpose_kernel(nchw_to_nhwc)': (2 * feat_bytes, stage_ms['nchw_to_nhwc_x5'] / 5 * 1),
+        }
+        # dominant kernel of OUR launches by total time in a step
+        t_roi, t_tr = stage_ms['roi_align_fwd'], stage_ms['nchw_to_nhwc_x5']
+        if t_tr >= t_roi:
+            ach = 2 * feat_bytes / (t_tr * 1e-3) / 1e9
+            roof = dict(kernel='transpose_kernel (5 launches, one per pyramid level; aggregate)',
+                        bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak,
+                        traffic=None, peak_source=peak_src,
+                        algorithmic_bytes_per_step=2 * feat_bytes, ms_per_step=t_tr)
+        else:
+            ach = kernels['roi_align_fwd_kernel'][0] / (t_roi * 1e-3) / 1e9
+            roof = dict(kernel='roi_align_fwd_kernel', bound='hbm', achieved=ach, peak=peak,
+                        unit='GB/s', frac=ach / peak, traffic=None, peak_source=peak_src,
+                        algorithmic_bytes_per_launch=kernels['roi_align_fwd_kernel'][0],
+                        ms_per_launch=t_roi, live_rois=n_live)
+        roof['other_kernels'] = {
+            'roi_align_fwd_kernel': dict(
+                achieved=kernels['roi_align_fwd_kernel'][0] / (t_roi * 1e-3) / 1e9,
+                frac=kernels['roi_align_fwd_kernel'][0] / (t_roi * 1e-3) / 1e9 / peak,
+                algorithmic_bytes=kernels['roi_align_fwd_kernel'][0], ms=t_roi),
+            'transpose_kernel_x5': dict(achieved=2 * feat_bytes / (t_tr * 1e-3) / 1e9,
+                                        frac=2 * feat_bytes / (t_tr * 1e-3) / 1e9 / peak,
+                                        algorithmic_bytes=2 * feat_bytes, ms=t_tr)}
+
+    # ------------------------------------------------------------ CPU baseline
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        n_img = args.cpu_images or min(threads, B)
+        ref = CpuReference(rpn_head, roi_head, model, geom, threads)
+        hf = [f[:n_img] for f in h_feats]
+        ref.run(hf, [c[:n_img] for c in h_cls], [c[:n_img] for c in h_box],
+                [c[:n_img] for c in h_iou], min(2, n_img))  # warm-up
+        reps, t = 0, 0.0
+        while t < 8.0 and reps < 20:
+            dt, _ = ref.run(hf, [c[:n_img] for c in h_cls], [c[:n_img] for c in h_box],
+                            [c[:n_img] for c in h_iou], n_img)
+            t += dt
+            reps += 1
+        cpu = {'value': n_img * reps / t, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+               'sample': f'{n_img} images x {reps} passes of the same workload, one image per '
+                         f'host thread (oracle C restatement + torch CPU 2-fc head)'}
+
+    if rank == 0:
+        h2d = sum(t.numel() * 4 for ts in (h_feats, h_cls, h_box, h_iou) for t in ts)
+        mp = test_rcnn['max_per_img']
+        d2h = B * mp * 5 * 4 + B * mp * 8 + B * 4
+        out = {
+            'metric': 'RoI-path images/s @1333x800', 'value': B * world * K / (ms * 1e-3),
+            'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': dict(base_cfg, feat_layout='NCHW-contiguous FPN maps in (reference neck '
+                           'layout); NCHW->NHWC conversion kernels are inside the timed step'),
+            'value_channels_last_feats': B * world * K / (ms_cl * 1e-3),
+            'e2e': {'value': B * world * k_e2e / (ms_e2e * 1e-3), 'unit': 'images/s',
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / k_e2e},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof,
+            'stages_ms': stage_ms, 'cpu_baseline': cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -84,6 +84,9 @@ SIGNATURES = {
     'brcnn_rpn_get_bboxes': (c_int32, [
         POINTER(RpnParams), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'brcnn_delta2bbox': (c_int32, [c_void_p, c_void_p, c_int32, c_int32,
+                                   POINTER(c_float), POINTER(c_float), c_float,
+                                   c_float, c_float, c_void_p, c_void_p]),
     'brcnn_nms_workspace_bytes': (c_size_t, [c_int32]),
     'brcnn_batched_nms': (c_int32, [
         c_void_p, c_void_p, c_void_p, c_int32, c_float, c_int32, c_void_p,

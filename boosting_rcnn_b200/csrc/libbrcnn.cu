@@ -102,6 +102,22 @@ __global__ void nms_finalize_kernel(const float* __restrict__ boxes,
   }
 }
 
+struct DecodeArgs { float means[4], stds[4], max_ratio, max_h, max_w; int n, ncls; };
+__global__ void delta2bbox_kernel(const __grid_constant__ DecodeArgs a,
+                                  const float* __restrict__ rois,
+                                  const float* __restrict__ deltas,
+                                  float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n * a.ncls) return;
+  const int r = i / a.ncls;
+  const float4 q = reinterpret_cast<const float4*>(rois)[r];
+  const float4 d = reinterpret_cast<const float4*>(deltas)[i];
+  Box4 rb; rb.x1 = q.x; rb.y1 = q.y; rb.x2 = q.z; rb.y2 = q.w;
+  const Box4 o = delta2bbox_one(rb, d.x, d.y, d.z, d.w, a.means, a.stds, a.max_ratio,
+                                a.max_h >= 0.f, a.max_w, a.max_h);
+  reinterpret_cast<float4*>(out)[i] = make_float4(o.x1, o.y1, o.x2, o.y2);
+}
+
 struct NmsWs {
   size_t sorted_boxes, sorted_key, order, count, maxc, mask, kept_pos, kept_count, total;
 };
@@ -304,6 +320,24 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
   nms_merge_kernel<RpnMergeEpilogue><<<p->batch, 256, 0, stream>>>(
       kept_pos, kept_key, kept_count, p->num_levels, d.keep_cap, p->max_per_img,
       num_proposals, ep);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+int brcnn_delta2bbox(const float* rois, const float* deltas, int32_t n, int32_t ncls,
+                     const float* means_host, const float* stds_host, float max_ratio,
+                     float max_h, float max_w, float* out, brcnn_stream_t stream_) {
+  if (n < 0 || ncls <= 0 || !means_host || !stds_host) return BRCNN_ERR_ARG;
+  if (n == 0) return BRCNN_OK;
+  if (!rois || !deltas || !out) return BRCNN_ERR_ARG;
+  DecodeArgs a;
+  for (int i = 0; i < 4; ++i) { a.means[i] = means_host[i]; a.stds[i] = stds_host[i]; }
+  a.max_ratio = max_ratio; a.max_h = max_h; a.max_w = max_w; a.n = n; a.ncls = ncls;
+  const long long tot = (long long)n * ncls;
+  if (tot > 0x7fffffff) return BRCNN_ERR_UNSUPPORTED;
+  delta2bbox_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+      a, rois, deltas, out);
   g_launch_count_add(1);
   BRCNN_CUDA_CHECK_LAST();
   return BRCNN_OK;

@@ -108,6 +108,29 @@ def rpn_get_bboxes(p, cls_scores, bbox_preds, iou_preds, base_anchors, img_hw,
     return proposals, num
 
 
+def delta2bbox(rois, deltas, means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.),
+               max_shape=None, wh_ratio_clip=16 / 1000, clip_border=True):
+    """mmdet delta2bbox for (N,4) rois and (N,4*k) deltas (one image)."""
+    import ctypes
+    rois, deltas = _f32c(rois, 'rois'), _f32c(deltas, 'deltas')
+    n = rois.size(0)
+    assert rois.dim() == 2 and rois.size(1) == 4 and deltas.size(0) == n
+    assert deltas.size(1) % 4 == 0
+    out = torch.empty_like(deltas)
+    if n == 0:
+        return out
+    mh, mw = -1.0, -1.0
+    if clip_border and max_shape is not None:
+        mh, mw = float(max_shape[0]), float(max_shape[1])
+    m = (ctypes.c_float * 4)(*[float(v) for v in means])
+    s = (ctypes.c_float * 4)(*[float(v) for v in stds])
+    check(_lib.load().brcnn_delta2bbox(rois.data_ptr(), deltas.data_ptr(), n,
+                                       deltas.size(1) // 4, m, s,
+                                       max_ratio_f32(wh_ratio_clip), mh, mw,
+                                       out.data_ptr(), _stream()), 'brcnn_delta2bbox')
+    return out
+
+
 # --------------------------------------------------------------------------
 # mmcv.ops.nms / batched_nms mirrors
 # --------------------------------------------------------------------------

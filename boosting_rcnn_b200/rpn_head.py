@@ -1,0 +1,224 @@
+"""ATSSRPNHead ("RetinaRPN") — drop-in for
+mmdet/models/dense_heads/atss_rpn_head.py:109-783.
+
+What is B200-native here: ``get_bboxes`` (:466-503, :688-760).  One
+``brcnn_rpn_get_bboxes`` call handles the whole batch and every pyramid level
+(score, per-level top-k, anchor + delta decode, size filter, batched NMS,
+top ``max_per_img``) — no Python loop over images/levels, no host sync.
+The conv tower (4x conv3x3+GN+ReLU, rpn_cls/rpn_reg/rpn_iou, per-level Scale)
+stays on torch/cuDNN as the north star says; parameter names match the
+reference so its checkpoints load (``rpn_convs.N.conv/gn``, ``rpn_cls``,
+``rpn_reg``, ``rpn_iou``, ``scales.N.scale``).
+
+Not ported: the RPN loss (`loss`, `loss_single`,
+`get_targets`, :299-464,505-686).
+"""
+import math
+from collections import namedtuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .registry import (HEADS, ConfigDict, build_anchor_generator, build_bbox_coder,
+                       build_loss)
+
+PaddedProposals = namedtuple('PaddedProposals', ['boxes', 'num'])
+PaddedProposals.__doc__ = """Fixed-capacity proposal batch that stays on the
+device: ``boxes`` (B, max_per_img, 5) zero padded [x1,y1,x2,y2,prior],
+``num`` (B,) int32.  ``to_list()``-style conversion is ``unpad_proposals``."""
+
+
+def unpad_proposals(padded):
+    """-> list of (n_b, 5) tensors like the reference (one host sync)."""
+    num = padded.num.tolist()
+    return [padded.boxes[b, :n] for b, n in enumerate(num)]
+
+
+class Scale(nn.Module):
+    """mmcv.cnn.Scale: one learnable scalar named ``scale``."""
+
+    def __init__(self, scale=1.0):
+        super().__init__()
+        self.scale = nn.Parameter(torch.tensor(scale, dtype=torch.float))
+
+    def forward(self, x):
+        return x * self.scale
+
+
+class ConvModule(nn.Module):
+    """conv -> norm -> ReLU with mmcv.cnn.ConvModule's sub-module names
+    (``conv``, ``gn``/``bn``, ``activate``)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0,
+                 conv_cfg=None, norm_cfg=None, act=True):
+        super().__init__()
+        if conv_cfg not in (None, dict(type='Conv2d')):
+            raise NotImplementedError(f'conv_cfg {conv_cfg} is outside the hot path')
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride,
+                              padding=padding, bias=norm_cfg is None)
+        self.norm_name = None
+        if norm_cfg is not None:
+            kind = norm_cfg.get('type')
+            if kind == 'GN':
+                self.norm_name = 'gn'
+                self.add_module('gn', nn.GroupNorm(norm_cfg.get('num_groups', 32), out_channels))
+            elif kind == 'BN':
+                self.norm_name = 'bn'
+                self.add_module('bn', nn.BatchNorm2d(out_channels))
+            else:
+                raise NotImplementedError(f'norm {kind}')
+            for prm in getattr(self, self.norm_name).parameters():
+                prm.requires_grad = norm_cfg.get('requires_grad', True)
+        self.activate = nn.ReLU(inplace=True) if act else None
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.norm_name is not None:
+            x = getattr(self, self.norm_name)(x)
+        if self.activate is not None:
+            x = self.activate(x)
+        return x
+
+
+@HEADS.register_module()
+class ATSSRPNHead(nn.Module):
+
+    def __init__(self, in_channels, num_classes=1, feat_channels=256, stacked_convs=4,
+                 conv_cfg=None, gamma=1, atss=False, bridge=False, last_conv='norm',
+                 aug_reg_loss=None,
+                 norm_cfg=dict(type='GN', num_groups=32, requires_grad=True),
+                 anchor_generator=dict(type='AnchorGenerator', scales=[8, 16, 32],
+                                       ratios=[0.5, 1.0, 2.0], strides=[4, 8, 16, 32, 64]),
+                 bbox_coder=dict(type='DeltaXYWHBBoxCoder', clip_border=True,
+                                 target_means=(.0, .0, .0, .0),
+                                 target_stds=(1.0, 1.0, 1.0, 1.0)),
+                 reg_decoded_bbox=False,
+                 loss_cls=dict(type='CrossEntropyLoss', use_sigmoid=True, loss_weight=1.0),
+                 loss_bbox=dict(type='SmoothL1Loss', beta=1.0 / 9.0, loss_weight=1.0),
+                 loss_centerness=dict(type='CrossEntropyLoss', use_sigmoid=True,
+                                      loss_weight=0.5),
+                 train_cfg=None, test_cfg=None, init_cfg=None, num_convs=1):
+        super().__init__()
+        if last_conv != 'norm':
+            raise NotImplementedError("last_conv='dcn'/'aspp' is not used by the named configs")
+        if bridge:
+            raise NotImplementedError('bridge=True is not used by the named configs')
+        self.in_channels, self.num_classes, self.feat_channels = in_channels, num_classes, feat_channels
+        self.stacked_convs, self.conv_cfg, self.norm_cfg = stacked_convs, conv_cfg, norm_cfg
+        self.gamma, self.atss, self.bridge, self.last_conv = gamma, atss, bridge, last_conv
+        self.use_sigmoid_cls = loss_cls.get('use_sigmoid', False)
+        if not self.use_sigmoid_cls:
+            raise NotImplementedError('softmax RPN scores are not used by the named configs')
+        self.cls_out_channels = num_classes
+        self.reg_decoded_bbox = reg_decoded_bbox
+        self.bbox_coder = build_bbox_coder(bbox_coder)
+        self.loss_cls = build_loss(loss_cls)
+        self.loss_bbox = build_loss(loss_bbox)
+        self.loss_centerness = build_loss(loss_centerness)
+        self.with_aug_loss = aug_reg_loss is not None
+        if self.with_aug_loss:
+            self.aug_loss = build_loss(aug_reg_loss)
+        self.train_cfg = ConfigDict(train_cfg) if train_cfg is not None else None
+        self.test_cfg = ConfigDict(test_cfg) if test_cfg is not None else None
+        self.anchor_generator = build_anchor_generator(anchor_generator)
+        self.num_anchors = self.anchor_generator.num_base_anchors[0]
+        self._init_layers()
+        self.init_weights()
+        self._const_cache = {}
+
+    # ---------------------------------------------------------------- layers
+    def _init_layers(self):
+        self.rpn_convs = nn.ModuleList()
+        for i in range(self.stacked_convs):
+            chn = self.in_channels if i == 0 else self.feat_channels
+            self.rpn_convs.append(ConvModule(chn, self.feat_channels, 3, stride=1, padding=1,
+                                             conv_cfg=self.conv_cfg, norm_cfg=self.norm_cfg))
+        self.rpn_cls = nn.Conv2d(self.feat_channels, self.num_anchors * self.cls_out_channels,
+                                 3, padding=1)
+        self.rpn_reg = nn.Conv2d(self.feat_channels, self.num_anchors * 4, 3, padding=1)
+        self.rpn_iou = nn.Conv2d(self.feat_channels, self.num_anchors * 1, 3, padding=1)
+        self.scales = nn.ModuleList([Scale(1.0) for _ in self.anchor_generator.strides])
+
+    def init_weights(self):
+        """init_cfg of atss_rpn_head.py:123-131: Normal(std=.01) on every
+        Conv2d, rpn_cls bias from bias_prob=0.01."""
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.normal_(m.weight, 0, 0.01)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+        nn.init.constant_(self.rpn_cls.bias, float(-math.log((1 - 0.01) / 0.01)))
+
+    def forward_single(self, x, scale):
+        for conv in self.rpn_convs:
+            x = conv(x)
+        rpn_cls_score = self.rpn_cls(x)
+        rpn_bbox_pred = scale(self.rpn_reg(x)).float()
+        rpn_iou_pred = self.rpn_iou(x)
+        return rpn_cls_score, rpn_bbox_pred, rpn_iou_pred
+
+    def forward(self, feats):
+        outs = [self.forward_single(x, s) for x, s in zip(feats, self.scales)]
+        return tuple(map(list, zip(*outs)))
+
+    # ------------------------------------------------------------- proposals
+    def _constants(self, device, img_shapes):
+        key = (str(device), tuple(img_shapes))
+        c = self._const_cache.get(key)
+        if c is None:
+            base = self.anchor_generator.base_anchor_table().to(device)
+            hw = torch.tensor([[s[0], s[1]] for s in img_shapes], dtype=torch.float32).to(device)
+            c = self._const_cache[key] = (base, hw)
+            if len(self._const_cache) > 64:
+                self._const_cache.pop(next(iter(self._const_cache)))
+        return c
+
+    def get_bboxes_padded(self, cls_scores, bbox_preds, iou_preds, img_metas, cfg=None):
+        """Whole-batch proposal generation; results stay on the device."""
+        assert len(cls_scores) == len(bbox_preds) == len(iou_preds)
+        cfg = self.test_cfg if cfg is None else ConfigDict(cfg)
+        nms = cfg.nms
+        if nms.get('type', 'nms') != 'nms':
+            raise NotImplementedError(f"nms type {nms.get('type')!r} is outside the hot path")
+        B = cls_scores[0].size(0)
+        assert len(img_metas) == B
+        sizes = [tuple(t.shape[-2:]) for t in cls_scores]
+        img_shapes = [tuple(m['img_shape'][:2]) for m in img_metas]
+        base, hw = self._constants(cls_scores[0].device, img_shapes)
+        p = ops.make_rpn_params(B, sizes, self.anchor_generator.strides, self.num_anchors,
+                                cfg.nms_pre, cfg.max_per_img, nms.iou_threshold,
+                                cfg.min_bbox_size, self.bbox_coder.means, self.bbox_coder.stds)
+        boxes, num = ops.rpn_get_bboxes(p, [t.detach() for t in cls_scores],
+                                        [t.detach() for t in bbox_preds],
+                                        [t.detach() for t in iou_preds], base, hw)
+        return PaddedProposals(boxes, num)
+
+    def get_bboxes(self, cls_scores, bbox_preds, iou_preds, img_metas, cfg=None,
+                   rescale=False, with_nms=True):
+        """Reference signature (:466-503): list of (n,5) proposals per image.
+        ``rescale`` is accepted and ignored exactly like the reference."""
+        assert with_nms, '``with_nms`` in RPNHead should always True'
+        return unpad_proposals(self.get_bboxes_padded(cls_scores, bbox_preds, iou_preds,
+                                                      img_metas, cfg))
+
+    def simple_test_rpn(self, x, img_metas, padded=False):
+        cls_scores, bbox_preds, iou_preds = self(x)
+        if padded:
+            return self.get_bboxes_padded(cls_scores, bbox_preds, iou_preds, img_metas)
+        return self.get_bboxes(cls_scores, bbox_preds, iou_preds, img_metas)
+
+    def loss(self, *args, **kwargs):
+        raise NotImplementedError('the RPN loss is outside the ported hot path '
+                                  '(SURVEY.md §8f rank 2)')
+
+    def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None,
+                      proposal_cfg=None, **kwargs):
+        """Proposal half of atss_rpn_head.py:270-294.  The loss half is not
+        ported; an empty loss dict is returned so the R-CNN stage can be
+        trained/benchmarked on B200-generated proposals."""
+        outs = self(x)
+        losses = dict()
+        if proposal_cfg is None:
+            return losses
+        return losses, self.get_bboxes(*outs, img_metas, cfg=proposal_cfg)

@@ -98,6 +98,15 @@ int brcnn_rpn_get_bboxes(
     int32_t* num_proposals,              /* (B)                              */
     void* workspace, size_t workspace_bytes, brcnn_stream_t stream);
 
+/* delta2bbox as a standalone operator: DeltaXYWHBBoxCoder.decode
+ * (mmdet/core/bbox/coder/delta_xywh_bbox_coder.py:63-95,144-272).
+ * rois (n,4), deltas (n,4*ncls) -> out (n,4*ncls); max_h < 0: no clipping
+ * (max_shape=None).  means/stds are HOST arrays of 4 floats.               */
+int brcnn_delta2bbox(const float* rois, const float* deltas, int32_t n,
+                     int32_t ncls, const float* means_host,
+                     const float* stds_host, float max_ratio, float max_h,
+                     float max_w, float* out, brcnn_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * (2) NMS operators — stand-ins for mmcv `_ext.nms` and the Python wrappers
  * mmcv.ops.nms / mmcv.ops.batched_nms (call sites atss_rpn_head.py:756,
