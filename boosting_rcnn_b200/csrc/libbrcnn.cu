@@ -129,7 +129,7 @@ static NmsWs nms_ws(int K) {
   w.order = o;        o = align256(o + (size_t)K * 4);
   w.count = o;        o = align256(o + 4);
   w.maxc = o;         o = align256(o + 4);
-  w.mask = o;         o = align256(o + (size_t)K * W * 8);
+  w.mask = o;         o = align256(o + (nms_use_fused(K) ? 0 : (size_t)K * W * 8));
   w.kept_pos = o;     o = align256(o + (size_t)K * 4);
   w.kept_count = o;   o = align256(o + 4);
   w.total = o;
@@ -182,7 +182,7 @@ static int rpn_ws(const brcnn_rpn_params* p, RpnWsInternal* w) {
   w->pub.kept_pos = o;   o = align256(o + S * d.keep_cap * 4);
   w->pub.kept_count = o; o = align256(o + S * 4);
   w->kept_key = o;       o = align256(o + S * d.keep_cap * 8);
-  w->mask = o;           o = align256(o + S * d.Kc * d.W * 8);
+  w->mask = o;           o = align256(o + (nms_use_fused(d.Kc) ? 0 : S * d.Kc * d.W * 8));
   w->pub.total_bytes = (int64_t)o;
   return BRCNN_OK;
 }
@@ -214,7 +214,7 @@ static int rcnn_ws(const brcnn_rcnn_params* p, RcnnWsInternal* w) {
   w->pub.kept_pos = o;   o = align256(o + B * C * w->keep_cap * 4);
   w->pub.kept_count = o; o = align256(o + B * C * 4);
   w->kept_key = o;       o = align256(o + B * C * w->keep_cap * 8);
-  w->mask = o;           o = align256(o + B * C * Rc * w->W * 8);
+  w->mask = o;           o = align256(o + (nms_use_fused((int)Rc) ? 0 : B * C * Rc * w->W * 8));
   w->pub.total_bytes = (int64_t)o;
   return BRCNN_OK;
 }
@@ -303,7 +303,9 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
   e = cudaFuncSetAttribute(rpn_select_decode_kernel,
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid(RPN_CS, p->num_levels, p->batch);
+  // clusters are scheduled in (x, y, z) order: level-major, so the 16x heavier
+  // level-0 clusters start first instead of being spread over later waves
+  dim3 grid(RPN_CS, p->batch, p->num_levels);
   rpn_select_decode_kernel<<<grid, RPN_THREADS, smem, stream>>>(
       a, base_anchors, img_hw, cand_boxes, cand_key, cand_valid, cand_count, img_maxc);
   g_launch_count_add(1);
@@ -317,12 +319,8 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
   if (rc) return rc;
 
   RpnMergeEpilogue ep{cand_boxes, proposals, d.Kc, p->max_per_img};
-  nms_merge_kernel<RpnMergeEpilogue><<<p->batch, 256, 0, stream>>>(
-      kept_pos, kept_key, kept_count, p->num_levels, d.keep_cap, p->max_per_img,
-      num_proposals, ep);
-  g_launch_count_add(1);
-  BRCNN_CUDA_CHECK_LAST();
-  return BRCNN_OK;
+  return launch_nms_merge(kept_pos, kept_key, kept_count, p->batch, p->num_levels,
+                          d.keep_cap, p->max_per_img, num_proposals, ep, stream);
 }
 
 int brcnn_delta2bbox(const float* rois, const float* deltas, int32_t n, int32_t ncls,
@@ -606,11 +604,8 @@ int brcnn_rcnn_get_bboxes(const brcnn_rcnn_params* p, const float* rois,
 
   RcnnMergeEpilogue ep{bboxes, det_bboxes, det_labels, a.Rc, a.C,
                        a.agnostic ? 1 : a.C, p->max_per_img};
-  nms_merge_kernel<RcnnMergeEpilogue><<<a.B, 256, 0, stream>>>(
-      kept_pos, kept_key, kept_count, a.C, w.keep_cap, p->max_per_img, num_dets, ep);
-  g_launch_count_add(1);
-  BRCNN_CUDA_CHECK_LAST();
-  return BRCNN_OK;
+  return launch_nms_merge(kept_pos, kept_key, kept_count, a.B, a.C, w.keep_cap,
+                          p->max_per_img, num_dets, ep, stream);
 }
 
 }  // extern "C"

@@ -58,7 +58,7 @@ rpn_select_decode_kernel(const __grid_constant__ RpnArgs a,
                          int* __restrict__ img_maxc_bits) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int l = blockIdx.y, b = blockIdx.z;
+  const int b = blockIdx.y, l = blockIdx.z;
   const RpnLevel& lv = a.lv[l];
   const int A = a.A;
   const int P = lv.H * lv.W;
