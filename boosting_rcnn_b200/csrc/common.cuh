@@ -179,7 +179,8 @@ __device__ __forceinline__ void bitonic_sort_desc_u64(unsigned long long* keys,
       __syncthreads();
       for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
         // index of the lower element of the t-th compare-exchange pair
-        int i = ((t / j) * (j << 1)) + (t % j);
+        // (j is a power of two: t/j*2j + t%j without integer division)
+        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
         int ixj = i + j;
         unsigned long long a = keys[i];
         unsigned long long b = keys[ixj];

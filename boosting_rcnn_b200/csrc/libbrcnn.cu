@@ -140,7 +140,7 @@ static NmsWs nms_ws(int K) {
 // RPN workspace layout
 // --------------------------------------------------------------------------
 struct RpnDerived {
-  int Kc, keep_cap, W;
+  int Kc, keep_cap, W, n_total, key_stride, cand_cap;
   int level_n[BRCNN_MAX_LEVELS], level_k[BRCNN_MAX_LEVELS];
 };
 static int rpn_derive(const brcnn_rpn_params* p, RpnDerived* d) {
@@ -148,14 +148,20 @@ static int rpn_derive(const brcnn_rpn_params* p, RpnDerived* d) {
       p->num_anchors <= 0 || p->num_anchors > BRCNN_MAX_ANCHORS || p->max_per_img <= 0)
     return BRCNN_ERR_ARG;
   int Kc = 0;
+  long long n_total = 0, key_stride = 0;
   for (int l = 0; l < p->num_levels; ++l) {
     if (p->feat_h[l] <= 0 || p->feat_w[l] <= 0) return BRCNN_ERR_ARG;
     const long long n = (long long)p->feat_h[l] * p->feat_w[l] * p->num_anchors;
     if (n > 0x3fffffff) return BRCNN_ERR_UNSUPPORTED;
+    n_total += n; key_stride += (n + 3) & ~3LL;
     d->level_n[l] = (int)n;
     d->level_k[l] = (p->nms_pre > 0 && n > p->nms_pre) ? p->nms_pre : (int)n;
     if (d->level_k[l] > Kc) Kc = d->level_k[l];
   }
+  if (n_total > 0x3fffffff) return BRCNN_ERR_UNSUPPORTED;
+  d->n_total = (int)n_total; d->key_stride = (int)key_stride;
+  // smem candidate slots of the top-k kernel: >= 2x the largest k, >= 4096
+  d->cand_cap = 2 * next_pow2(Kc) > 4096 ? 2 * next_pow2(Kc) : 4096;
   d->Kc = Kc;
   d->keep_cap = Kc < p->max_per_img ? Kc : p->max_per_img;
   d->W = (Kc + 63) / 64;
@@ -164,7 +170,7 @@ static int rpn_derive(const brcnn_rpn_params* p, RpnDerived* d) {
 
 struct RpnWsInternal {
   brcnn_rpn_ws_layout pub;
-  size_t mask, kept_key;
+  size_t mask, kept_key, keys, ghist, zero_bytes;
 };
 static int rpn_ws(const brcnn_rpn_params* p, RpnWsInternal* w) {
   RpnDerived d;
@@ -179,10 +185,13 @@ static int rpn_ws(const brcnn_rpn_params* p, RpnWsInternal* w) {
   w->pub.cand_valid = o; o = align256(o + S * d.Kc);
   w->pub.cand_count = o; o = align256(o + S * 4);
   w->pub.img_maxc = o;   o = align256(o + (size_t)p->batch * 4);
+  w->ghist = o;          o = align256(o + S * RPN_BINS * 4);
+  w->zero_bytes = o - (size_t)w->pub.img_maxc;  // img_maxc + ghist, zeroed per call
+  w->keys = o;           o = align256(o + (size_t)p->batch * d.key_stride * 4);
   w->pub.kept_pos = o;   o = align256(o + S * d.keep_cap * 4);
   w->pub.kept_count = o; o = align256(o + S * 4);
   w->kept_key = o;       o = align256(o + S * d.keep_cap * 8);
-  w->mask = o;           o = align256(o + (nms_use_fused(d.Kc) ? 0 : S * d.Kc * d.W * 8));
+  w->mask = o;           o = align256(o + (nms_use_fused(d.keep_cap) ? 0 : S * d.Kc * d.W * 8));
   w->pub.total_bytes = (int64_t)o;
   return BRCNN_OK;
 }
@@ -214,7 +223,7 @@ static int rcnn_ws(const brcnn_rcnn_params* p, RcnnWsInternal* w) {
   w->pub.kept_pos = o;   o = align256(o + B * C * w->keep_cap * 4);
   w->pub.kept_count = o; o = align256(o + B * C * 4);
   w->kept_key = o;       o = align256(o + B * C * w->keep_cap * 8);
-  w->mask = o;           o = align256(o + (nms_use_fused((int)Rc) ? 0 : B * C * Rc * w->W * 8));
+  w->mask = o;           o = align256(o + (nms_use_fused(w->keep_cap) ? 0 : B * C * Rc * w->W * 8));
   w->pub.total_bytes = (int64_t)o;
   return BRCNN_OK;
 }
@@ -267,7 +276,7 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
   RpnArgs a;
   memset(&a, 0, sizeof(a));
   a.A = p->num_anchors; a.L = p->num_levels; a.B = p->batch; a.Kc = d.Kc;
-  int idx_base = 0, slice_cap = 0;
+  int idx_base = 0, chunk_base = 0, key_off = 0;
   for (int l = 0; l < p->num_levels; ++l) {
     RpnLevel& lv = a.lv[l];
     lv.cls = cls_scores_host[l]; lv.bbox = bbox_preds_host[l]; lv.iou = iou_preds_host[l];
@@ -275,17 +284,18 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
     lv.H = p->feat_h[l]; lv.W = p->feat_w[l];
     lv.stride_w = p->stride_w[l]; lv.stride_h = p->stride_h[l];
     lv.n = d.level_n[l]; lv.k = d.level_k[l]; lv.idx_base = idx_base;
+    lv.chunk_base = chunk_base;
+    lv.key_off = key_off;
     idx_base += lv.n;
-    const int P = lv.H * lv.W;
-    const int pp = (P + RPN_CS - 1) / RPN_CS;
-    if (pp * a.A > slice_cap) slice_cap = pp * a.A;
+    key_off += (lv.n + 3) & ~3;
+    chunk_base += (lv.n + RPN_SCORE_CHUNK - 1) / RPN_SCORE_CHUNK;
   }
-  a.kpow2 = next_pow2(d.Kc);
-  a.slice_cap = slice_cap;
+  a.key_stride = d.key_stride;
+  a.cand_cap = d.cand_cap;
   for (int i = 0; i < 4; ++i) { a.means[i] = p->means[i]; a.stds[i] = p->stds[i]; }
   a.max_ratio = p->max_ratio; a.min_size = p->min_bbox_size;
-  const size_t smem = (size_t)a.kpow2 * 8 + (size_t)slice_cap * 4;
-  if (smem > 220 * 1024) return BRCNN_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)a.cand_cap * 8;
+  if (smem > 200 * 1024) return BRCNN_ERR_UNSUPPORTED;
 
   char* ws = (char*)workspace;
   float4* cand_boxes = (float4*)(ws + w.pub.cand_boxes);
@@ -297,21 +307,34 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
   int32_t* kept_count = (int32_t*)(ws + w.pub.kept_count);
   u64* kept_key = (u64*)(ws + w.kept_key);
   u64* mask = (u64*)(ws + w.mask);
-
-  cudaError_t e = cudaMemsetAsync(img_maxc, 0, (size_t)p->batch * 4, stream);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(rpn_select_decode_kernel,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  // clusters are scheduled in (x, y, z) order: level-major, so the 16x heavier
-  // level-0 clusters start first instead of being spread over later waves
-  dim3 grid(RPN_CS, p->batch, p->num_levels);
-  rpn_select_decode_kernel<<<grid, RPN_THREADS, smem, stream>>>(
-      a, base_anchors, img_hw, cand_boxes, cand_key, cand_valid, cand_count, img_maxc);
-  g_launch_count_add(1);
-  BRCNN_CUDA_CHECK_LAST();
-
+  uint32_t* keys = (uint32_t*)(ws + w.keys);
+  uint32_t* ghist = (uint32_t*)(ws + w.ghist);
   const int S = p->batch * p->num_levels;
+
+  // img_maxc and ghist are adjacent in the workspace: one memset
+  cudaError_t e = cudaMemsetAsync(ws + w.pub.img_maxc, 0, w.zero_bytes, stream);
+  if (e != cudaSuccess) return (int)e;
+  {
+    dim3 grid(chunk_base, p->batch);
+    rpn_score_kernel<<<grid, RPN_SCORE_THREADS, 0, stream>>>(a, keys, ghist);
+    g_launch_count_add(1);
+    BRCNN_CUDA_CHECK_LAST();
+  }
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(rpn_topk_decode_kernel,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  {
+    // x = image: the heavy level-0 CTAs of every image are scheduled first
+    dim3 grid(p->batch, p->num_levels);
+    rpn_topk_decode_kernel<<<grid, RPN_TOPK_THREADS, smem, stream>>>(
+        a, keys, ghist, base_anchors, img_hw, cand_boxes, cand_key, cand_valid, cand_count,
+        img_maxc);
+    g_launch_count_add(1);
+    BRCNN_CUDA_CHECK_LAST();
+  }
+
   rc = launch_nms_segments(cand_boxes, cand_valid, cand_count, S, d.Kc,
                            p->iou_threshold, 0.f, (const float*)img_maxc,
                            p->num_levels, mask, cand_key, kept_pos, kept_key,
@@ -439,20 +462,41 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
     a.feat[l] = feats_nhwc_host[l];
   }
   const int nbins = a.PH * a.PW;
-  // channel chunk: as many channels as fit ~56 KB of staging, multiple of 32
-  int chunk = a.C;
+  if (a.PH > ROI_MAXP || a.PW > ROI_MAXP) return BRCNN_ERR_UNSUPPORTED;
+  for (int l = 0; l < a.L; ++l) {
+    if (a.H[l] > a.max_h) a.max_h = a.H[l];
+    if (a.W[l] > a.max_w) a.max_w = a.W[l];
+  }
+  // channel slab per CTA: <= 256 channels (64 quads x 4 bin-row slots) and
+  // <= ~56 KB of staging, multiple of 32
+  int chunk = a.C < 256 ? a.C : 256;
   const int max_chunk = ((56 * 1024) / (nbins * 4)) & ~31;
   if (max_chunk < 32) return BRCNN_ERR_UNSUPPORTED;
   if (chunk > max_chunk) chunk = max_chunk;
   a.chunk_c = chunk;
   const int nchunks = (a.C + chunk - 1) / chunk;
-  const size_t smem = (size_t)chunk * nbins * 4;
-  cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  const size_t smem = ((size_t)chunk * nbins + (size_t)a.PH * a.max_h +
+                       (size_t)a.PW * a.max_w) * 4;
+  if (smem > 200 * 1024) return BRCNN_ERR_UNSUPPORTED;
   dim3 grid(R, nchunks);
-  roi_align_fwd_kernel<<<grid, 256, smem, stream>>>(a, rois, R, out, roi_levels);
+  cudaError_t e;
+  if (a.PW <= 7) {
+    e = cudaFuncSetAttribute(roi_align_fwd_kernel<7>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    // 3 CTAs x ~58 KB per SM: ask for the large shared-memory carveout
+    e = cudaFuncSetAttribute(roi_align_fwd_kernel<7>,
+                             cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    roi_align_fwd_kernel<7><<<grid, ROI_THREADS, smem, stream>>>(a, rois, R, out, roi_levels);
+  } else {
+    e = cudaFuncSetAttribute(roi_align_fwd_kernel<ROI_MAXP>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    roi_align_fwd_kernel<ROI_MAXP><<<grid, ROI_THREADS, smem, stream>>>(a, rois, R, out,
+                                                                         roi_levels);
+  }
   g_launch_count_add(1);
   BRCNN_CUDA_CHECK_LAST();
   return BRCNN_OK;

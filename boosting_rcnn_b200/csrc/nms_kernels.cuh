@@ -44,11 +44,29 @@ __device__ __forceinline__ bool nms_suppresses(const float4 a, const float aa,
   const float h = fminf(a.w, b.w) - fmaxf(a.y, b.y) + off;
   if (!(w > 0.f) || !(h > 0.f)) return false;
   const float inter = w * h;
-  return inter / (aa + ba - inter) > thr;
+  const float u = aa + ba - inter;
+  // fl(inter/u) > thr decided without the division when inter is more than
+  // ~16 ulp away from thr*u (the IEEE quotient is within 1 ulp of the real
+  // ratio); the exact division only runs inside that band.
+  const float p = thr * u;
+  if (thr > 1e-30f && p > 1e-30f && p < 1e30f) {  // normal range, u > 0
+    if (inter > p * 1.000001f) return true;
+    if (inter < p * 0.999999f) return false;
+  }
+  return inter / u > thr;
 }
 
 // ---------------------------------------------------------------------------
-// fused small-segment NMS.  dynamic smem: cap_pad*(16+4) + W*8 + 64*8 bytes
+// fused NMS, "pull" form.  One CTA per segment walks the sorted candidates in
+// tiles of 64:
+//   1. pull   : the tile's candidates are tested against every box kept so
+//               far (kept list lives in shared memory) -> dead bits;
+//   2. diag   : 64x64 intra-tile suppression bits for the survivors;
+//   3. resolve: warp 0 walks the tile in order (ffs over the alive bits);
+//   4. append : kept boxes join the shared-memory list.
+// IoUs are only ever evaluated between a candidate and an earlier KEPT box,
+// tiles after the max_keep-th keep are never touched, and there is no global
+// bitmask.  dynamic smem: keep_pad*(16+4) bytes.
 // ---------------------------------------------------------------------------
 constexpr int NMS_FUSED_THREADS = 512;
 
@@ -58,15 +76,14 @@ nms_fused_kernel(const float4* __restrict__ boxes, const uint8_t* __restrict__ v
                  const float* __restrict__ img_maxc, int Sg,
                  const u64* __restrict__ cand_key, int32_t* __restrict__ kept_pos,
                  u64* __restrict__ kept_key, int32_t* __restrict__ kept_count,
-                 int keep_cap, int max_keep) {
+                 int keep_cap, int max_keep, int keep_pad) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
-  const int W = (cap + 63) >> 6;
-  const int cap_pad = W * 64;
-  float4* sb = reinterpret_cast<float4*>(nms_smem);
-  float* sa = reinterpret_cast<float*>(sb + cap_pad);
-  u64* remv = reinterpret_cast<u64*>(sa + cap_pad);
-  u64* diag = remv + W;
-  __shared__ u64 s_keepbits;
+  float4* kbox = reinterpret_cast<float4*>(nms_smem);        // [keep_pad]
+  float* karea = reinterpret_cast<float*>(kbox + keep_pad);  // [keep_pad]
+  __shared__ float4 tb[64];
+  __shared__ float ta[64];
+  __shared__ u64 diag[64];
+  __shared__ unsigned s_dead[2];
   __shared__ int s_nkept;
 
   const int s = blockIdx.x;
@@ -77,43 +94,75 @@ nms_fused_kernel(const float4* __restrict__ boxes, const uint8_t* __restrict__ v
   float segoff = 0.f;
   const bool has_off = (img_maxc != nullptr);
   if (has_off) segoff = (float)(s % Sg) * (img_maxc[s / Sg] + 1.0f);
-  for (int i = tid; i < n; i += NMS_FUSED_THREADS) {
-    float4 b = seg[i];
-    if (has_off) b = add_seg_offset(b, segoff);
-    sb[i] = b;
-    sa[i] = (b.z - b.x + off) * (b.w - b.y + off);
-  }
-  for (int w = tid; w < Wn; w += NMS_FUSED_THREADS) {
-    u64 r = 0;
-    const int base = w * 64;
-    if (valid != nullptr) {
-      const uint8_t* v = valid + (size_t)s * cap + base;
-      const int m = min(64, n - base);
-      for (int j = 0; j < m; ++j)
-        if (!v[j]) r |= (1ull << j);
-    }
-    if (n - base < 64) r |= ~((1ull << (n - base)) - 1ull);
-    remv[w] = r;
-  }
   if (tid == 0) s_nkept = 0;
+  // first tile prefetched into registers by threads 0..63
+  float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool ndead = true;
+  if (tid < 64 && tid < n) {
+    nb = seg[tid];
+    ndead = (valid != nullptr && valid[(size_t)s * cap + tid] == 0);
+  }
   __syncthreads();
 
   for (int t = 0; t < Wn; ++t) {
-    const u64 alive = ~remv[t];
-    if (alive == 0ull) continue;  // block-uniform
-    // (b) 64x64 diagonal block: thread (r, g) tests row r against cols 8g..8g+7
+    // ---- stage tile t, prefetch tile t+1 ----
+    if (tid < 64) {
+      float4 b = nb;
+      if (has_off) b = add_seg_offset(b, segoff);
+      tb[tid] = b;
+      ta[tid] = (b.z - b.x + off) * (b.w - b.y + off);
+      const unsigned bal = __ballot_sync(0xffffffffu, ndead);
+      if (lane == 0) s_dead[tid >> 5] = bal;
+      const int i = (t + 1) * 64 + tid;
+      ndead = true;
+      if (i < n) {
+        nb = seg[i];
+        ndead = (valid != nullptr && valid[(size_t)s * cap + i] == 0);
+      }
+    }
+    __syncthreads();
+    const int nkept = s_nkept;
+    // ---- 1. pull: candidate c vs kept boxes q = g, g+8, ... ----
+    {
+      const int c = tid & 63, g = tid >> 6;
+      bool hit = false;
+      if (!((s_dead[c >> 5] >> (c & 31)) & 1u)) {
+        const float4 b = tb[c];
+        const float ba = ta[c];
+        int q = g;
+        for (; q + 24 < nkept && !hit; q += 32) {
+          const bool h0 = nms_suppresses(kbox[q], karea[q], b, ba, thr, off);
+          const bool h1 = nms_suppresses(kbox[q + 8], karea[q + 8], b, ba, thr, off);
+          const bool h2 = nms_suppresses(kbox[q + 16], karea[q + 16], b, ba, thr, off);
+          const bool h3 = nms_suppresses(kbox[q + 24], karea[q + 24], b, ba, thr, off);
+          hit = h0 | h1 | h2 | h3;
+        }
+        for (; q < nkept && !hit; q += 8)
+          hit = nms_suppresses(kbox[q], karea[q], b, ba, thr, off);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0 && bal) atomicOr(&s_dead[(tid >> 5) & 1], bal);
+    }
+    __syncthreads();
+    const u64 alive = ~(((u64)s_dead[1] << 32) | (u64)s_dead[0]);
+    if (alive == 0ull) {  // block-uniform
+      __syncthreads();  // s_dead is rewritten by the next tile's staging
+      continue;
+    }
+    // ---- 2. diag: thread (r, g) tests row r against cols 8g..8g+7 ----
     {
       const int r = tid >> 3, g = tid & 7;
-      const int row = t * 64 + r;
       unsigned bits8 = 0;
       if ((alive >> r) & 1ull) {
-        const float4 a = sb[row];
-        const float aa = sa[row];
+        const float4 a = tb[r];
+        const float aa = ta[r];
+        // column form: which EARLIER alive candidates of the tile suppress r
+        // (the IoU test is symmetric)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const int cc = g * 8 + c;
-          if (cc > r && ((alive >> cc) & 1ull) &&
-              nms_suppresses(a, aa, sb[t * 64 + cc], sa[t * 64 + cc], thr, off))
+          if (cc < r && ((alive >> cc) & 1ull) &&
+              nms_suppresses(tb[cc], ta[cc], a, aa, thr, off))
             bits8 |= (1u << c);
         }
       }
@@ -124,56 +173,39 @@ nms_fused_kernel(const float4* __restrict__ boxes, const uint8_t* __restrict__ v
       if (g == 0) diag[r] = word;
     }
     __syncthreads();
-    // (c) warp 0 resolves the tile in order
+    // ---- 3./4. warp 0 resolves the tile and appends the keeps ----
+    // Greedy NMS inside the tile is the unique fixpoint of
+    //   K = { r alive : no earlier r' in K suppresses r };
+    // iterating from K = alive fixes the first i candidates after i rounds, so
+    // it converges in (suppression-chain depth + 1) ballot rounds instead of
+    // one serial step per kept box.
     if (tid < 32) {
-      const u64 d0 = diag[lane], d1 = diag[lane + 32];
-      u64 al = alive, keep = 0;
-      while (al) {
-        const int r = __ffsll((long long)al) - 1;
-        const u64 d = __shfl_sync(0xffffffffu, (r < 32) ? d0 : d1, r & 31);
-        keep |= (1ull << r);
-        al &= ~(d | (1ull << r));
+      const u64 c0 = diag[lane], c1 = diag[lane + 32];
+      const bool a0 = (alive >> lane) & 1ull, a1 = (alive >> (lane + 32)) & 1ull;
+      u64 keep = alive;
+      for (int it = 0; it < 64; ++it) {
+        const unsigned k0 = __ballot_sync(0xffffffffu, a0 && !(c0 & keep));
+        const unsigned k1 = __ballot_sync(0xffffffffu, a1 && !(c1 & keep));
+        const u64 kn = ((u64)k1 << 32) | (u64)k0;
+        if (kn == keep) break;
+        keep = kn;
       }
-      const int base = s_nkept;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int r = lane + 32 * h;
         if ((keep >> r) & 1ull) {
-          const int idx = base + __popcll(keep & ((1ull << r) - 1ull));
-          if (idx < keep_cap) kept_pos[(size_t)s * keep_cap + idx] = t * 64 + r;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        s_keepbits = keep;
-        s_nkept = base + __popcll(keep);
-      }
-    }
-    __syncthreads();
-    const u64 kb = s_keepbits;
-    if (s_nkept >= max_keep) break;
-    // (d) kept candidates of this tile suppress later ones (lazy IoUs)
-    const int jend = Wn * 64;
-    for (int j = (t + 1) * 64 + tid; j < jend; j += NMS_FUSED_THREADS) {
-      bool newly = false;
-      if (!((remv[j >> 6] >> (j & 63)) & 1ull)) {
-        const float4 b = sb[j];
-        const float ba = sa[j];
-        u64 bl = kb;
-        while (bl) {
-          const int r = __ffsll((long long)bl) - 1;
-          bl &= bl - 1;
-          if (nms_suppresses(sb[t * 64 + r], sa[t * 64 + r], b, ba, thr, off)) {
-            newly = true;
-            break;
+          const int q = nkept + __popcll(keep & ((1ull << r) - 1ull));
+          if (q < keep_cap && q < max_keep) {
+            kept_pos[(size_t)s * keep_cap + q] = t * 64 + r;
+            kbox[q] = tb[r];
+            karea[q] = ta[r];
           }
         }
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, newly);
-      // each warp owns one 32-bit half of a remv word in this round
-      if (lane == 0 && bal) reinterpret_cast<unsigned*>(remv)[j >> 5] |= bal;
+      if (lane == 0) s_nkept = nkept + __popcll(keep);
     }
     __syncthreads();
+    if (s_nkept >= max_keep) break;
   }
   __syncthreads();
   const int nk = min(min(s_nkept, keep_cap), max_keep);
@@ -241,17 +273,10 @@ nms_sweep_kernel(const u64* __restrict__ mask,
   const int Wn = (n + 63) >> 6;
   const int lane = threadIdx.x & 31;
   const u64* segmask = mask + (size_t)s * cap * W;
-  for (int w = threadIdx.x; w < Wn; w += blockDim.x) {
-    u64 r = 0;
-    const int base = w * 64;
-    if (valid != nullptr) {
-      const uint8_t* v = valid + (size_t)s * cap + base;
-      const int m = min(64, n - base);
-      for (int j = 0; j < m; ++j)
-        if (!v[j]) r |= (1ull << j);
-    }
-    if (n - base < 64) r |= ~((1ull << (n - base)) - 1ull);  // beyond count
-    remv[w] = r;
+  for (int i = threadIdx.x; i < Wn * 64; i += blockDim.x) {
+    const bool dead = (i >= n) || (valid != nullptr && valid[(size_t)s * cap + i] == 0);
+    const unsigned bal = __ballot_sync(0xffffffffu, dead);
+    if (lane == 0) reinterpret_cast<unsigned*>(remv)[i >> 5] = bal;
   }
   if (threadIdx.x == 0) s_nkept = 0;
   // diagonal words of tile 0 (prefetched one tile ahead below)
@@ -403,11 +428,12 @@ inline int launch_nms_merge(const int32_t* kept_pos, const u64* kept_key,
 
 // bytes of bitmask workspace needed for S segments of capacity cap (0 when the
 // fused kernel handles them)
-inline bool nms_use_fused(int cap) {
-  const int W = (cap + 63) / 64;
-  const size_t smem = (size_t)W * 64 * 20 + (size_t)W * 8 + 64 * 8;
-  return smem <= 160 * 1024 && cap <= 2048;
+// the fused kernel keeps min(keep_cap, max_keep) boxes (20 B each) in smem
+inline int nms_keep_pad(int keep_cap, int max_keep) {
+  const int k = keep_cap < max_keep ? keep_cap : max_keep;
+  return ((k > 0 ? k : 1) + 7) & ~7;
 }
+inline bool nms_use_fused(int keep) { return (size_t)nms_keep_pad(keep, keep) * 20 <= 160 * 1024; }
 
 // host-side launcher for S uniform segments
 inline int launch_nms_segments(const float4* boxes, const uint8_t* valid,
@@ -419,8 +445,9 @@ inline int launch_nms_segments(const float4* boxes, const uint8_t* valid,
                                cudaStream_t stream) {
   if (S <= 0 || cap <= 0) return BRCNN_OK;
   const int W = (cap + 63) / 64;
-  if (nms_use_fused(cap)) {
-    const size_t smem = (size_t)W * 64 * 20 + (size_t)W * 8 + 64 * 8;
+  const int keep_pad = nms_keep_pad(keep_cap, max_keep);
+  if (nms_use_fused(keep_pad)) {
+    const size_t smem = (size_t)keep_pad * 20;
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(nms_fused_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -429,7 +456,7 @@ inline int launch_nms_segments(const float4* boxes, const uint8_t* valid,
     }
     nms_fused_kernel<<<S, NMS_FUSED_THREADS, smem, stream>>>(
         boxes, valid, count, cap, thr, off, img_maxc, Sg, cand_key, kept_pos, kept_key,
-        kept_count, keep_cap, max_keep);
+        kept_count, keep_cap, max_keep, keep_pad);
     g_launch_count_add(1);
     BRCNN_CUDA_CHECK_LAST();
     return BRCNN_OK;

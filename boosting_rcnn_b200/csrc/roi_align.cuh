@@ -4,15 +4,28 @@
 // Reference behaviour: single_level_roi_extractor.py:36-115 + mmcv RoIAlign
 // (aligned=True, pool_mode='avg', sampling_ratio=0), SURVEY.md App. A5/A6.
 //
-// Mapping: one CTA per (RoI, channel chunk <= 256).  A warp covers 8 channel
-// quads x 4 bins: every tap is a 128-byte line read as 8 x LDG.128, the four
-// taps of a sample come from at most four lines.  The chunk's ph*pw*C outputs
-// are staged in shared memory in (c, bin) order (bank-conflict free for 7x7)
-// and streamed out as 128-bit coalesced stores.
+// Formulation.  mmcv averages gh x gw bilinear samples per bin; bilinear
+// weights are separable, so for one RoI
+//     out[c][ph][pw] = sum_y sum_x Wy[ph][y] * Wx[pw][x] * F[y][x][c]
+// with Wy[ph][y] = (1/count) * sum over the bin's sample rows of the tap weight
+// landing on feature row y (Wx likewise, without the 1/count).  Both tables
+// are tiny (7 x footprint side) and banded; they are built once per RoI in
+// shared memory.  The kernel then reads every footprint pixel of a bin row
+// ONCE per bin row (not 4 taps x samples), as 128-bit channel-quad loads:
+//     t[x]  = sum_{y in band(ph)} Wy[ph][y] * F[y][x]     (registers, 8 px chunk)
+//     u[pw] += Wx[pw][x] * t[x]                            (7 accumulators)
+// Mapping: one CTA per (RoI, <=256-channel slab); thread = (channel quad,
+// bin-row slot), so a warp reads 512 contiguous bytes per pixel.  The slab's
+// outputs are staged in shared memory in (c, bin) order and streamed out with
+// coalesced 128-bit stores.
 #pragma once
 #include "common.cuh"
 
 namespace brcnn {
+
+constexpr int ROI_THREADS = 256;
+constexpr int ROI_XCH = 8;       // pixels per register chunk
+constexpr int ROI_MAXP = 14;     // max pooled side (table / accumulator bound)
 
 struct RoiArgs {
   const float* feat[BRCNN_MAX_LEVELS];  // NHWC (B,H,W,C)
@@ -20,7 +33,8 @@ struct RoiArgs {
   float scale[BRCNN_MAX_LEVELS];
   int B, C, L, PH, PW, sampling_ratio, aligned;
   float finest_scale;
-  int chunk_c;  // channels per CTA (multiple of 32)
+  int chunk_c;   // channels per CTA (multiple of 4, <= 256)
+  int max_h, max_w;  // largest level map (table capacity)
 };
 
 struct RoiGeom {
@@ -75,78 +89,179 @@ __device__ __forceinline__ bool bilinear_axis(float v, int size, int& lo, int& h
   return true;
 }
 
-__global__ void __launch_bounds__(256)
+// Conservative inclusive range of feature rows (or columns) any sample of the
+// RoI can touch along one axis; empty (lo > hi) when nothing is valid.
+__device__ __forceinline__ void roi_axis_range(float start, float bin, int nbin, int grid,
+                                               int size, int& lo, int& hi) {
+  const float v0 = start, v1 = start + bin * (float)nbin;
+  if (!(grid > 0) || !(v1 >= -1.0f) || !(v0 <= (float)size)) { lo = 1; hi = 0; return; }
+  lo = max(0, (int)floorf(fmaxf(v0, 0.f)));
+  hi = min(size - 1, (int)floorf(fminf(fmaxf(v1, 0.f), (float)size)) + 1);
+}
+
+// Weight of feature index `pos` for pooled bin `pb` along one axis:
+// sum over the bin's `grid` samples of the tap weight that lands on `pos`.
+__device__ __forceinline__ float roi_axis_weight(float start, float bin, int grid, int size,
+                                                 int pb, int pos) {
+  float w = 0.f;
+  const float base = start + (float)pb * bin;
+  for (int i = 0; i < grid; ++i) {
+    const float v = base + ((float)i + 0.5f) * bin / (float)grid;
+    int lo, hi; float wl, wh;
+    if (!bilinear_axis(v, size, lo, hi, wl, wh)) continue;
+    if (lo == pos) w += wl;
+    if (hi == pos) w += wh;
+  }
+  return w;
+}
+
+// dynamic smem: chunk_c*nbins floats (stage) + PH*max_h + PW*max_w floats
+// NPW: compile-time bound on pooled_w (number of register accumulators)
+template <int NPW>
+__global__ void __launch_bounds__(ROI_THREADS, NPW <= 7 ? 2 : 1)
 roi_align_fwd_kernel(const __grid_constant__ RoiArgs a,
                      const float* __restrict__ rois, int R,
                      float* __restrict__ out, int32_t* __restrict__ roi_levels) {
-  extern __shared__ __align__(16) float stage[];  // [chunk_c][nbins]
+  extern __shared__ __align__(16) float roi_smem[];
+  const int nbins = a.PH * a.PW;
+  float* stage = roi_smem;                       // [chunk_c][nbins]
+  float* wy = stage + (size_t)a.chunk_c * nbins; // [PH][fh]   (includes 1/count)
+  float* wx = wy + (size_t)a.PH * a.max_h;       // [fw][PW]   (x-major)
+  __shared__ int s_ys[ROI_MAXP], s_ye[ROI_MAXP];  // row band of every bin row
+
   const int r = blockIdx.x;
   const int c0 = blockIdx.y * a.chunk_c;
   const int cc = min(a.chunk_c, a.C - c0);
-  const int nbins = a.PH * a.PW;
   const float* roi = rois + (size_t)r * 5;
   float* dst = out + ((size_t)r * a.C + c0) * nbins;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x;
   const int total = cc * nbins;
 
   if (roi[0] < 0.f) {  // padding row
-    for (int i = tid; i < total; i += blockDim.x) dst[i] = 0.f;
+    for (int i = tid; i < total; i += ROI_THREADS) dst[i] = 0.f;
     if (roi_levels != nullptr && blockIdx.y == 0 && tid == 0) roi_levels[r] = -1;
     return;
   }
   const RoiGeom g = roi_geometry(a, roi);
   if (roi_levels != nullptr && blockIdx.y == 0 && tid == 0) roi_levels[r] = g.lvl;
-  const float* feat = a.feat[g.lvl] + (size_t)g.b * g.H * g.W * a.C + c0;
-  const int C = a.C;
+  int ylo, yhi, xlo, xhi;
+  roi_axis_range(g.start_h, g.bin_h, a.PH, g.gh, g.H, ylo, yhi);
+  roi_axis_range(g.start_w, g.bin_w, a.PW, g.gw, g.W, xlo, xhi);
+  const int fh = yhi - ylo + 1, fw = xhi - xlo + 1;
+  const bool empty = (fh <= 0) || (fw <= 0);
 
-  const int ncg = cc >> 2;             // channel quads in this chunk
-  const int ncgt = (ncg + 7) >> 3;     // tiles of 8 quads
-  const int nbt = (nbins + 3) >> 2;    // tiles of 4 bins
-  const int cg_sub = lane & 7, bin_sub = lane >> 3;
-  const int nwarps = blockDim.x >> 5;
-  for (int it = wid; it < ncgt * nbt; it += nwarps) {
-    const int bt = it / ncgt, cgt = it - bt * ncgt;
-    const int bin = bt * 4 + bin_sub;
-    const int cg = cgt * 8 + cg_sub;
-    if (bin >= nbins || cg >= ncg) continue;
-    const int ph = bin / a.PW, pw = bin - ph * a.PW;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float ybase = g.start_h + (float)ph * g.bin_h;
-    const float xbase = g.start_w + (float)pw * g.bin_w;
-    for (int iy = 0; iy < g.gh; ++iy) {
-      const float y = ybase + ((float)iy + 0.5f) * g.bin_h / (float)g.gh;
-      int yl, yh; float hy, ly;
-      if (!bilinear_axis(y, g.H, yl, yh, hy, ly)) continue;
-      const float* rowl = feat + (size_t)yl * g.W * C + cg * 4;
-      const float* rowh = feat + (size_t)yh * g.W * C + cg * 4;
-      for (int ix = 0; ix < g.gw; ++ix) {
-        const float x = xbase + ((float)ix + 0.5f) * g.bin_w / (float)g.gw;
-        int xl, xh; float hx, lx;
-        if (!bilinear_axis(x, g.W, xl, xh, hx, lx)) continue;
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(rowl + (size_t)xl * C));
-        const float4 v2 = __ldg(reinterpret_cast<const float4*>(rowl + (size_t)xh * C));
-        const float4 v3 = __ldg(reinterpret_cast<const float4*>(rowh + (size_t)xl * C));
-        const float4 v4 = __ldg(reinterpret_cast<const float4*>(rowh + (size_t)xh * C));
-        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-        acc.x = fmaf(w1, v1.x, fmaf(w2, v2.x, fmaf(w3, v3.x, fmaf(w4, v4.x, acc.x))));
-        acc.y = fmaf(w1, v1.y, fmaf(w2, v2.y, fmaf(w3, v3.y, fmaf(w4, v4.y, acc.y))));
-        acc.z = fmaf(w1, v1.z, fmaf(w2, v2.z, fmaf(w3, v3.z, fmaf(w4, v4.z, acc.z))));
-        acc.w = fmaf(w1, v1.w, fmaf(w2, v2.w, fmaf(w3, v3.w, fmaf(w4, v4.w, acc.w))));
+  // ---- pull the whole footprint towards L2 in one shot ----
+  // Every footprint row is a contiguous run of fw*C floats; issuing all the
+  // prefetches up front turns the ~dozen dependent DRAM round trips of the
+  // main loop into one DRAM latency plus L2 hits.
+  if (!empty) {
+    const char* fb = reinterpret_cast<const char*>(
+        a.feat[g.lvl] + (size_t)g.b * g.H * g.W * a.C + c0);
+    const int row_bytes = (fw - 1) * a.C * 4 + cc * 4;
+    const int lines = (row_bytes + 127) >> 7;
+    for (int i = tid; i < fh * lines; i += ROI_THREADS) {
+      const int dy = i / lines, ln = i - dy * lines;
+      const char* p = fb + ((size_t)(ylo + dy) * g.W + xlo) * a.C * 4 + (size_t)ln * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
+
+  // ---- separable weight tables ----
+  if (!empty) {
+    for (int i = tid; i < a.PH * fh; i += ROI_THREADS) {
+      const int ph = i / fh, dy = i - ph * fh;
+      wy[ph * fh + dy] =
+          roi_axis_weight(g.start_h, g.bin_h, g.gh, g.H, ph, ylo + dy) * g.inv_count;
+    }
+    for (int i = tid; i < a.PW * fw; i += ROI_THREADS) {
+      const int dx = i / a.PW, pw = i - dx * a.PW;
+      wx[dx * a.PW + pw] = roi_axis_weight(g.start_w, g.bin_w, g.gw, g.W, pw, xlo + dx);
+    }
+  }
+  __syncthreads();
+  if (!empty && tid < a.PH) {  // non-zero row band of bin row `tid`
+    int ys = fh, ye = -1;
+    for (int dy = 0; dy < fh; ++dy)
+      if (wy[tid * fh + dy] != 0.f) { ys = min(ys, dy); ye = dy; }
+    s_ys[tid] = ys;
+    s_ye[tid] = ye;
+  }
+  __syncthreads();
+
+  // ---- main loop: thread = (channel quad, bin-row slot) ----
+  const int ncq = cc >> 2;
+  const int nslot = ROI_THREADS / 64;          // 4 slots of 64 quads
+  const int cq = tid & 63, slot = tid >> 6;
+  const int C = a.C;
+  for (int cqb = 0; cqb < ncq; cqb += 64) {
+    const int q = cqb + cq;
+    const bool q_ok = q < ncq;
+    const float* fbase = a.feat[g.lvl] + (size_t)g.b * g.H * g.W * C + c0 + q * 4;
+    for (int ph = slot; ph < a.PH; ph += nslot) {
+      float4 u[NPW];
+#pragma unroll
+      for (int pw = 0; pw < NPW; ++pw) u[pw] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!empty && q_ok) {
+        const int ys = s_ys[ph], ye = s_ye[ph];
+        for (int x0 = 0; x0 < fw; x0 += ROI_XCH) {
+          float4 t[ROI_XCH];
+#pragma unroll
+          for (int i = 0; i < ROI_XCH; ++i) t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int dy = ys; dy <= ye; ++dy) {
+            const float w = wy[ph * fh + dy];
+            const float* row = fbase + ((size_t)(ylo + dy) * g.W + xlo + x0) * C;
+#pragma unroll
+            for (int i = 0; i < ROI_XCH; ++i) {
+              if (x0 + i < fw) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(row + (size_t)i * C));
+                t[i].x = fmaf(w, v.x, t[i].x);
+                t[i].y = fmaf(w, v.y, t[i].y);
+                t[i].z = fmaf(w, v.z, t[i].z);
+                t[i].w = fmaf(w, v.w, t[i].w);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < ROI_XCH; ++i) {
+            if (x0 + i < fw) {
+              const float* wrow = wx + (x0 + i) * a.PW;
+#pragma unroll
+              for (int pw = 0; pw < NPW; ++pw) {
+                if (pw < a.PW) {
+                  const float w = wrow[pw];
+                  if (w != 0.f) {
+                    u[pw].x = fmaf(w, t[i].x, u[pw].x);
+                    u[pw].y = fmaf(w, t[i].y, u[pw].y);
+                    u[pw].z = fmaf(w, t[i].z, u[pw].z);
+                    u[pw].w = fmaf(w, t[i].w, u[pw].w);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      if (q_ok) {
+        float* s = stage + (size_t)(q * 4) * nbins + ph * a.PW;
+#pragma unroll
+        for (int pw = 0; pw < NPW; ++pw) {
+          if (pw < a.PW) {
+            s[pw] = u[pw].x;
+            s[nbins + pw] = u[pw].y;
+            s[2 * nbins + pw] = u[pw].z;
+            s[3 * nbins + pw] = u[pw].w;
+          }
+        }
       }
     }
-    float* s = stage + (size_t)(cg * 4) * nbins + bin;
-    s[0] = acc.x * g.inv_count;
-    s[nbins] = acc.y * g.inv_count;
-    s[2 * nbins] = acc.z * g.inv_count;
-    s[3 * nbins] = acc.w * g.inv_count;
   }
   __syncthreads();
   if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
     const float4* s4 = reinterpret_cast<const float4*>(stage);
     float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int i = tid; i < (total >> 2); i += blockDim.x) __stcs(d4 + i, s4[i]);
+    for (int i = tid; i < (total >> 2); i += ROI_THREADS) __stcs(d4 + i, s4[i]);
   } else {
-    for (int i = tid; i < total; i += blockDim.x) dst[i] = stage[i];
+    for (int i = tid; i < total; i += ROI_THREADS) dst[i] = stage[i];
   }
 }
 
