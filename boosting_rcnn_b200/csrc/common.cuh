@@ -155,14 +155,17 @@ __device__ __forceinline__ int map_roi_level(float x1, float y1,
                                                       int num_levels) {
   float scale = sqrtf((x2 - x1) * (y2 - y1));
   float v = scale / finest_scale + 1e-6f;
+  // floor(log2f(v)) >= k  <=>  v >= T[k], with log2f rounded to nearest: near
+  // k >= 3 the fp32 grid of the RESULT is coarser than log2's slope, so the
+  // 1 (k = 3,4) or 2 (k >= 5) floats just below 2^k already round up to k.
+  // The table holds exactly those thresholds (checked against torch.log2 on a
+  // +-50-float sweep around every power of two, tests/test_oracle_golden.py).
+  const uint32_t T[8] = {0u,          0x40000000u, 0x40800000u, 0x40FFFFFFu,
+                         0x417FFFFFu, 0x41FFFFFEu, 0x427FFFFEu, 0x42FFFFFEu};
   int lvl = 0;
-  float thr = 2.0f;
   // NaN compares false everywhere -> level 0 (torch: floor(nan).clamp.long()
   // is implementation defined; documented in DESIGN.md)
-  while (lvl < num_levels - 1 && v >= thr) {
-    ++lvl;
-    thr = thr * 2.0f;
-  }
+  while (lvl < num_levels - 1 && lvl < 7 && v >= __uint_as_float(T[lvl + 1])) ++lvl;
   return lvl;
 }
 

@@ -1,0 +1,67 @@
+"""Multi-GPU plumbing of the hot path (torch.distributed only carries bytes).
+
+The path shards by image with NO data-path collective:
+``shard_range`` gives each rank its images.  The only collectives are the
+ones the reference issues around the path in training:
+  * the gradient all-reduce (left to torch DDP / NCCL, mmdet/apis/train.py:75-83);
+  * scalar reductions — ``reduce_mean`` x2 in the RPN loss
+    (atss_rpn_head.py:441-444,458-459) and one all-reduce per logged key in
+    ``_parse_losses`` (mmdet/models/detectors/base.py:201-207), each followed
+    by ``.item()``.  ``fused_scalar_allreduce`` replaces those 2 + 7 tiny
+    all-reduces by ONE all-reduce of a packed <=16-float vector.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.distributed as dist
+
+
+def get_dist_info():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(num_images, rank=None, world_size=None):
+    """Contiguous image shard [lo, hi) of this rank; remainders go to the
+    first ranks (every image is processed exactly once)."""
+    if rank is None or world_size is None:
+        rank, world_size = get_dist_info()
+    base, rem = divmod(num_images, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def reduce_mean(tensor):
+    """mmdet/core/utils/dist_utils.py:67-73: all-reduce of tensor / world."""
+    _, world = get_dist_info()
+    if world == 1:
+        return tensor
+    tensor = tensor.clone()
+    dist.all_reduce(tensor.div_(world), op=dist.ReduceOp.SUM)
+    return tensor
+
+
+def fused_scalar_allreduce(named_scalars):
+    """Average every scalar of an ordered {name: 0-dim tensor} dict over the
+    ranks with a single all-reduce; returns an OrderedDict of 0-dim tensors.
+    Same values as calling ``reduce_mean`` once per entry (base.py:201-207),
+    one collective instead of len(named_scalars)."""
+    named_scalars = OrderedDict(named_scalars)
+    _, world = get_dist_info()
+    if world == 1 or not named_scalars:
+        return named_scalars
+    vals = list(named_scalars.values())
+    packed = torch.stack([v.detach().reshape(()).float() for v in vals])
+    dist.all_reduce(packed.div_(world), op=dist.ReduceOp.SUM)
+    return OrderedDict((k, packed[i]) for i, k in enumerate(named_scalars))
+
+
+def max_over_ranks(value, device=None):
+    """Timing rule of bench.py: device time of a step is the max over ranks."""
+    _, world = get_dist_info()
+    if world == 1:
+        return float(value)
+    t = torch.tensor([float(value)], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

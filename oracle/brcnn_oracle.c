@@ -313,8 +313,13 @@ API void oracle_map_roi_levels(const float* rois, int R, float finest_scale, int
     const float* q = rois + (size_t)r * 5;
     const float scale = sqrtf((q[3] - q[1]) * (q[4] - q[2]));
     const float v = scale / finest_scale + 1e-6f;
-    int lvl = 0; float thr = 2.0f;
-    while (lvl < L - 1 && v >= thr) { ++lvl; thr = thr * 2.0f; }
+    /* floor(log2f(v)) >= k  <=>  v >= T[k] for a round-to-nearest log2f: the
+     * 1-2 floats just below 2^k (k >= 3) already round UP to k in fp32.
+     * Pinned against torch.log2 (CPU) in tests/test_oracle_golden.py. */
+    static const uint32_t T[8] = {0u,          0x40000000u, 0x40800000u, 0x40FFFFFFu,
+                                  0x417FFFFFu, 0x41FFFFFEu, 0x427FFFFEu, 0x42FFFFFEu};
+    int lvl = 0;
+    while (lvl < L - 1 && lvl < 7 && v >= as_float((int32_t)T[lvl + 1])) ++lvl;
     out[r] = lvl;
   }
 }

@@ -1,0 +1,57 @@
+"""CPU, world_size 2, gloo: the N>1 plumbing (image sharding, the fused scalar
+all-reduce that replaces the reference's 2 + 7 scalar all-reduces, max-over-
+ranks timing)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from boosting_rcnn_b200 import dist as bdist
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    lo, hi = bdist.shard_range(33)
+    losses = {k: torch.tensor(float(i + 1 + 10 * rank)) for i, k in enumerate(
+        ['loss_rpn_cls', 'loss_rpn_bbox', 'loss_rpn_iou', 'loss_cls', 'acc', 'loss_bbox', 'loss'])}
+    fused = bdist.fused_scalar_allreduce(losses)
+    each = {k: bdist.reduce_mean(v) for k, v in losses.items()}
+    ms = bdist.max_over_ranks(1.5 + rank)
+    out.put((rank, lo, hi, {k: float(v) for k, v in fused.items()},
+             {k: float(v) for k, v in each.items()}, ms))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_fused_allreduce():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, lo0, hi0, f0, e0, m0), (r1, lo1, hi1, f1, e1, m1) = res
+    assert (lo0, hi0, lo1, hi1) == (0, 17, 17, 33)  # every image exactly once
+    assert f0 == f1 == e0 == e1  # one fused collective == 7 separate reduce_means
+    assert f0['loss_cls'] == (4 + 14) / 2 and list(f0) == list(e0)
+    assert m0 == m1 == 2.5
+
+
+def test_single_process_paths_are_identity():
+    assert bdist.shard_range(16) == (0, 16)
+    assert bdist.get_dist_info() == (0, 1)
+    d = {'a': torch.tensor(2.0)}
+    assert bdist.fused_scalar_allreduce(d)['a'].item() == 2.0
+    assert [bdist.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]

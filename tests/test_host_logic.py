@@ -1,0 +1,123 @@
+"""CPU: host-side mirror of the reference interfaces (registry, configs,
+padding helpers, assign/sample glue)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from boosting_rcnn_b200 import configs, ops, roi_head, sampling
+from boosting_rcnn_b200.registry import HEADS, ConfigDict, build_from_cfg, build_head
+from boosting_rcnn_b200.rpn_head import PaddedProposals
+
+G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden.npz'))
+
+
+def test_registry_names_and_config_building():
+    for cfg in ('utdac', 'coco', 'voc'):
+        rpn, roi, m = configs.build_hot_path(cfg, train=True)
+        assert type(rpn).__name__ == 'ATSSRPNHead' and type(roi).__name__ == 'ProbRoIHead'
+        assert type(roi.bbox_roi_extractor).__name__ == 'SingleRoIExtractor'
+        assert type(roi.bbox_head).__name__ == 'ProbConvFCBBoxHead'
+        assert roi.bbox_roi_extractor.num_inputs == 5
+        assert roi.bbox_roi_extractor.roi_layers[0].output_size == (7, 7)
+    for name in ('ATSSRPNHead', 'SingleRoIExtractor', 'ProbRoIHead', 'ProbConvFCBBoxHead'):
+        assert HEADS.get(name) is not None
+    with pytest.raises(KeyError):
+        build_head(dict(type='NoSuchHead'))
+    with pytest.raises(KeyError):
+        build_from_cfg(dict(), HEADS)
+
+
+def test_state_dict_keys_match_reference_checkpoints():
+    rpn, roi, _ = configs.build_hot_path('utdac')
+    keys = set(rpn.state_dict())
+    assert {'rpn_convs.0.conv.weight', 'rpn_convs.3.gn.weight', 'rpn_cls.weight', 'rpn_reg.bias',
+            'rpn_iou.weight', 'scales.4.scale'} <= keys
+    assert 'rpn_convs.0.conv.bias' not in keys  # ConvModule drops the bias under GN
+    assert set(roi.state_dict()) == {
+        f'bbox_head.{n}.{p}' for n in ('shared_fcs.0', 'shared_fcs.1', 'fc_cls', 'fc_reg')
+        for p in ('weight', 'bias')}
+    assert abs(rpn.rpn_cls.bias[0].item() + 4.59512) < 1e-4  # bias_prob = 0.01
+    _, roi_voc, _ = configs.build_hot_path('voc')
+    assert any(k.startswith('bbox_head.reg_convs.3.gn') for k in roi_voc.state_dict())
+    assert roi_voc.bbox_head.fc_cls.in_features == 1024 and roi_voc.bbox_head.fc_reg.in_features == 256 * 49
+
+
+def test_configdict_attribute_access_and_nesting():
+    c = ConfigDict(nms=dict(type='nms', iou_threshold=0.7), nms_pre=1000)
+    assert c.nms.iou_threshold == 0.7 and c['nms_pre'] == 1000
+    assert c.get('missing', 3) == 3
+    with pytest.raises(AttributeError):
+        c.nope
+    import copy
+    d = copy.deepcopy(c)
+    d.nms.iou_threshold = 0.5
+    assert c.nms.iou_threshold == 0.7
+
+
+def test_pad_proposals_and_padded_rois():
+    plist = [torch.rand(3, 5), torch.zeros(0, 5), torch.rand(5, 5)]
+    pp = roi_head.pad_proposals(plist)
+    assert isinstance(pp, PaddedProposals) and pp.boxes.shape == (3, 5, 5)
+    assert pp.num.tolist() == [3, 0, 5]
+    rois = roi_head.padded_rois(pp)
+    assert rois.shape == (15, 5)
+    assert rois[:, 0].tolist() == [0, 0, 0, -1, -1] + [-1] * 5 + [2] * 5
+    assert torch.equal(rois[10:, 1:], plist[2][:, :4])
+    ref = roi_head.bbox2roi(plist)
+    assert torch.equal(rois[rois[:, 0] >= 0], ref)
+
+
+def test_bbox2result_splits_by_label():
+    det = np.arange(20, dtype=np.float32).reshape(4, 5)
+    lab = np.array([1, 0, 1, 3])
+    res = roi_head.bbox2result(det, lab, 4)
+    assert [r.shape[0] for r in res] == [1, 2, 0, 1]
+    assert all(r.shape == (0, 5) for r in roi_head.bbox2result(np.zeros((0, 5)), lab[:0], 4))
+
+
+def test_max_iou_assigner_reference_kat():
+    # tests/test_utils/test_assigner.py:16-37
+    a = sampling.MaxIoUAssigner(pos_iou_thr=0.5, neg_iou_thr=0.5)
+    bboxes = torch.FloatTensor([[0, 0, 10, 10], [10, 10, 20, 20], [5, 5, 15, 15], [32, 32, 38, 42]])
+    gt = torch.FloatTensor([[0, 0, 10, 9], [0, 10, 10, 19]])
+    res = a.assign(bboxes, gt, gt_labels=torch.LongTensor([2, 3]))
+    assert res.gt_inds.tolist() == [1, 0, 2, 0]
+    assert len(res.labels) == 4
+    res = a.assign(bboxes, torch.empty(0, 4), gt_labels=torch.empty(0, dtype=torch.long))
+    assert res.gt_inds.tolist() == [0, 0, 0, 0]
+
+
+def test_random_sampler_row_order_and_prior_indexing():
+    torch.manual_seed(0)
+    props = torch.cat([torch.rand(200, 2) * 300, torch.rand(200, 2) * 300 + 300, torch.rand(200, 1)], 1)
+    gt = torch.tensor([[10., 10., 320., 330.], [100., 120., 500., 480.]])
+    # few positives (< num*pos_fraction) so every GT row survives the sampling,
+    # the regime prob_roi_head.py:52-57 silently assumes
+    a = sampling.MaxIoUAssigner(pos_iou_thr=0.8, neg_iou_thr=0.8, min_pos_iou=0.8, match_low_quality=False)
+    s = sampling.RandomSampler(num=64, pos_fraction=0.25, add_gt_as_proposals=True)
+    ar = a.assign(props, gt, None, torch.tensor([1, 2]))
+    res = s.sample(ar, props, gt, torch.tensor([1, 2]))
+    assert res.bboxes.shape[0] == 64 and res.pos_inds.numel() <= 16
+    assert res.pos_inds[:2].tolist() == [0, 1]  # GTs first (prob_roi_head.py:52-57)
+    assert torch.equal(res.pos_inds, res.pos_inds.sort().values)
+    assert torch.equal(res.neg_inds, res.neg_inds.sort().values)
+    assert res.pos_is_gt[:2].tolist() == [1, 1]
+
+
+def test_coder_encode_vs_executed_reference():
+    from boosting_rcnn_b200.coder import DeltaXYWHBBoxCoder
+    c = DeltaXYWHBBoxCoder(target_stds=(.1, .1, .2, .2))
+    rois = torch.from_numpy(G['d2b_rois'])
+    out = c.encode(rois, rois.flip(0)).numpy()
+    assert np.allclose(out, G['b2d_out'], rtol=1e-6, atol=1e-6)
+
+
+def test_ops_reject_cpu_tensors():
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        ops.map_roi_levels(torch.zeros(3, 5), 5)
+    with pytest.raises(RuntimeError):
+        ops.delta2bbox(torch.zeros(3, 4), torch.zeros(3, 4))
+    with pytest.raises(RuntimeError):
+        ops.roi_extract([torch.zeros(1, 4, 8, 8)], torch.zeros(2, 5), [0.125])

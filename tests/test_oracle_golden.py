@@ -1,0 +1,216 @@
+"""CPU: pin the oracle (oracle/brcnn_oracle.c) before trusting it.
+
+1. against tests/golden/reference_golden.npz — outputs of the reference's OWN
+   Python functions executed by tests/golden/make_golden.py;
+2. against the known-answer vectors held by the reference's test-suite
+   (tests/test_utils/test_anchor.py:548-646, tests/test_utils/test_coder.py:
+   27-75, tests/test_metrics/test_losses.py:186-240);
+3. against torchvision.ops.{nms,roi_align} — the algorithm mmcv delegates to
+   under use_torchvision=True — for the two mmcv-native ops.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torchvision
+
+import synth
+from boosting_rcnn_b200.anchors import AnchorGenerator
+from oracle import oracle
+
+G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden.npz'))
+
+
+# ------------------------------------------------------------------ pinned math
+def test_pinned_expf_accuracy_and_edges():
+    x = np.concatenate([np.linspace(-104, 88.7, 400001), [0.0, -0.0, 1e-8, -1e-8]]).astype(np.float32)
+    e = oracle.expf(x).astype(np.float64)
+    ref = np.exp(x.astype(np.float64))
+    ok = ref > 1e-37  # normal range
+    ulp = np.abs(e[ok] - ref[ok]) / np.spacing(ref[ok].astype(np.float32)).astype(np.float64)
+    assert ulp.max() < 1.1, ulp.max()  # measured 1.004 ulp worst case
+    sub = ~ok
+    assert np.all(np.abs(e[sub] - ref[sub]) <= 2e-45 + 1e-6 * ref[sub])
+    assert oracle.expf(np.array([200.0], np.float32))[0] == np.inf
+    assert oracle.expf(np.array([-200.0], np.float32))[0] == 0.0
+    assert np.isnan(oracle.expf(np.array([np.nan], np.float32))[0])
+    assert oracle.expf(np.array([0.0], np.float32))[0] == 1.0
+
+
+def test_pinned_sigmoid_matches_torch_within_ulps():
+    x = np.random.RandomState(0).normal(0, 4, 200000).astype(np.float32)
+    mine = oracle.sigmoid(x)
+    ref = torch.from_numpy(x).sigmoid().numpy()
+    rel = np.abs(mine.astype(np.float64) - ref) / np.maximum(ref, 1e-30)
+    assert rel.max() < 4e-7  # <= ~3 ulp of the reference's own (libm-dependent) sigmoid
+
+
+# ------------------------------------------------------------------ anchors
+EXPECTED_BASE_ANCHORS_L0 = np.array(  # tests/test_utils/test_anchor.py:582-590
+    [[-22.6274, -11.3137, 22.6274, 11.3137], [-28.5088, -14.2544, 28.5088, 14.2544],
+     [-35.9188, -17.9594, 35.9188, 17.9594], [-16.0000, -16.0000, 16.0000, 16.0000],
+     [-20.1587, -20.1587, 20.1587, 20.1587], [-25.3984, -25.3984, 25.3984, 25.3984],
+     [-11.3137, -22.6274, 11.3137, 22.6274], [-14.2544, -28.5088, 14.2544, 28.5088],
+     [-17.9594, -35.9188, 17.9594, 35.9188]], dtype=np.float32)
+
+
+def test_base_anchors_match_reference_kat_and_executed_reference():
+    g = AnchorGenerator(strides=[8, 16, 32, 64, 128], ratios=[0.5, 1.0, 2.0],
+                        octave_base_scale=4, scales_per_octave=3)
+    assert g.num_base_anchors == [9] * 5  # test_anchor.py:640
+    t = g.base_anchor_table().numpy()
+    for l in range(5):  # every level is level 0 scaled by 2**l (test_anchor.py:581-627)
+        assert np.allclose(t[l], EXPECTED_BASE_ANCHORS_L0 * 2 ** l, rtol=1e-5, atol=1e-4 * 2 ** l)
+    np.testing.assert_array_equal(t, G['anchor_base_a9'])  # bit-exact vs executed reference
+    g1 = AnchorGenerator(strides=[8, 16, 32, 64, 128], ratios=[1.0], octave_base_scale=8,
+                         scales_per_octave=1)
+    np.testing.assert_array_equal(g1.base_anchor_table().numpy(), G['anchor_base_a1'])
+    grid = torch.cat(g.grid_anchors_cpu([(5, 7), (3, 4), (2, 2), (1, 1), (1, 1)])).numpy()
+    np.testing.assert_array_equal(grid, G['anchor_grid_a9'])
+
+
+# ------------------------------------------------------------------ delta2bbox
+def test_delta2bbox_reference_kats():
+    # tests/test_utils/test_coder.py:27-40 and the doctest delta_xywh_bbox_coder.py:191-204
+    rois = np.array([[0., 0., 1., 1.], [0., 0., 1., 1.], [0., 0., 1., 1.], [5., 5., 5., 5.]], np.float32)
+    deltas = np.array([[0., 0., 0., 0.], [1., 1., 1., 1.], [0., 0., 2., -1.],
+                       [0.7, -1.9, -0.5, 0.3]], np.float32)
+    expected = np.array([[0.0000, 0.0000, 1.0000, 1.0000], [0.1409, 0.1409, 2.8591, 2.8591],
+                         [0.0000, 0.3161, 4.1945, 0.6839], [5.0000, 5.0000, 5.0000, 5.0000]], np.float32)
+    out = oracle.delta2bbox(rois, deltas, max_shape=(32, 32))
+    assert np.allclose(out, expected, atol=1e-4)
+    assert oracle.delta2bbox(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32),
+                             max_shape=(32, 32)).shape == (0, 4)
+
+
+def test_delta2bbox_vs_executed_reference():
+    out1 = oracle.delta2bbox(G['d2b_rois'], G['d2b_deltas1'], max_shape=(320, 400))
+    out4 = oracle.delta2bbox(G['d2b_rois'], G['d2b_deltas4'], stds=(.1, .1, .2, .2), max_shape=(320, 400))
+    outn = oracle.delta2bbox(G['d2b_rois'], G['d2b_deltas1'])
+    # the reference's exp() is libm's; the oracle pins it (<= 1 ulp) -> 1e-5 relative
+    for mine, ref in ((out1, G['d2b_out1']), (out4, G['d2b_out4']), (outn, G['d2b_out1_noclip'])):
+        assert np.allclose(mine, ref, rtol=1e-5, atol=1e-4)
+
+
+# ------------------------------------------------------------------ RPN path
+def test_rpn_get_bboxes_single_vs_executed_reference():
+    g = AnchorGenerator(strides=[8, 16, 32, 64, 128], ratios=[0.5, 1.0, 2.0],
+                        octave_base_scale=4, scales_per_octave=3)
+    props = oracle.rpn_get_bboxes_single(
+        [G[f'rpn_cls_{l}'] for l in range(5)], [G[f'rpn_box_{l}'] for l in range(5)],
+        [G[f'rpn_iou_{l}'] for l in range(5)], g.base_anchor_table().numpy(), synth.STRIDES,
+        tuple(G['rpn_img_shape']), nms_pre=60, max_per_img=40, iou_threshold=0.7)
+    ref = G['rpn_proposals']
+    assert props.shape == ref.shape  # same number of proposals, same order
+    assert np.allclose(props[:, 4], ref[:, 4], rtol=1e-6, atol=1e-7)
+    assert np.allclose(props[:, :4], ref[:, :4], rtol=1e-5, atol=1e-4)
+
+
+def test_map_roi_levels_vs_executed_reference():
+    lv = oracle.map_roi_levels(G['lvl_rois'], 5, 56)
+    np.testing.assert_array_equal(lv, G['lvl_out'])
+
+
+def test_map_roi_levels_dense_boundary_sweep_vs_torch_log2():
+    # compare-form level mapping == floor(log2(.)) of the reference on a dense
+    # set of scales straddling every threshold by a few ulp (SURVEY.md hard part vi)
+    rois = []
+    for s in (112.0, 224.0, 448.0, 896.0):
+        base = np.float32(s)
+        for k in range(-40, 41):
+            v = base
+            for _ in range(abs(k)):
+                v = np.nextafter(v, np.float32(np.inf if k > 0 else -np.inf), dtype=np.float32)
+            rois.append([0, 0, 0, v, v])
+    rois = np.array(rois, dtype=np.float32)
+    t = torch.from_numpy(rois)
+    scale = torch.sqrt((t[:, 3] - t[:, 1]) * (t[:, 4] - t[:, 2]))
+    ref = torch.floor(torch.log2(scale / 56 + 1e-6)).clamp(min=0, max=4).long().numpy()
+    mine = oracle.map_roi_levels(rois, 5, 56)
+    bad = np.nonzero(mine != ref)[0]
+    assert len(bad) == 0, f'{len(bad)} boundary disagreements, first at roi {rois[bad[0]]}'
+
+
+# ------------------------------------------------------------------ mmcv-native stand-ins
+@pytest.mark.parametrize('n,clustered', [(200, False), (1000, True), (3000, True)])
+def test_nms_cpu_vs_torchvision(n, clustered):
+    boxes = synth.random_boxes(n, 800, 1333, seed=n, clustered=clustered)
+    scores = np.random.RandomState(n).permutation(n).astype(np.float32) / n  # unique
+    for thr in (0.5, 0.7):
+        keep = oracle.nms_cpu(boxes, scores, thr)
+        ref = torchvision.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), thr).numpy()
+        np.testing.assert_array_equal(keep, ref)
+
+
+def test_batched_nms_split_equals_unsplit():
+    boxes = synth.random_boxes(2500, 600, 1000, seed=3, clustered=True)
+    scores = (np.round(np.random.RandomState(4).rand(2500) * 100) / 100).astype(np.float32)
+    ids = np.random.RandomState(5).randint(0, 6, 2500)
+    d1, k1 = oracle.batched_nms(boxes, scores, ids, 0.6, split_thr=10000)
+    d2, k2 = oracle.batched_nms(boxes, scores, ids, 0.6, split_thr=100)  # forces the split path
+    np.testing.assert_array_equal(k1, k2)
+    np.testing.assert_array_equal(d1, d2)
+
+
+def test_multiclass_nms_vs_executed_reference():
+    mb, ms = G['mc_bboxes'], G['mc_scores']
+    R, C = ms.shape[0], ms.shape[1] - 1
+    rois = np.zeros((R, 5), np.float32)
+    # decode is bypassed: feed already-decoded boxes through the NMS half
+    import ctypes
+    cb, cs, cl = [], [], []
+    for r in range(R):
+        for c in range(C):
+            if ms[r, c] > 0.05:
+                cb.append(mb[r, c * 4:c * 4 + 4]); cs.append(ms[r, c]); cl.append(c)
+    dets, keep = oracle.batched_nms(np.array(cb), np.array(cs), np.array(cl), 0.5)
+    dets, labels = dets[:30], np.array(cl)[keep][:30]
+    np.testing.assert_array_equal(labels, G['mc_labels'])
+    np.testing.assert_array_equal(dets, G['mc_dets'])
+
+
+@pytest.mark.parametrize('scale,H,W', [(1 / 8, 50, 84), (1 / 32, 13, 21)])
+def test_roi_align_forward_backward_vs_torchvision(scale, H, W):
+    rng = np.random.RandomState(1)
+    feat = rng.normal(0, 1, (2, 8, H, W)).astype(np.float32)
+    rois = synth.random_rois(2, 40, 400, 672, seed=2)
+    extra = np.array([[0, -30, -30, 20, 20], [1, 600, 350, 700, 420], [0, 5, 5, 5, 5],
+                      [1, 0, 0, 672, 400]], np.float32)
+    rois = np.concatenate([rois, extra])
+    out = oracle.roi_align_forward(feat, rois, 7, scale)
+    tf = torch.from_numpy(feat).requires_grad_(True)
+    ref = torchvision.ops.roi_align(tf, torch.from_numpy(rois), 7, scale, sampling_ratio=0, aligned=True)
+    assert np.allclose(out, ref.detach().numpy(), rtol=1e-5, atol=1e-5)
+    g = rng.normal(0, 1, out.shape).astype(np.float32)
+    ref.backward(torch.from_numpy(g))
+    gi = oracle.roi_align_backward(g, rois, feat.shape, scale)
+    assert np.allclose(gi, tf.grad.numpy(), rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------ fusion + loss
+def test_fusion_vs_executed_reference():
+    out = oracle.fuse_scores(G['fuse_cls'], G['fuse_prior'])
+    assert np.allclose(out, G['fuse_out'], rtol=2e-6, atol=1e-7)
+
+
+def test_boost_loss_vs_executed_reference():
+    N, C1 = G['loss_cls_score'].shape
+    z4 = np.zeros((N, 4), np.float32)
+    o = oracle.boost_loss(G['loss_cls_score'], G['loss_labels'], G['loss_prior'],
+                          np.zeros((N, 4 * (C1 - 1)), np.float32), z4, z4, C1 - 1, gamma=0.5,
+                          loss_cls_weight=2.0, loss_bbox_weight=2.0)
+    assert abs(o['loss_cls'] - G['loss_cls']) <= 1e-5 * abs(G['loss_cls'])
+    assert abs(o['acc'] - G['loss_acc']) <= 1e-4
+    scale = np.abs(G['loss_grad_cls']).max()
+    assert np.abs(o['grad_cls'] - G['loss_grad_cls']).max() <= 1e-5 * scale
+
+
+def test_accuracy_reference_kat():
+    # tests/test_metrics/test_losses.py:193-201: top-1 accuracy 100 on this fixture
+    pred = np.array([[0.2, 0.3, 0.6, 0.5], [0.1, 0.1, 0.2, 0.6], [0.9, 0.0, 0.0, 0.1],
+                     [0.4, 0.7, 0.1, 0.1], [0.0, 0.0, 0.99, 0]], np.float32)
+    label = np.array([2, 3, 0, 1, 2])
+    z = np.zeros((5, 4), np.float32)
+    o = oracle.boost_loss(pred, label, np.zeros(5, np.float32), np.zeros((5, 12), np.float32), z, z, 3)
+    assert o['acc'] == 100.0
