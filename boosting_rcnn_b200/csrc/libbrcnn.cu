@@ -18,6 +18,7 @@ static std::atomic<int64_t> g_launches{0};
 int64_t g_launch_count_add(int n) { return g_launches.fetch_add(n) + n; }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline bool misaligned16(const void* p) { return ((uintptr_t)p & 15) != 0; }
 static inline int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 // --------------------------------------------------------------------------
@@ -270,6 +271,7 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
   if (!cls_scores_host || !bbox_preds_host || !iou_preds_host || !base_anchors ||
       !img_hw || !proposals || !num_proposals || !workspace)
     return BRCNN_ERR_ARG;
+  if (misaligned16(base_anchors) || misaligned16(workspace)) return BRCNN_ERR_ARG;
   if (workspace_bytes < (size_t)w.pub.total_bytes) return BRCNN_ERR_WORKSPACE;
   if (p->batch > 65535) return BRCNN_ERR_UNSUPPORTED;
 
@@ -352,6 +354,7 @@ int brcnn_delta2bbox(const float* rois, const float* deltas, int32_t n, int32_t 
   if (n < 0 || ncls <= 0 || !means_host || !stds_host) return BRCNN_ERR_ARG;
   if (n == 0) return BRCNN_OK;
   if (!rois || !deltas || !out) return BRCNN_ERR_ARG;
+  if (misaligned16(rois) || misaligned16(deltas) || misaligned16(out)) return BRCNN_ERR_ARG;
   DecodeArgs a;
   for (int i = 0; i < 4; ++i) { a.means[i] = means_host[i]; a.stds[i] = stds_host[i]; }
   a.max_ratio = max_ratio; a.max_h = max_h; a.max_w = max_w; a.n = n; a.ncls = ncls;
@@ -382,6 +385,7 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
     return e == cudaSuccess ? BRCNN_OK : (int)e;
   }
   if (!boxes || !scores || !keep || !workspace) return BRCNN_ERR_ARG;
+  if (misaligned16(boxes) || misaligned16(workspace)) return BRCNN_ERR_ARG;
   if (K > 393216) return BRCNN_ERR_UNSUPPORTED;
   NmsWs w = nms_ws(K);
   if (workspace_bytes < w.total) return BRCNN_ERR_WORKSPACE;
@@ -458,7 +462,7 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
   if (R == 0) return BRCNN_OK;
   if (!feats_nhwc_host || !rois || !out) return BRCNN_ERR_ARG;
   for (int l = 0; l < a.L; ++l) {
-    if (!feats_nhwc_host[l]) return BRCNN_ERR_ARG;
+    if (!feats_nhwc_host[l] || misaligned16(feats_nhwc_host[l])) return BRCNN_ERR_ARG;
     a.feat[l] = feats_nhwc_host[l];
   }
   const int nbins = a.PH * a.PW;
@@ -601,7 +605,8 @@ int brcnn_rcnn_get_bboxes(const brcnn_rcnn_params* p, const float* rois,
       !det_labels || !num_dets || !workspace)
     return BRCNN_ERR_ARG;
   if (p->prob && !prior) return BRCNN_ERR_ARG;
-  if (p->rescale && !scale_factor) return BRCNN_ERR_ARG;
+  if (p->rescale && (!scale_factor || misaligned16(scale_factor))) return BRCNN_ERR_ARG;
+  if (misaligned16(workspace)) return BRCNN_ERR_ARG;
   if (workspace_bytes < (size_t)w.pub.total_bytes) return BRCNN_ERR_WORKSPACE;
   if (p->batch > 65535 || p->num_classes > 65535) return BRCNN_ERR_UNSUPPORTED;
   RcnnArgs a;

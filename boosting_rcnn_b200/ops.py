@@ -32,7 +32,12 @@ def _f32c(t, name):
             f'{name} must be a CUDA tensor: boosting_rcnn_b200 has no CPU path')
     if t.dtype != torch.float32:
         t = t.float()
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        # a "contiguous" view can still start mid-row (e.g. rois[:1, 1:]); the
+        # kernels read boxes / feature quads with 128-bit loads
+        t = t.clone()
+    return t
 
 
 def _ws(nbytes, device):
