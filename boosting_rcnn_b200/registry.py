@@ -158,17 +158,20 @@ HOT_PATH_CLASSES = ('ATSSRPNHead', 'SingleRoIExtractor', 'ProbRoIHead',
                     'ProbConvFCBBoxHead')
 
 
-def register_into_mmdet(force=True):
+def register_into_mmdet(force=True, names=HOT_PATH_CLASSES):
     """Register the B200 classes under the reference's names in a real mmdet
     install (the drop-in step).  Raises ImportError when
     mmdet/mmcv are absent."""
     from mmdet.models.builder import HEADS as MM_HEADS  # noqa: N811
     from mmdet.models.builder import ROI_EXTRACTORS as MM_EXTRACTORS  # noqa: N811
     from . import bbox_head, roi_extractor, roi_head, rpn_head
-    MM_HEADS.register_module(name='ATSSRPNHead', force=force, module=rpn_head.ATSSRPNHead)
-    MM_HEADS.register_module(name='ProbRoIHead', force=force, module=roi_head.ProbRoIHead)
-    MM_HEADS.register_module(name='ProbConvFCBBoxHead', force=force,
-                             module=bbox_head.ProbConvFCBBoxHead)
-    MM_EXTRACTORS.register_module(name='SingleRoIExtractor', force=force,
-                                  module=roi_extractor.SingleRoIExtractor)
-    return HOT_PATH_CLASSES
+    table = {
+        'ATSSRPNHead': (MM_HEADS, rpn_head.ATSSRPNHead),
+        'ProbRoIHead': (MM_HEADS, roi_head.ProbRoIHead),
+        'ProbConvFCBBoxHead': (MM_HEADS, bbox_head.ProbConvFCBBoxHead),
+        'SingleRoIExtractor': (MM_EXTRACTORS, roi_extractor.SingleRoIExtractor),
+    }
+    for n in names:
+        reg, cls = table[n]
+        reg.register_module(name=n, force=force, module=cls)
+    return tuple(names)
