@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument('--cpu-images', type=int, default=0,
                     help='images in the CPU-baseline sample (0: one per host thread, <= 16)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch kernels one by one')
     return ap.parse_args()
 
 
@@ -262,84 +263,132 @@ def main():
     d_feats_cl = [f.contiguous(memory_format=torch.channels_last) for f in d_feats]
     torch.cuda.synchronize()
     test_rcnn = model['test_cfg']['rcnn']
+    from boosting_rcnn_b200.graph import HostPipeline, HotPathGraph
 
-    @torch.no_grad()
-    def step(feats, cls, box, iou):
-        props = rpn_head.get_bboxes_padded(cls, box, iou, metas)
-        return roi_head.simple_test_bboxes_padded(feats, metas, props, test_rcnn, rescale=True)
+    # the step: one CUDA graph over the whole batch; --no-graph
+    # launches the same kernels one by one from Python
+    if args.no_graph:
+        @torch.no_grad()
+        def _eager(feats):
+            props = rpn_head.get_bboxes_padded(d_cls, d_box, d_iou, metas)
+            return roi_head.simple_test_bboxes_padded(feats, metas, props, test_rcnn, rescale=True)
+        step, step_cl = (lambda: _eager(d_feats)), (lambda: _eager(d_feats_cl))
+        l0 = lib.brcnn_launch_count()
+        step()
+        launches_per_step = int(lib.brcnn_launch_count() - l0)
+    else:
+        g_nchw = HotPathGraph(rpn_head, roi_head, metas, d_feats, d_cls, d_box, d_iou,
+                              rcnn_test_cfg=test_rcnn, rescale=True)
+        g_cl = HotPathGraph(rpn_head, roi_head, metas, d_feats_cl, d_cls, d_box, d_iou,
+                            rcnn_test_cfg=test_rcnn, rescale=True)
+        step, step_cl = g_nchw.replay, g_cl.replay
+        launches_per_step = g_nchw.launches_per_replay
 
-    @torch.no_grad()
-    def step_e2e():
-        det, lab, num = step(to_dev(h_feats), to_dev(h_cls), to_dev(h_box), to_dev(h_iou))
-        return det.cpu(), lab.cpu(), num.cpu()
+    # end to end: pinned host buffers -> H2D -> graph -> D2H, double buffered
+    pipe = HostPipeline(rpn_head, roi_head, metas, (h_feats, h_cls, h_box, h_iou),
+                        rcnn_test_cfg=test_rcnn, rescale=True, slots=2)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, drain=None):
         for _ in range(warmup):
             fn()
+        if drain:
+            drain()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = lib.brcnn_launch_count()
         e0.record()
         for _ in range(steps):
             fn()
+        if drain:
+            drain()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        launches = lib.brcnn_launch_count() - l0
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, launches
+        return ms
+
+    class E2E:
+        """K steps through HostPipeline; every step copies its inputs from
+        pinned host memory and reads its detections back to the host."""
+        prev = None
+
+        def step(self):
+            t = pipe.submit(h_feats, h_cls, h_box, h_iou)
+            if self.prev is not None:
+                self.prev.result()
+            self.prev = t
+
+        def drain(self):
+            if self.prev is not None:
+                self.prev.result()
+                self.prev = None
+            # e1 is recorded on the default stream: make it wait for the pipeline
+            torch.cuda.current_stream().wait_stream(pipe.compute_stream)
 
     W, K = max(args.warmup, 3), args.steps
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms, launches = timed(lambda: step(d_feats, d_cls, d_box, d_iou), K, W)
+    ms = timed(step, K, W)
+    launches = launches_per_step * K
     clocks = sampler.stop() if sampler else None
-    ms_cl, _ = timed(lambda: step(d_feats_cl, d_cls, d_box, d_iou), K, W)
-    ms_e2e, _ = timed(step_e2e, max(K // 3, 3), 3)
-    k_e2e = max(K // 3, 3)
+    ms_cl = timed(step_cl, K, W)
+    e2e = E2E()
+    k_e2e = max(K // 2, 4)
+    ms_e2e = timed(e2e.step, k_e2e, 3, drain=e2e.drain)
 
     # -------------------------------------------------- per-stage device times
     stage_ms, roof = {}, None
     if rank == 0:
         with torch.no_grad():
             props = rpn_head.get_bboxes_padded(d_cls, d_box, d_iou, metas)
-            rois = padded_rois(props)
+            rois, prior = ops.bbox2roi_padded(props.boxes, props.num)
             scales = [1.0 / s for s in STRIDES]
-            nhwc = [ops.to_nhwc(f) for f in d_feats]
+            nhwc = ops.pyramid_to_nhwc(d_feats)
             feats_cl = [t.permute(0, 3, 1, 2) for t in nhwc]
             rf = ops.roi_extract(feats_cl, rois, scales, 7)
             cs, bp = roi_head.bbox_head(rf)
             hw, sf = roi_head._img_consts(metas, dev)
             rp = roi_head.bbox_head.rcnn_params(B, props.boxes.size(1), ConfigDict(test_rcnn), True, True)
-            prior = props.boxes[..., 4].reshape(-1).contiguous()
             stages = {
                 'rpn_get_bboxes': lambda: rpn_head.get_bboxes_padded(d_cls, d_box, d_iou, metas),
-                'nchw_to_nhwc_x5': lambda: [ops.to_nhwc(f) for f in d_feats],
+                'nchw_to_nhwc_x5': lambda: ops.pyramid_to_nhwc(d_feats),
                 'roi_align_fwd': lambda: ops.roi_extract(feats_cl, rois, scales, 7),
                 'fc_head_cublas': lambda: roi_head.bbox_head(rf),
                 'rcnn_get_bboxes': lambda: ops.rcnn_get_bboxes(rp, rois, prior, props.num, cs, bp,
                                                                hw, sf),
             }
+            # device time of each stage: captured alone in a CUDA graph (no
+            # host launch overhead in the number), L2 flushed before every rep
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
             for name, fn in stages.items():
-                for _ in range(3):
+                for _ in range(2):
                     fn()
                 torch.cuda.synchronize()
+                if args.no_graph:
+                    run = fn
+                else:
+                    sg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(sg):
+                        fn()
+                    run = sg.replay
+                run()
                 evs = []
                 for _ in range(10):
+                    flush.zero_()
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record()
-                    fn()
+                    run()
                     b.record()
                     evs.append((a, b))
                 torch.cuda.synchronize()
                 stage_ms[name] = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+            del flush
         peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
         if os.path.exists(peaks_path):
             peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
@@ -350,32 +399,29 @@ def main():
         feat_bytes = sum(f.numel() * 4 for f in d_feats)
         out_bytes = rois_h.shape[0] * C * 49 * 4
         fp = roi_footprint_bytes(rois_h, sizes, C)
-        kernels = {
-            'roi_align_fwd_kernel': (out_bytes + min(fp, feat_bytes), stage_ms['roi_align_fwd']),
-            'transpose_kernel(nchw_to_nhwc)': (2 * feat_bytes, stage_ms['nchw_to_nhwc_x5'] / 5 * 1),
+        # ncu dram__bytes_read+write per launch of the same command (profiles/)
+        traffic = {}
+        tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f'{args.cfg}_b{B}', {})
+        # algorithmic bytes per launch (DESIGN.md §4 / SURVEY.md §8d)
+        kern = {
+            'roi_align_fwd_kernel': dict(bytes=out_bytes + min(fp, feat_bytes),
+                                         ms=stage_ms['roi_align_fwd'], live_rois=n_live,
+                                         rois=int(rois_h.shape[0])),
+            'transpose_multi_kernel': dict(bytes=2 * feat_bytes, ms=stage_ms['nchw_to_nhwc_x5']),
         }
-        # dominant kernel of OUR launches by total time in a step
-        t_roi, t_tr = stage_ms['roi_align_fwd'], stage_ms['nchw_to_nhwc_x5']
-        if t_tr >= t_roi:
-            ach = 2 * feat_bytes / (t_tr * 1e-3) / 1e9
-            roof = dict(kernel='transpose_kernel (5 launches, one per pyramid level; aggregate)',
-                        bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak,
-                        traffic=None, peak_source=peak_src,
-                        algorithmic_bytes_per_step=2 * feat_bytes, ms_per_step=t_tr)
-        else:
-            ach = kernels['roi_align_fwd_kernel'][0] / (t_roi * 1e-3) / 1e9
-            roof = dict(kernel='roi_align_fwd_kernel', bound='hbm', achieved=ach, peak=peak,
-                        unit='GB/s', frac=ach / peak, traffic=None, peak_source=peak_src,
-                        algorithmic_bytes_per_launch=kernels['roi_align_fwd_kernel'][0],
-                        ms_per_launch=t_roi, live_rois=n_live)
-        roof['other_kernels'] = {
-            'roi_align_fwd_kernel': dict(
-                achieved=kernels['roi_align_fwd_kernel'][0] / (t_roi * 1e-3) / 1e9,
-                frac=kernels['roi_align_fwd_kernel'][0] / (t_roi * 1e-3) / 1e9 / peak,
-                algorithmic_bytes=kernels['roi_align_fwd_kernel'][0], ms=t_roi),
-            'transpose_kernel_x5': dict(achieved=2 * feat_bytes / (t_tr * 1e-3) / 1e9,
-                                        frac=2 * feat_bytes / (t_tr * 1e-3) / 1e9 / peak,
-                                        algorithmic_bytes=2 * feat_bytes, ms=t_tr)}
+        for k, v in kern.items():
+            v['achieved'] = v['bytes'] / (v['ms'] * 1e-3) / 1e9
+            v['frac'] = v['achieved'] / peak
+            v['traffic'] = traffic.get(k)
+        # dominant kernel = largest share of OUR kernel time in the step
+        dom = max(kern, key=lambda k: kern[k]['ms'])
+        d = kern[dom]
+        roof = dict(kernel=dom, bound='hbm', achieved=d['achieved'], peak=peak, unit='GB/s',
+                    frac=d['frac'], traffic=d['traffic'], peak_source=peak_src,
+                    algorithmic_bytes_per_launch=d['bytes'], ms_per_launch=d['ms'],
+                    kernels=kern)
 
     # ------------------------------------------------------------ CPU baseline
     cpu = None

@@ -91,6 +91,8 @@ SIGNATURES = {
     'brcnn_batched_nms': (c_int32, [
         c_void_p, c_void_p, c_void_p, c_int32, c_float, c_int32, c_void_p,
         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'brcnn_bbox2roi_padded': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
+                                        c_void_p]),
     'brcnn_map_roi_levels': (c_int32, [c_void_p, c_int32, c_float, c_int32,
                                        c_void_p, c_void_p]),
     'brcnn_roi_extract_forward': (c_int32, [
@@ -102,6 +104,10 @@ SIGNATURES = {
         c_void_p, c_size_t, c_void_p]),
     'brcnn_nchw_to_nhwc': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     'brcnn_nhwc_to_nchw': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    'brcnn_nchw_to_nhwc_multi': (c_int32, [POINTER(c_void_p), POINTER(c_void_p), c_int32, c_int32,
+                                           c_int32, POINTER(c_int32), c_void_p]),
+    'brcnn_nhwc_to_nchw_multi': (c_int32, [POINTER(c_void_p), POINTER(c_void_p), c_int32, c_int32,
+                                           c_int32, POINTER(c_int32), c_void_p]),
     'brcnn_boost_loss': (c_int32, [
         POINTER(LossParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

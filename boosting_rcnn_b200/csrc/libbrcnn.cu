@@ -2,6 +2,7 @@
 // Single translation unit: nvcc -gencode arch=compute_100a,code=sm_100a
 //   -fmad=false -O3 -lineinfo -shared -Xcompiler -fPIC
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/brcnn.h"
@@ -11,6 +12,7 @@
 #include "rcnn_post.cuh"
 #include "roi_align.cuh"
 #include "roi_align_bwd.cuh"
+#include "roi_align_tma.cuh"
 #include "rpn.cuh"
 
 namespace brcnn {
@@ -433,6 +435,21 @@ int brcnn_map_roi_levels(const float* rois, int32_t R, float finest_scale,
   return BRCNN_OK;
 }
 
+int brcnn_bbox2roi_padded(const float* proposals, const int32_t* num_proposals,
+                          int32_t batch, int32_t cap, float* rois, float* prior,
+                          brcnn_stream_t stream_) {
+  if (batch < 0 || cap < 0) return BRCNN_ERR_ARG;
+  if (batch == 0 || cap == 0) return BRCNN_OK;
+  if (!proposals || !num_proposals || !rois) return BRCNN_ERR_ARG;
+  const long long n = (long long)batch * cap;
+  if (n > 0x7fffffff) return BRCNN_ERR_UNSUPPORTED;
+  bbox2roi_padded_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+      proposals, num_proposals, batch, cap, rois, prior);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
 static int roi_args_from(const brcnn_roi_params* p, RoiArgs* a) {
   if (!p || p->batch <= 0 || p->channels <= 0 || (p->channels & 3) ||
       p->num_levels <= 0 || p->num_levels > BRCNN_MAX_LEVELS || p->pooled_h <= 0 ||
@@ -470,6 +487,39 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
   for (int l = 0; l < a.L; ++l) {
     if (a.H[l] > a.max_h) a.max_h = a.H[l];
     if (a.W[l] > a.max_w) a.max_w = a.W[l];
+  }
+  // ---- v2: TMA row-streaming kernel (roi_align_tma.cuh) ----
+  {
+    static const bool force_v1 = [] {
+      const char* e = getenv("BRCNN_ROI_FWD");
+      return e && e[0] == 'v' && e[1] == '1';
+    }();
+    const int chunk = a.C < 4 * RT_SLAB_Q ? a.C : 4 * RT_SLAB_Q;
+    const size_t tables = ((size_t)a.max_h * 8 + (size_t)8 * a.max_w) * 4 + (size_t)a.max_h * 4;
+    const size_t budget = 110 * 1024;  // two CTAs per SM
+    size_t ring = 96 * 1024;
+    if (tables + ring > budget) ring = tables < budget ? ((budget - tables) & ~(size_t)127) : 0;
+    const size_t need = (size_t)chunk * nbins * 4 > (size_t)3 * 128 * ((chunk * 4 + 127) / 128)
+                            ? (size_t)chunk * nbins * 4
+                            : (size_t)3 * 128 * ((chunk * 4 + 127) / 128);
+    if (!force_v1 && a.PH <= RT_P && a.PW <= RT_P && ring >= need && !misaligned16(out)) {
+      a.chunk_c = chunk;
+      const size_t smem = ring + tables;
+      cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_tma_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(roi_align_fwd_tma_kernel,
+                               cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return (int)e;
+      dim3 grid(R, (a.C + chunk - 1) / chunk);
+      roi_align_fwd_tma_kernel<<<grid, RT_THREADS, smem, stream>>>(a, rois, R, out, roi_levels,
+                                                                   (int)ring);
+      g_launch_count_add(1);
+      BRCNN_CUDA_CHECK_LAST();
+      return BRCNN_OK;
+    }
   }
   // channel slab per CTA: <= 256 channels (64 quads x 4 bin-row slots) and
   // <= ~56 KB of staging, multiple of 32
@@ -527,24 +577,33 @@ int brcnn_roi_extract_backward(const brcnn_roi_params* p, const float* grad_out,
                         workspace_bytes, stream);
 }
 
-static int transpose_launch(const float* in, float* out, int batch, int rows,
-                            int cols, cudaStream_t stream) {
-  if (batch <= 0 || rows <= 0 || cols <= 0 || !in || !out) return BRCNN_ERR_ARG;
-  if (batch > 65535 || (rows + 31) / 32 > 65535) return BRCNN_ERR_UNSUPPORTED;
-  dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
-  transpose_kernel<<<grid, 256, 0, stream>>>(in, out, rows, cols);
-  g_launch_count_add(1);
-  BRCNN_CUDA_CHECK_LAST();
-  return BRCNN_OK;
-}
-
 int brcnn_nchw_to_nhwc(const float* in, float* out, int32_t batch, int32_t channels,
                        int32_t hw, brcnn_stream_t stream) {
-  return transpose_launch(in, out, batch, channels, hw, (cudaStream_t)stream);
+  const float* i1[1] = {in}; float* o1[1] = {out};
+  const int r[1] = {channels}, c[1] = {hw};
+  return transpose_launch_multi(i1, o1, 1, batch, r, c, (cudaStream_t)stream);
 }
 int brcnn_nhwc_to_nchw(const float* in, float* out, int32_t batch, int32_t channels,
                        int32_t hw, brcnn_stream_t stream) {
-  return transpose_launch(in, out, batch, hw, channels, (cudaStream_t)stream);
+  const float* i1[1] = {in}; float* o1[1] = {out};
+  const int r[1] = {hw}, c[1] = {channels};
+  return transpose_launch_multi(i1, o1, 1, batch, r, c, (cudaStream_t)stream);
+}
+int brcnn_nchw_to_nhwc_multi(const float* const* in_host, float* const* out_host,
+                             int32_t num_maps, int32_t batch, int32_t channels,
+                             const int32_t* hw_host, brcnn_stream_t stream) {
+  if (num_maps <= 0 || num_maps > BRCNN_MAX_LEVELS || !hw_host) return BRCNN_ERR_ARG;
+  int r[BRCNN_MAX_LEVELS], c[BRCNN_MAX_LEVELS];
+  for (int i = 0; i < num_maps; ++i) { r[i] = channels; c[i] = hw_host[i]; }
+  return transpose_launch_multi(in_host, out_host, num_maps, batch, r, c, (cudaStream_t)stream);
+}
+int brcnn_nhwc_to_nchw_multi(const float* const* in_host, float* const* out_host,
+                             int32_t num_maps, int32_t batch, int32_t channels,
+                             const int32_t* hw_host, brcnn_stream_t stream) {
+  if (num_maps <= 0 || num_maps > BRCNN_MAX_LEVELS || !hw_host) return BRCNN_ERR_ARG;
+  int r[BRCNN_MAX_LEVELS], c[BRCNN_MAX_LEVELS];
+  for (int i = 0; i < num_maps; ++i) { r[i] = hw_host[i]; c[i] = channels; }
+  return transpose_launch_multi(in_host, out_host, num_maps, batch, r, c, (cudaStream_t)stream);
 }
 
 // ------------------------------- loss -------------------------------------

@@ -19,9 +19,13 @@
 // outputs are staged in shared memory in (c, bin) order and streamed out with
 // coalesced 128-bit stores.
 #pragma once
+#include <cstring>
+
 #include "common.cuh"
 
 namespace brcnn {
+
+extern int64_t g_launch_count_add(int n);
 
 constexpr int ROI_THREADS = 256;
 constexpr int ROI_XCH = 8;       // pixels per register chunk
@@ -275,26 +279,131 @@ __global__ void map_roi_levels_kernel(const float* __restrict__ rois, int R,
   out[r] = (int64_t)map_roi_level(roi[1], roi[2], roi[3], roi[4], finest_scale, L);
 }
 
-// (B, rows, cols) -> (B, cols, rows) fp32 tile transpose.  NCHW->NHWC is
-// rows=C, cols=HW; NHWC->NCHW is rows=HW, cols=C.
+// bbox2roi (mmdet/core/bbox/transforms.py:59-78) on the padded proposal layout
+// of brcnn_rpn_get_bboxes: (B,cap,5)[x1,y1,x2,y2,score] + num[B] ->
+// rois (B*cap,5)[b,x1,y1,x2,y2] (b = -1 on padding rows) and prior (B*cap)
+// = proposals[:, -1] (prob_roi_head.py:214).
+__global__ void bbox2roi_padded_kernel(const float* __restrict__ props,
+                                       const int32_t* __restrict__ num, int B, int cap,
+                                       float* __restrict__ rois, float* __restrict__ prior) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * cap) return;
+  const int b = i / cap, j = i - b * cap;
+  const float* p = props + (size_t)i * 5;
+  float* r = rois + (size_t)i * 5;
+  const bool live = j < num[b];
+  r[0] = live ? (float)b : -1.0f;
+  r[1] = p[0]; r[2] = p[1]; r[3] = p[2]; r[4] = p[3];
+  if (prior != nullptr) prior[i] = p[4];
+}
+
+// (B, rows, cols) -> (B, cols, rows) fp32 tile transpose of up to
+// BRCNN_MAX_LEVELS maps in ONE launch.  NCHW->NHWC is rows=C, cols=HW;
+// NHWC->NCHW is rows=HW, cols=C.  64x64 tiles, 256 threads: 128-bit global
+// loads along cols and 128-bit global stores along rows whenever the map's
+// geometry allows it (cols % 4 == 0 / rows % 4 == 0), scalar otherwise; the
+// tile is staged in shared memory with a 65-float pitch (<= 2-way conflicts).
+// 16 KB of loads in flight per CTA, up to 8 CTAs per SM.
+constexpr int TR_TILE = 64;
+constexpr int TR_PITCH = 65;
+
+struct TransposeMap {
+  const float* in;
+  float* out;
+  int rows, cols;
+  int tiles_x, tiles_y;  // tiles along cols / rows
+  int tile_base;         // first CTA of this map
+  int pad;
+};
+struct TransposeArgs {
+  TransposeMap m[BRCNN_MAX_LEVELS];
+  int n, batch;
+};
+
 __global__ void __launch_bounds__(256)
-transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows,
-                 int cols) {
-  __shared__ float tile[32][33];
-  const size_t boff = (size_t)blockIdx.z * rows * cols;
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+transpose_multi_kernel(const __grid_constant__ TransposeArgs a) {
+  __shared__ float tile[TR_TILE * TR_PITCH];
+  int mi = 0;
+  while (mi + 1 < a.n && (int)blockIdx.x >= a.m[mi + 1].tile_base) ++mi;
+  const TransposeMap& m = a.m[mi];
+  int t = blockIdx.x - m.tile_base;
+  const int tpb = m.tiles_x * m.tiles_y;
+  const int b = t / tpb; t -= b * tpb;
+  const int tyi = t / m.tiles_x, txi = t - tyi * m.tiles_x;
+  const int r0 = tyi * TR_TILE, c0 = txi * TR_TILE;
+  const int rows = m.rows, cols = m.cols;
+  const size_t boff = (size_t)b * rows * cols;
+  const float* __restrict__ in = m.in + boff;
+  float* __restrict__ out = m.out + boff;
+  const int q = threadIdx.x & 15, s = threadIdx.x >> 4;
+  const bool vin = ((cols & 3) == 0) && ((reinterpret_cast<uintptr_t>(m.in) & 15) == 0);
+  const bool vout = ((rows & 3) == 0) && ((reinterpret_cast<uintptr_t>(m.out) & 15) == 0);
+  // ---- load: thread (s, q) reads rows r0+s+16k, cols c0+4q..4q+3 ----
+  float4 v[4];
 #pragma unroll
-  for (int k = 0; k < 32; k += 8) {
-    const int r = r0 + ty + k, c = c0 + tx;
-    if (r < rows && c < cols) tile[ty + k][tx] = in[boff + (size_t)r * cols + c];
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + s + 16 * k, c = c0 + 4 * q;
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows) {
+      const float* p = in + (size_t)r * cols + c;
+      if (vin) {
+        if (c < cols) v[k] = __ldcs(reinterpret_cast<const float4*>(p));
+      } else {
+        if (c < cols) v[k].x = __ldcs(p);
+        if (c + 1 < cols) v[k].y = __ldcs(p + 1);
+        if (c + 2 < cols) v[k].z = __ldcs(p + 2);
+        if (c + 3 < cols) v[k].w = __ldcs(p + 3);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float* d = tile + (s + 16 * k) * TR_PITCH + 4 * q;
+    d[0] = v[k].x; d[1] = v[k].y; d[2] = v[k].z; d[3] = v[k].w;
   }
   __syncthreads();
+  // ---- store: thread (s, q) writes out rows (= in cols) c0+s+16k, in-rows r0+4q.. ----
 #pragma unroll
-  for (int k = 0; k < 32; k += 8) {
-    const int c = c0 + ty + k, r = r0 + tx;
-    if (r < rows && c < cols) out[boff + (size_t)c * rows + r] = tile[tx][ty + k];
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + s + 16 * k, r = r0 + 4 * q;
+    if (c >= cols || r >= rows) continue;
+    const float* sp = tile + (4 * q) * TR_PITCH + s + 16 * k;
+    const float4 o = make_float4(sp[0], sp[TR_PITCH], sp[2 * TR_PITCH], sp[3 * TR_PITCH]);
+    float* p = out + (size_t)c * rows + r;
+    if (vout) {
+      *reinterpret_cast<float4*>(p) = o;
+    } else {
+      p[0] = o.x;
+      if (r + 1 < rows) p[1] = o.y;
+      if (r + 2 < rows) p[2] = o.z;
+      if (r + 3 < rows) p[3] = o.w;
+    }
   }
+}
+
+// host launcher: n maps sharing `batch`; map i is (batch, rows[i], cols[i])
+inline int transpose_launch_multi(const float* const* in, float* const* out, int n,
+                                  int batch, const int* rows, const int* cols,
+                                  cudaStream_t stream) {
+  if (n <= 0 || n > BRCNN_MAX_LEVELS || batch <= 0 || !in || !out) return BRCNN_ERR_ARG;
+  TransposeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n; a.batch = batch;
+  long long base = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!in[i] || !out[i] || rows[i] <= 0 || cols[i] <= 0) return BRCNN_ERR_ARG;
+    TransposeMap& m = a.m[i];
+    m.in = in[i]; m.out = out[i]; m.rows = rows[i]; m.cols = cols[i];
+    m.tiles_x = (cols[i] + TR_TILE - 1) / TR_TILE;
+    m.tiles_y = (rows[i] + TR_TILE - 1) / TR_TILE;
+    m.tile_base = (int)base;
+    base += (long long)m.tiles_x * m.tiles_y * batch;
+    if (base > 0x7fffffffLL) return BRCNN_ERR_UNSUPPORTED;
+  }
+  transpose_multi_kernel<<<(unsigned)base, 256, 0, stream>>>(a);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
 }
 
 }  // namespace brcnn

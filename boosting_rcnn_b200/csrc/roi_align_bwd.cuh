@@ -13,7 +13,7 @@
 // summation order -> bit-reproducible.
 //
 //   roi_bwd_geom_kernel    per-RoI geometry (level, footprint box)
-//   transpose_kernel       grad_out (R,C,49) -> (R,49,C) so taps are 128-bit
+//   transpose_multi_kernel grad_out (R,C,49) -> (R,49,C) so taps are 128-bit
 //   roi_bwd_gather_kernel  the tile-owner gather
 #pragma once
 #include "common.cuh"
@@ -258,11 +258,11 @@ static inline int roi_bwd_launch(RoiArgs a, const float* grad_out, const float* 
     roi_bwd_geom_kernel<<<(R + 255) / 256, 256, 0, stream>>>(a, rois, R, geom);
     g_launch_count_add(1);
     BRCNN_CUDA_CHECK_LAST();
-    if (R > 65535) return BRCNN_ERR_UNSUPPORTED;
-    dim3 tg((nbins + 31) / 32, (a.C + 31) / 32, R);
-    transpose_kernel<<<tg, 256, 0, stream>>>(grad_out, gt, a.C, nbins);
-    g_launch_count_add(1);
-    BRCNN_CUDA_CHECK_LAST();
+    const float* tin[1] = {grad_out};
+    float* tout[1] = {gt};
+    const int trows[1] = {a.C}, tcols[1] = {nbins};
+    const int rc = transpose_launch_multi(tin, tout, 1, R, trows, tcols, stream);
+    if (rc) return rc;
   }
   dim3 grid(base, (a.C + BWD_CCH - 1) / BWD_CCH);
   if (grid.y > 65535) return BRCNN_ERR_UNSUPPORTED;

@@ -1,0 +1,126 @@
+"""CUDA-graph execution of the inference hot path for fixed shapes.
+
+The proposal-to-detection step is ~20 short kernels; launched one by one from
+Python it is host-bound (the kernels take ~1 ms, the launches ~1.5 ms).  The
+whole step is sync-free by construction (fixed-capacity buffers + device
+counters), so it captures into one CUDA graph:
+
+    g = HotPathGraph(rpn_head, roi_head, img_metas, feats, cls, box, iou, rescale=True)
+    det, lab, num = g.replay()          # reads the tensors given at capture time
+
+``HostPipeline`` puts two such graphs behind a double-buffered host->device
+copy stream so that the H2D of step i+1 overlaps the compute of step i; this
+is the end-to-end entry point for callers whose inputs live in host memory.
+"""
+import torch
+
+from . import _lib
+from .registry import ConfigDict
+
+
+class HotPathGraph:
+    """One captured pass RPN outputs + FPN maps -> detections over a batch.
+
+    The input tensors passed to the constructor are the graph's static inputs:
+    refill them in place (``copy_``) between replays."""
+
+    def __init__(self, rpn_head, roi_head, img_metas, feats, cls_scores, bbox_preds, iou_preds,
+                 rcnn_test_cfg=None, rescale=True, warmup=2, stream=None):
+        assert torch.cuda.is_available(), 'HotPathGraph needs a CUDA device'
+        lib = _lib.load()
+        self.inputs = (list(feats), list(cls_scores), list(bbox_preds), list(iou_preds))
+        cfg = ConfigDict(rcnn_test_cfg if rcnn_test_cfg is not None else roi_head.test_cfg)
+
+        @torch.no_grad()
+        def fn():
+            f, c, b, i = self.inputs
+            props = rpn_head.get_bboxes_padded(c, b, i, img_metas)
+            return roi_head.simple_test_bboxes_padded(f, img_metas, props, cfg, rescale=rescale)
+
+        self._fn = fn
+        cur = torch.cuda.current_stream()
+        side = stream if stream is not None else torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):   # allocator / cuBLAS / attribute warm-up
+                fn()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = lib.brcnn_launch_count()
+        with torch.cuda.graph(self.graph, stream=side):
+            self.outputs = fn()
+        #: libbrcnn kernels inside one replay (the rest are cuBLAS + bias adds)
+        self.launches_per_replay = int(lib.brcnn_launch_count() - l0)
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs
+
+    def eager(self):
+        return self._fn()
+
+
+class HostPipeline:
+    """Double-buffered end-to-end pipeline for host-resident inputs.
+
+    ``submit(feats, cls, box, iou)`` takes pinned host tensors, enqueues their
+    H2D copies on a copy stream, the graph replay on a compute stream and the
+    D2H of the detections into pinned host buffers; it returns a ticket whose
+    ``result()`` blocks until that step's detections are on the host.  With two
+    slots the copy of step i+1 overlaps the kernels of step i."""
+
+    def __init__(self, rpn_head, roi_head, img_metas, example, rcnn_test_cfg=None, rescale=True,
+                 slots=2):
+        dev = next(roi_head.parameters()).device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.compute_stream = torch.cuda.Stream(device=dev)
+        self.slots = []
+        for _ in range(slots):
+            bufs = tuple([torch.empty_like(t, device=dev) for t in ts] for ts in example)
+            g = HotPathGraph(rpn_head, roi_head, img_metas, *bufs, rcnn_test_cfg=rcnn_test_cfg,
+                             rescale=rescale, stream=self.compute_stream)
+            host_out = tuple(torch.empty_like(o, device='cpu').pin_memory() for o in g.outputs)
+            self.slots.append(dict(bufs=bufs, graph=g, host_out=host_out,
+                                   copied=torch.cuda.Event(), done=torch.cuda.Event(),
+                                   busy=False))
+        self.h2d_bytes = sum(t.numel() * t.element_size() for ts in example for t in ts)
+        self.d2h_bytes = sum(o.numel() * o.element_size() for o in self.slots[0]['host_out'])
+        self.launches_per_step = self.slots[0]['graph'].launches_per_replay
+        self._next = 0
+
+    class Ticket:
+        def __init__(self, slot):
+            self._slot = slot
+
+        def result(self):
+            self._slot['done'].synchronize()
+            self._slot['busy'] = False
+            return self._slot['host_out']
+
+    def submit(self, feats, cls_scores, bbox_preds, iou_preds):
+        s = self.slots[self._next]
+        self._next = (self._next + 1) % len(self.slots)
+        if s['busy']:
+            # the slot's previous step must have left the device before its
+            # input buffers are overwritten
+            s['done'].synchronize()
+        with torch.cuda.stream(self.copy_stream):
+            for dst, src in zip(s['bufs'], (feats, cls_scores, bbox_preds, iou_preds)):
+                for d, h in zip(dst, src):
+                    d.copy_(h, non_blocking=True)
+            s['copied'].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(s['copied'])
+            s['graph'].replay()
+            for h, o in zip(s['host_out'], s['graph'].outputs):
+                h.copy_(o, non_blocking=True)
+            s['done'].record(self.compute_stream)
+        s['busy'] = True
+        return HostPipeline.Ticket(s)
+
+    def drain(self):
+        for s in self.slots:
+            if s['busy']:
+                s['done'].synchronize()
+                s['busy'] = False

@@ -10,6 +10,7 @@ torch is plumbing here: it owns device memory and the current stream; every
 computation is a libbrcnn kernel.  CPU tensors are rejected (no fallback).
 """
 import math
+from ctypes import c_int32
 
 import numpy as np
 import torch
@@ -245,6 +246,78 @@ def nhwc_to_nchw(x):
     return out
 
 
+def _multi_transpose(fn_name, srcs, dst_shapes):
+    """One launch for a whole pyramid: srcs are contiguous fp32 CUDA tensors
+    sharing batch and channel counts."""
+    lib = _lib.load()
+    outs = [torch.empty(sh, dtype=torch.float32, device=srcs[0].device) for sh in dst_shapes]
+    B = srcs[0].shape[0]
+    if fn_name == 'brcnn_nchw_to_nhwc_multi':
+        C = srcs[0].shape[1]
+        hw = [s.shape[2] * s.shape[3] for s in srcs]
+    else:
+        C = srcs[0].shape[3]
+        hw = [s.shape[1] * s.shape[2] for s in srcs]
+    hw_arr = (c_int32 * len(hw))(*hw)
+    check(getattr(lib, fn_name)(ptr_array([s.data_ptr() for s in srcs]),
+                                ptr_array([o.data_ptr() for o in outs]), len(srcs), B, C,
+                                hw_arr, _stream()), fn_name)
+    return outs
+
+
+def pyramid_to_nhwc(feats):
+    """list of (B,C,H,W) maps -> list of NHWC-contiguous (B,H,W,C) tensors.
+    channels_last maps are free views; all NCHW-contiguous ones are converted
+    by ONE multi-map transpose launch."""
+    out = [None] * len(feats)
+    todo = []
+    for i, f in enumerate(feats):
+        assert f.dim() == 4
+        if not f.is_cuda:
+            raise RuntimeError('pyramid_to_nhwc: CUDA tensors required (no CPU path)')
+        if f.dtype != torch.float32:
+            f = f.float()
+        fp = f.permute(0, 2, 3, 1)
+        if fp.is_contiguous():
+            out[i] = fp
+        else:
+            todo.append((i, f.contiguous()))
+    same = len({(f.shape[0], f.shape[1]) for _, f in todo}) == 1
+    if todo and same and len(todo) <= _lib.MAX_LEVELS:
+        srcs = [f for _, f in todo]
+        res = _multi_transpose('brcnn_nchw_to_nhwc_multi', srcs,
+                               [(f.shape[0], f.shape[2], f.shape[3], f.shape[1]) for f in srcs])
+        for (i, _), r in zip(todo, res):
+            out[i] = r
+    else:
+        for i, f in todo:
+            out[i] = to_nhwc(f)
+    return out
+
+
+def pyramid_to_nchw(grads_nhwc):
+    """list of NHWC-contiguous (B,H,W,C) -> NCHW-contiguous (B,C,H,W), one launch."""
+    if not grads_nhwc:
+        return []
+    return _multi_transpose('brcnn_nhwc_to_nchw_multi', grads_nhwc,
+                            [(g.shape[0], g.shape[3], g.shape[1], g.shape[2]) for g in grads_nhwc])
+
+
+def bbox2roi_padded(proposals, num):
+    """Padded proposals (B,cap,5) + num (B) int32 -> rois (B*cap,5) with
+    b = -1 padding rows, prior (B*cap).  One kernel (bbox2roi, transforms.py:59-78)."""
+    proposals = _f32c(proposals, 'proposals')
+    assert proposals.dim() == 3 and proposals.size(2) == 5
+    assert num.dtype == torch.int32 and num.is_cuda
+    B, cap = proposals.shape[:2]
+    rois = torch.empty((B * cap, 5), dtype=torch.float32, device=proposals.device)
+    prior = torch.empty((B * cap,), dtype=torch.float32, device=proposals.device)
+    check(_lib.load().brcnn_bbox2roi_padded(proposals.data_ptr(), num.contiguous().data_ptr(),
+                                            B, cap, rois.data_ptr(), prior.data_ptr(),
+                                            _stream()), 'brcnn_bbox2roi_padded')
+    return rois, prior
+
+
 def map_roi_levels(rois, num_levels, finest_scale=56):
     rois = _f32c(rois, 'rois')
     out = torch.empty((rois.size(0),), dtype=torch.int64, device=rois.device)
@@ -268,7 +341,7 @@ class _RoiExtractFunction(Function):
         sizes = [tuple(f.shape[-2:]) for f in feats]
         p = make_roi_params(B, C, sizes, spatial_scales, output_size,
                             sampling_ratio, aligned, finest_scale)
-        nhwc = [to_nhwc(f) for f in feats]
+        nhwc = pyramid_to_nhwc(feats)
         R = rois.size(0)
         out = torch.empty((R, C, p.pooled_h, p.pooled_w), dtype=torch.float32,
                           device=rois.device)
@@ -298,11 +371,11 @@ class _RoiExtractFunction(Function):
             p, grad_out.data_ptr(), rois.data_ptr(), R,
             ptr_array([g.data_ptr() for g in grads]), ws.data_ptr(), ws.numel(),
             _stream()), 'brcnn_roi_extract_backward')
-        outs = []
-        for g, cl in zip(grads, ctx.channels_last):
-            # channels_last inputs get a channels_last gradient for free;
-            # NCHW-contiguous inputs get an NCHW-contiguous one.
-            outs.append(g.permute(0, 3, 1, 2) if cl else nhwc_to_nchw(g))
+        # channels_last inputs get a channels_last gradient for free;
+        # NCHW-contiguous inputs get an NCHW-contiguous one (one launch).
+        need = [i for i, cl in enumerate(ctx.channels_last) if not cl]
+        conv = dict(zip(need, pyramid_to_nchw([grads[i] for i in need])))
+        outs = [conv[i] if i in conv else g.permute(0, 3, 1, 2) for i, g in enumerate(grads)]
         return (None, None, None, None, None, None, *outs)
 
 

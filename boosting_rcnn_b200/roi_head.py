@@ -166,8 +166,7 @@ class ProbRoIHead(nn.Module):
         if not isinstance(proposals, PaddedProposals):
             proposals = pad_proposals(proposals)
         B, cap = proposals.boxes.shape[:2]
-        rois = padded_rois(proposals)
-        prior = proposals.boxes[..., 4].reshape(-1).contiguous()
+        rois, prior = ops.bbox2roi_padded(proposals.boxes, proposals.num)
         bbox_results = self._bbox_forward(x, rois)
         hw, sf = self._img_consts(img_metas, rois.device)
         p = self.bbox_head.rcnn_params(B, cap, ConfigDict(rcnn_test_cfg), self.prob, rescale)

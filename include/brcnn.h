@@ -145,6 +145,14 @@ typedef struct brcnn_roi_params {
   float finest_scale;                    /* 56                               */
 } brcnn_roi_params;
 
+/* bbox2roi (mmdet/core/bbox/transforms.py:59-78) on the padded proposal
+ * layout of brcnn_rpn_get_bboxes: proposals (B,cap,5) + num (B) ->
+ * rois (B*cap,5) [b,x1,y1,x2,y2] with b = -1 on padding rows, and (optional)
+ * prior (B*cap) = proposals[..., 4] (prob_roi_head.py:214).                  */
+int brcnn_bbox2roi_padded(const float* proposals, const int32_t* num_proposals,
+                          int32_t batch, int32_t cap, float* rois, float* prior,
+                          brcnn_stream_t stream);
+
 /* target_lvls of map_roi_levels: int64[R] */
 int brcnn_map_roi_levels(const float* rois, int32_t num_rois,
                          float finest_scale, int32_t num_levels,
@@ -177,6 +185,14 @@ int brcnn_nchw_to_nhwc(const float* in, float* out, int32_t batch,
                        int32_t channels, int32_t hw, brcnn_stream_t stream);
 int brcnn_nhwc_to_nchw(const float* in, float* out, int32_t batch,
                        int32_t channels, int32_t hw, brcnn_stream_t stream);
+/* the same for up to BRCNN_MAX_LEVELS maps in ONE launch (the whole pyramid):
+ * host arrays of device pointers; map i is (batch, channels, hw_host[i])    */
+int brcnn_nchw_to_nhwc_multi(const float* const* in_host, float* const* out_host,
+                             int32_t num_maps, int32_t batch, int32_t channels,
+                             const int32_t* hw_host, brcnn_stream_t stream);
+int brcnn_nhwc_to_nchw_multi(const float* const* in_host, float* const* out_host,
+                             int32_t num_maps, int32_t batch, int32_t channels,
+                             const int32_t* hw_host, brcnn_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * (4) Boosting reweighted R-CNN loss, forward + gradient in one pass

@@ -133,3 +133,93 @@ def test_layout_helpers_roundtrip(cuda):
     assert y.shape == (3, 13, 21, 20) and y.is_contiguous()
     assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
     assert torch.equal(ops.nhwc_to_nchw(y), x)
+
+
+@pytest.mark.parametrize('B,C,sizes', [
+    (2, 256, [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]),   # UTDAC pyramid
+    (3, 20, [(13, 21), (5, 3), (1, 1)]),                              # odd hw, C % 64 != 0
+    (1, 68, [(64, 64), (9, 130)]),
+])
+def test_pyramid_transposes_one_launch(cuda, B, C, sizes):
+    from boosting_rcnn_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device='cpu').manual_seed(B * 1000 + C)
+    feats = [torch.randn(B, C, h, w, generator=g).to(cuda) for h, w in sizes]
+    l0 = lib.brcnn_launch_count()
+    nhwc = ops.pyramid_to_nhwc(feats)
+    assert lib.brcnn_launch_count() - l0 == 1
+    for f, y in zip(feats, nhwc):
+        assert y.is_contiguous() and torch.equal(y, f.permute(0, 2, 3, 1).contiguous())
+    back = ops.pyramid_to_nchw(nhwc)
+    for f, y in zip(feats, back):
+        assert y.is_contiguous() and torch.equal(y, f)
+    # channels_last inputs are free views (no launch)
+    cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    l0 = lib.brcnn_launch_count()
+    views = ops.pyramid_to_nhwc(cl)
+    assert lib.brcnn_launch_count() == l0
+    assert all(v.data_ptr() == f.data_ptr() for v, f in zip(views, cl))
+
+
+def test_bbox2roi_padded_matches_reference_bbox2roi(cuda):
+    from boosting_rcnn_b200.roi_head import padded_rois
+    from boosting_rcnn_b200.rpn_head import PaddedProposals
+    g = torch.Generator().manual_seed(5)
+    boxes = torch.rand(4, 37, 5, generator=g).to(cuda) * 300
+    num = torch.tensor([37, 0, 5, 36], dtype=torch.int32, device=cuda)
+    rois, prior = ops.bbox2roi_padded(boxes, num)
+    assert torch.equal(rois, padded_rois(PaddedProposals(boxes, num)))
+    assert torch.equal(prior, boxes[..., 4].reshape(-1))
+
+
+def test_roi_forward_wide_footprints_multi_pass(cuda):
+    # elongated RoIs: footprints wider than one ring slot -> several x-chunk
+    # passes of the TMA row-streaming kernel; also whole-image RoIs
+    ex = [[0, 2, 100, 1330, 160], [1, 0, 0, 1333, 800], [0, 10, 300, 1300, 330],
+          [1, 600, 2, 660, 798], [0, 0, 0, 1344, 60], [1, 3, 3, 900, 120]]
+    _case(cuda, 2, (800, 1344), 256, 20, seed=21, extra_rois=np.array(ex, dtype=np.float32))
+
+
+@pytest.mark.parametrize('C', [4, 64, 320, 516])
+def test_roi_forward_channel_slabs(cuda, C):
+    # C < 256 (partial slab), C > 256 (several slabs, strided per-pixel TMA copies)
+    _case(cuda, 2, (256, 320), C, 30, seed=30 + C)
+
+
+def test_roi_forward_pooled_sizes(cuda):
+    # non-7x7 outputs: 5x3 on the TMA kernel, 14x14 on the register-tile kernel
+    feat = synth.fpn_feats(2, 32, [(50, 84)], seed=4)[0]
+    rois = synth.random_rois(2, 25, 800, 1344, seed=12)
+    tf, tr = torch.from_numpy(feat).to(cuda), torch.from_numpy(rois).to(cuda)
+    for osz in [(5, 3), (14, 14), (1, 1)]:
+        out = ops.roi_align(tf, tr, osz, 1 / 16)
+        _close(out.cpu().numpy(), oracle.roi_align_forward(feat, rois, osz, 1 / 16), f'out {osz}')
+
+
+def test_roi_forward_v1_and_v2_kernels_agree(cuda):
+    """BRCNN_ROI_FWD=v1 (register-tile kernel) vs the default TMA kernel: run in
+    a subprocess because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = '''
+import sys, numpy as np, torch
+sys.path[:0] = [%r, %r]
+import synth
+from boosting_rcnn_b200 import ops
+sizes = synth.featmap_sizes(800, 1344)
+feats = [torch.from_numpy(f).cuda() for f in synth.fpn_feats(1, 256, sizes, seed=7)]
+rois = torch.from_numpy(synth.random_rois(1, 300, 800, 1344, seed=8)).cuda()
+out = ops.roi_extract(feats, rois, [1.0 / s for s in synth.STRIDES], 7)
+np.save(sys.argv[1], out.cpu().numpy())
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+       os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for mode in ('v1', 'v2'):
+            path = os.path.join(d, mode + '.npy')
+            env = dict(os.environ, BRCNN_ROI_FWD=mode)
+            subprocess.run([sys.executable, '-c', code, path], check=True, env=env)
+            outs.append(np.load(path))
+    _close(outs[0], outs[1], 'v1 vs v2')
