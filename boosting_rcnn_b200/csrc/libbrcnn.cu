@@ -495,7 +495,7 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
       return e && e[0] == 'v' && e[1] == '1';
     }();
     const int chunk = a.C < 4 * RT_SLAB_Q ? a.C : 4 * RT_SLAB_Q;
-    const size_t tables = ((size_t)a.max_h * 8 + (size_t)8 * a.max_w) * 4 + (size_t)a.max_h * 4;
+    const size_t tables = ((size_t)a.max_h * 8 + (size_t)8 * a.max_w) * 4;
     const size_t budget = 110 * 1024;  // two CTAs per SM
     size_t ring = 96 * 1024;
     if (tables + ring > budget) ring = tables < budget ? ((budget - tables) & ~(size_t)127) : 0;

@@ -13,11 +13,12 @@
 //     completion signalled on a per-slot mbarrier.  Up to 96 KB of loads are in
 //     flight per CTA with zero registers spent on them; every footprint pixel
 //     crosses L2->SM exactly once.
-//   * 14 consumer warps = 7 pooled columns (pw) x 2 half-slabs of 32 channel
-//     quads.  Per row a thread forms h = sum_{x in band(pw)} Wx[pw][x]*F[y][x]
-//     (128-bit conflict-free LDS, warp-uniform weights), releases the slot,
-//     then folds h into the 1-3 pooled rows whose Wy[.][y] is non-zero
-//     (register accumulators acc[7]).
+//   * 7 consumer warps = the 7 pooled columns (pw); a lane owns two channel
+//     quads (lane, lane+32).  Per row a thread forms
+//     h = sum_{x in band(pw)} Wx[pw][x]*F[y][x] (128-bit conflict-free LDS,
+//     warp-uniform weights), releases the slot, then folds h into the 7 pooled
+//     rows with the row's Wy[.][y] (zero outside the band; branch-free, two
+//     128-bit weight loads) in register accumulators.
 //   * The (c, ph, pw) result is staged in the (now idle) ring and leaves the
 //     SM as one `cp.async.bulk` shared->global store of C*49*4 bytes.
 // Wide footprints (fw*C*4 too large for >= 3 slots) are processed in several
@@ -29,10 +30,10 @@
 namespace brcnn {
 
 constexpr int RT_P = 7;                       // max pooled side on this path
-constexpr int RT_CONS_WARPS = 2 * RT_P;       // (pw, half-slab)
+constexpr int RT_CONS_WARPS = RT_P;           // one consumer warp per pooled column
 constexpr int RT_THREADS = (RT_CONS_WARPS + 1) * 32;
 constexpr int RT_MAX_STAGES = 8;
-constexpr int RT_SLAB_Q = 64;                 // channel quads per CTA (256 channels)
+constexpr int RT_SLAB_Q = 64;                 // channel quads per CTA (2 per lane)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -49,6 +50,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
   uint32_t ok;
   do {
     asm volatile(
@@ -75,16 +89,16 @@ __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-// dynamic smem: ring_bytes | wy [max_h][8] | wx [8][max_w] | rowpk [max_h]
+// dynamic smem: ring_bytes | wy [max_h][8] | wx [8][max_w]
 __global__ void __launch_bounds__(RT_THREADS, 2)
 roi_align_fwd_tma_kernel(const __grid_constant__ RoiArgs a, const float* __restrict__ rois,
                          int R, float* __restrict__ out, int32_t* __restrict__ roi_levels,
                          int ring_bytes) {
   extern __shared__ __align__(128) unsigned char rt_smem[];
   float* ring = reinterpret_cast<float*>(rt_smem);
-  float* wy = reinterpret_cast<float*>(rt_smem + ring_bytes);   // [fh][8]   (1/count folded in)
+  float* wy = reinterpret_cast<float*>(rt_smem + ring_bytes);   // [fh][8], 1/count folded in,
+                                                                 // zero outside the row's band
   float* wx = wy + (size_t)a.max_h * 8;                          // [pw][max_w]
-  int* rowpk = reinterpret_cast<int*>(wx + (size_t)8 * a.max_w); // [fh] first | last<<8 pooled row
   __shared__ __align__(8) uint64_t full_bar[RT_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[RT_MAX_STAGES];
   __shared__ int s_xs[8], s_xe[8];
@@ -117,12 +131,16 @@ roi_align_fwd_tma_kernel(const __grid_constant__ RoiArgs a, const float* __restr
   // ---- ring geometry (block-uniform) ----
   const int px_bytes = cc * 4;
   const int cw_max = max(1, (ring_bytes / 3) / px_bytes);   // >= 3 slots
-  const int npass = (fw + cw_max - 1) / cw_max;
-  const int cw = (fw + npass - 1) / npass;                  // pixels per slot
+  int npass = 1, cw = fw;
+  if (fw > cw_max) {
+    npass = (fw + cw_max - 1) / cw_max;
+    cw = (fw + npass - 1) / npass;                          // pixels per slot
+  }
   const int slot_bytes = ((cw * px_bytes) + 127) & ~127;
-  const int NS = min(RT_MAX_STAGES, ring_bytes / slot_bytes);
+  int NS = RT_MAX_STAGES;
+  while (NS * slot_bytes > ring_bytes) --NS;
   const int slot_floats = slot_bytes >> 2;
-  const int niter = npass * fh;
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -137,12 +155,12 @@ roi_align_fwd_tma_kernel(const __grid_constant__ RoiArgs a, const float* __restr
     // =========================== producer warp ===========================
     const float* fbase = a.feat[g.lvl] + ((size_t)g.b * g.H * g.W) * a.C + c0;
     const bool contiguous = (cc == a.C);
-    int s = 0, round = 0, it = 0;
+    int s = 0, round = 0;
     for (int pass = 0; pass < npass; ++pass) {
       const int x0 = pass * cw;
       const int cwe = min(cw, fw - x0);
-      for (int dy = 0; dy < fh; ++dy, ++it) {
-        if (round > 0) mbar_wait(&empty_bar[s], (uint32_t)((round - 1) & 1));
+      for (int dy = 0; dy < fh; ++dy) {
+        if (round > 0) mbar_wait_addr(empty0 + 8u * s, (uint32_t)((round - 1) & 1));
         const float* src = fbase + ((size_t)(ylo + dy) * g.W + xlo + x0) * a.C;
         float* slot = ring + (size_t)s * slot_floats;
         if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(cwe * px_bytes));
@@ -159,78 +177,74 @@ roi_align_fwd_tma_kernel(const __grid_constant__ RoiArgs a, const float* __restr
     }
   } else {
     // =========================== consumer warps ==========================
-    const int ctid = tid;  // 0 .. 447
+    constexpr int NCT = RT_CONS_WARPS * 32;
     // separable weight tables (built while the first rows are in flight)
-    for (int i = ctid; i < a.PH * fh; i += RT_CONS_WARPS * 32) {
-      const int dy = i / a.PH, ph = i - dy * a.PH;
-      wy[dy * 8 + ph] =
-          roi_axis_weight(g.start_h, g.bin_h, g.gh, g.H, ph, ylo + dy) * g.inv_count;
+    for (int i = tid; i < 8 * fh; i += NCT) {
+      const int dy = i >> 3, ph = i & 7;
+      wy[i] = (ph < a.PH)
+          ? roi_axis_weight(g.start_h, g.bin_h, g.gh, g.H, ph, ylo + dy) * g.inv_count : 0.f;
     }
-    for (int i = ctid; i < a.PW * fw; i += RT_CONS_WARPS * 32) {
+    for (int i = tid; i < a.PW * fw; i += NCT) {
       const int pw = i / fw, dx = i - pw * fw;
       wx[pw * a.max_w + dx] = roi_axis_weight(g.start_w, g.bin_w, g.gw, g.W, pw, xlo + dx);
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(RT_CONS_WARPS * 32) : "memory");
-    for (int dy = ctid; dy < fh; dy += RT_CONS_WARPS * 32) {
-      int pa = a.PH, pb = -1;
-      for (int ph = 0; ph < a.PH; ++ph)
-        if (wy[dy * 8 + ph] != 0.f) { pa = min(pa, ph); pb = ph; }
-      rowpk[dy] = (pb < 0) ? (1 | (0 << 8)) : (pa | (pb << 8));   // empty: pa=1 > pb=0
-    }
-    if (ctid >= 64 && ctid < 64 + a.PW) {
-      const int pw = ctid - 64;
+    asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
+    if (tid < a.PW) {
       int xs = fw, xe = -1;
       for (int dx = 0; dx < fw; ++dx)
-        if (wx[pw * a.max_w + dx] != 0.f) { xs = min(xs, dx); xe = dx; }
-      s_xs[pw] = xs; s_xe[pw] = xe;
+        if (wx[tid * a.max_w + dx] != 0.f) { xs = min(xs, dx); xe = dx; }
+      s_xs[tid] = xs; s_xe[tid] = xe;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(RT_CONS_WARPS * 32) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
 
-    const int pw = warp >> 1;
-    const int q = ((warp & 1) << 5) | lane;
-    const bool active = (pw < a.PW) && (q < ncq);
-    float4 acc[RT_P];
+    const int pw = warp;
+    const bool act0 = (pw < a.PW) && (lane < ncq);
+    const bool act1 = (pw < a.PW) && (lane + 32 < ncq);
+    float4 acc0[RT_P], acc1[RT_P];
 #pragma unroll
-    for (int i = 0; i < RT_P; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int bxs = active ? s_xs[pw] : 1, bxe = active ? s_xe[pw] : 0;
-    const float* wxp = wx + (size_t)(active ? pw : 0) * a.max_w;
+    for (int i = 0; i < RT_P; ++i) {
+      acc0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      acc1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int bxs = act0 ? s_xs[pw] : 1, bxe = act0 ? s_xe[pw] : 0;
+    const float* wxp = wx + (size_t)(act0 ? pw : 0) * a.max_w;
+    const int q1 = act1 ? lane + 32 : lane;   // inactive second quad re-reads the first
 
     int s = 0, round = 0;
     for (int pass = 0; pass < npass; ++pass) {
       const int x0 = pass * cw;
       const int cwe = min(cw, fw - x0);
       const int xs = max(bxs, x0), xe = min(bxe, x0 + cwe - 1);
-      const bool work = active && (xs <= xe);
+      const bool work = act0 && (xs <= xe);
       for (int dy = 0; dy < fh; ++dy) {
-        mbar_wait(&full_bar[s], (uint32_t)(round & 1));
-        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait_addr(full0 + 8u * s, (uint32_t)(round & 1));
+        float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
         if (work) {
-          const float4* rowq =
-              reinterpret_cast<const float4*>(ring + (size_t)s * slot_floats) + q;
+          const float4* rowq = reinterpret_cast<const float4*>(ring + (size_t)s * slot_floats);
           for (int x = xs; x <= xe; ++x) {
-            const float4 v = rowq[(size_t)(x - x0) * ncq];
+            const float4* px = rowq + (x - x0) * ncq;
+            const float4 v0 = px[lane];
+            const float4 v1 = px[q1];
             const float w = wxp[x];
-            h.x = fmaf(w, v.x, h.x);
-            h.y = fmaf(w, v.y, h.y);
-            h.z = fmaf(w, v.z, h.z);
-            h.w = fmaf(w, v.w, h.w);
+            h0.x = fmaf(w, v0.x, h0.x); h0.y = fmaf(w, v0.y, h0.y);
+            h0.z = fmaf(w, v0.z, h0.z); h0.w = fmaf(w, v0.w, h0.w);
+            h1.x = fmaf(w, v1.x, h1.x); h1.y = fmaf(w, v1.y, h1.y);
+            h1.z = fmaf(w, v1.z, h1.z); h1.w = fmaf(w, v1.w, h1.w);
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (lane == 0) mbar_arrive_addr(empty0 + 8u * s);
         if (work) {
-          const int pk = rowpk[dy];
-          const int pa = pk & 0xff, pb = pk >> 8;
-          const float* wrow = wy + dy * 8;
+          const float4 wa = *reinterpret_cast<const float4*>(wy + dy * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(wy + dy * 8 + 4);
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
           for (int ph = 0; ph < RT_P; ++ph) {
-            if (ph >= pa && ph <= pb) {
-              const float w = wrow[ph];
-              acc[ph].x = fmaf(w, h.x, acc[ph].x);
-              acc[ph].y = fmaf(w, h.y, acc[ph].y);
-              acc[ph].z = fmaf(w, h.z, acc[ph].z);
-              acc[ph].w = fmaf(w, h.w, acc[ph].w);
-            }
+            const float w = wv[ph];
+            acc0[ph].x = fmaf(w, h0.x, acc0[ph].x); acc0[ph].y = fmaf(w, h0.y, acc0[ph].y);
+            acc0[ph].z = fmaf(w, h0.z, acc0[ph].z); acc0[ph].w = fmaf(w, h0.w, acc0[ph].w);
+            acc1[ph].x = fmaf(w, h1.x, acc1[ph].x); acc1[ph].y = fmaf(w, h1.y, acc1[ph].y);
+            acc1[ph].z = fmaf(w, h1.z, acc1[ph].z); acc1[ph].w = fmaf(w, h1.w, acc1[ph].w);
           }
         }
         if (++s == NS) { s = 0; ++round; }
@@ -238,16 +252,28 @@ roi_align_fwd_tma_kernel(const __grid_constant__ RoiArgs a, const float* __restr
     }
     // every slot has been consumed by this warp; wait for the other consumers
     // before the ring is reused as the output stage
-    asm volatile("bar.sync 1, %0;" ::"n"(RT_CONS_WARPS * 32) : "memory");
-    if (active) {
-      float* st = ring + (size_t)(q * 4) * nbins + pw;
+    asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
+    if (act0) {
+      float* st = ring + (size_t)(lane * 4) * nbins + pw;
 #pragma unroll
       for (int ph = 0; ph < RT_P; ++ph) {
         if (ph < a.PH) {
-          st[ph * a.PW] = acc[ph].x;
-          st[nbins + ph * a.PW] = acc[ph].y;
-          st[2 * nbins + ph * a.PW] = acc[ph].z;
-          st[3 * nbins + ph * a.PW] = acc[ph].w;
+          st[ph * a.PW] = acc0[ph].x;
+          st[nbins + ph * a.PW] = acc0[ph].y;
+          st[2 * nbins + ph * a.PW] = acc0[ph].z;
+          st[3 * nbins + ph * a.PW] = acc0[ph].w;
+        }
+      }
+    }
+    if (act1) {
+      float* st = ring + (size_t)((lane + 32) * 4) * nbins + pw;
+#pragma unroll
+      for (int ph = 0; ph < RT_P; ++ph) {
+        if (ph < a.PH) {
+          st[ph * a.PW] = acc1[ph].x;
+          st[nbins + ph * a.PW] = acc1[ph].y;
+          st[2 * nbins + ph * a.PW] = acc1[ph].z;
+          st[3 * nbins + ph * a.PW] = acc1[ph].w;
         }
       }
     }
@@ -258,7 +284,6 @@ roi_align_fwd_tma_kernel(const __grid_constant__ RoiArgs a, const float* __restr
     tma_store_1d(dst, ring, (uint32_t)(total * 4));
     tma_store_wait_read();
   }
-  (void)niter;
 }
 
 }  // namespace brcnn
