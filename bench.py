@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=16, help='images per GPU per step')
     ap.add_argument('--cfg', default='utdac', choices=['utdac', 'coco', 'voc'])
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'stress'],
+                    help='infer: configs[1] (the headline); train: configs[2] training step '
+                         '(use --cfg coco --batch 2); stress: configs[4] proposal stress test')
     ap.add_argument('--cpu-images', type=int, default=0,
                     help='images in the CPU-baseline sample (0: one per host thread, <= 16)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -196,6 +199,265 @@ def roi_footprint_bytes(rois, sizes, channels, finest=56.0):
     return tot
 
 
+# ----------------------------------------------------------------------------
+# secondary workloads (not the headline line; same JSON contract)
+# ----------------------------------------------------------------------------
+def _dev_time(fn, reps, dev, flush_mb=256):
+    """mean device ms of fn() over reps, L2 flushed before each rep"""
+    flush = torch.empty(flush_mb << 20, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+
+def _peak():
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def _dist_setup(world, dev):
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+        return dist
+    return None
+
+
+def _timed_steps(fn, K, W, world, dist, dev):
+    for _ in range(W):
+        fn()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        fn()
+    e1.record()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def bench_train(args, rank, world, local_rank):
+    """configs[2]: R-CNN training step on B200-generated proposals: train-cfg
+    proposal generation (nms_pre 4000 / 2000 per image), assign + sample (host
+    logic of the reference), RoIAlign forward, 2-fc head,
+    boost loss, backward (head GEMMs on cuBLAS, RoIAlign backward gather),
+    NCCL all-reduce of the head gradients + one fused scalar all-reduce."""
+    from boosting_rcnn_b200 import _lib, configs, ops
+    from boosting_rcnn_b200 import dist as bdist
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    dist = _dist_setup(world, dev)
+    lib = _lib.load()
+    geom = configs.IMAGE_GEOMETRY[args.cfg]
+    B = args.batch
+    torch.manual_seed(0)
+    rpn_head, roi_head, model = configs.build_hot_path(args.cfg, train=True)
+    rpn_head, roi_head = rpn_head.to(dev).eval(), roi_head.to(dev).train()
+    A, C = rpn_head.num_anchors, roi_head.bbox_roi_extractor.out_channels
+    NC = roi_head.bbox_head.num_classes
+    sizes, h_feats, h_cls, h_box, h_iou = make_inputs(B, geom['pad_shape'][:2], A, C,
+                                                      seed=4321 + rank, pin=False)
+    metas = img_metas_for(B, geom)
+    feats = [t.to(dev).requires_grad_(True) for t in h_feats]
+    cls, box, iou = ([t.to(dev) for t in ts] for ts in (h_cls, h_box, h_iou))
+    rng = np.random.RandomState(77 + rank)
+    gts, labels = [], []
+    for b in range(B):
+        n = int(rng.randint(1, 21))
+        wh = rng.uniform(16, 400, (n, 2))
+        ctr = rng.uniform(0, 1, (n, 2)) * [geom['img_shape'][1], geom['img_shape'][0]]
+        g = np.concatenate([ctr - wh / 2, ctr + wh / 2], 1)
+        g[:, 0::2] = g[:, 0::2].clip(0, geom['img_shape'][1])
+        g[:, 1::2] = g[:, 1::2].clip(0, geom['img_shape'][0])
+        gts.append(torch.from_numpy(g.astype(np.float32)).to(dev))
+        labels.append(torch.from_numpy(rng.randint(0, NC, n)).to(dev))
+    prop_cfg = model['train_cfg']['rpn_proposal']
+    params = [p for p in roi_head.parameters() if p.requires_grad]
+    scal = {}
+
+    def step():
+        for p in params:
+            p.grad = None
+        for f in feats:
+            f.grad = None
+        with torch.no_grad():
+            plist = rpn_head.get_bboxes(cls, box, iou, metas, cfg=prop_cfg)
+        losses = roi_head.forward_train(feats, metas, plist, gts, labels)
+        (losses['loss_cls'] + losses['loss_bbox']).backward()
+        if world > 1:
+            # one flat bucket (the head has ~14M parameters): all-reduce, average, scatter back
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat /= world
+            off = 0
+            for p in params:
+                n = p.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                off += n
+        scal.update(bdist.fused_scalar_allreduce({k: v.detach() for k, v in losses.items()}))
+
+    K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = lib.brcnn_launch_count()
+    ms = _timed_steps(step, K, W, world, dist, dev)
+    launches = (lib.brcnn_launch_count() - l0) * K // (K + W)
+    clocks = sampler.stop() if sampler else None
+    out = None
+    if rank == 0:
+        peak, peak_src = _peak()
+        # stage device times on fixed sampled RoIs
+        with torch.no_grad():
+            plist = rpn_head.get_bboxes(cls, box, iou, metas, cfg=prop_cfg)
+        rois = torch.cat([torch.cat([p.new_full((min(512, p.size(0)), 1), float(b)),
+                                     p[:512, :4]], 1) for b, p in enumerate(plist)])
+        R = rois.size(0)
+        scales = [1.0 / s_ for s_ in STRIDES]
+        nhwc = [f.detach().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True)
+                for f in feats]
+        rf = ops.roi_extract(nhwc, rois, scales, 7)
+        go = torch.randn_like(rf)
+        cs = torch.randn(R, NC + 1, device=dev)
+        bp = torch.randn(R, 4 * NC, device=dev)
+        lab = torch.randint(0, NC + 1, (R,), device=dev)
+        lw = torch.ones(R, device=dev)
+        pr = torch.rand(R, device=dev)
+        bt, bw = torch.randn(R, 4, device=dev), (lab < NC).float()[:, None].expand(R, 4).contiguous()
+        st = {
+            'rpn_get_bboxes_train_cfg': _dev_time(
+                lambda: rpn_head.get_bboxes_padded(cls, box, iou, metas, cfg=prop_cfg), 10, dev),
+            'roi_align_fwd': _dev_time(lambda: ops.roi_extract(nhwc, rois, scales, 7), 10, dev),
+            'roi_align_bwd': _dev_time(
+                lambda: torch.autograd.grad(ops.roi_extract(nhwc, rois, scales, 7), nhwc, go), 10, dev),
+            'boost_loss_fwd_bwd': _dev_time(
+                lambda: ops.boost_loss(cs, bp, lab, lw, pr, bt, bw, NC, False, 0.5, 0.0, 2.0, 2.0,
+                                       False), 10, dev),
+        }
+        st['roi_align_bwd'] -= st['roi_align_fwd']
+        feat_bytes = sum(f.numel() * 4 for f in feats)
+        bwd_bytes = R * C * 49 * 4 + feat_bytes
+        ach = bwd_bytes / (st['roi_align_bwd'] * 1e-3) / 1e9
+        roof = dict(kernel='roi_bwd_gather_kernel (+ geometry, grad_out transpose)', bound='hbm',
+                    achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,
+                    peak_source=peak_src, algorithmic_bytes_per_launch=bwd_bytes,
+                    ms_per_launch=st['roi_align_bwd'])
+        out = {
+            'metric': 'RoI-path training images/s @1333x800', 'value': B * world * K / (ms * 1e-3),
+            'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': dict(workload=f'boosting_rcnn {args.cfg} R-CNN training step, {B} synthetic '
+                                    f'1333x800 images per GPU, 512 sampled RoIs/img',
+                           images_per_gpu=B, rpn_proposal=prop_cfg, rcnn=model['train_cfg']['rcnn'],
+                           parallelism=f'image-sharded x{world}; NCCL all-reduce of head grads + '
+                                       f'one fused scalar all-reduce',
+                           note='eager (assign/sample is the reference host logic with its syncs)'),
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'stages_ms': st,
+            'losses': {k: float(v) for k, v in scal.items()},
+        }
+        print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_stress(args, rank, world, local_rank):
+    """configs[4]: 5 levels x 4000 pre-NMS boxes per image, batched NMS
+    (ids = level, IoU 0.7), keep 2000, then 2000 RoIs/img through RoIAlign."""
+    from boosting_rcnn_b200 import _lib, ops
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    dist = _dist_setup(world, dev)
+    lib = _lib.load()
+    B, C = args.batch, 256
+    pad_hw, img_hw = (800, 1344), (800, 1333)
+    sizes = [(-(-pad_hw[0] // s), -(-pad_hw[1] // s)) for s in STRIDES]
+    rng = np.random.RandomState(99 + rank)
+    boxes, scores, ids = [], [], []
+    for b in range(B):
+        bl, il = [], []
+        for l in range(5):
+            ctr = rng.rand(4000, 2) * [img_hw[1], img_hw[0]]
+            wh = np.exp(rng.uniform(np.log(8 * 2 ** l), np.log(64 * 2 ** l), (4000, 2)))
+            bx = np.concatenate([ctr - wh / 2, ctr + wh / 2], 1)
+            bx[:, 0::2] = bx[:, 0::2].clip(0, img_hw[1])
+            bx[:, 1::2] = bx[:, 1::2].clip(0, img_hw[0])
+            bl.append(bx)
+            il.append(np.full(4000, l))
+        boxes.append(torch.from_numpy(np.concatenate(bl).astype(np.float32)).to(dev))
+        ids.append(torch.from_numpy(np.concatenate(il)).to(dev))
+        scores.append(torch.from_numpy(rng.permutation(20000).astype(np.float32) / 20000).to(dev))
+    g = torch.Generator().manual_seed(5 + rank)
+    feats = [torch.randn(B, C, h, w, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+             for h, w in sizes]
+    scales = [1.0 / s for s in STRIDES]
+    nms_cfg = dict(type='nms', iou_threshold=0.7)
+
+    def nms_all():
+        rois = []
+        for b in range(B):
+            dets, _ = ops.batched_nms(boxes[b], scores[b], ids[b], nms_cfg)
+            d = dets[:2000]
+            rois.append(torch.cat([d.new_full((d.size(0), 1), float(b)), d[:, :4]], 1))
+        return torch.cat(rois)
+
+    def step():
+        return ops.roi_extract(feats, nms_all(), scales, 7)
+
+    K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = lib.brcnn_launch_count()
+    ms = _timed_steps(step, K, W, world, dist, dev)
+    launches = (lib.brcnn_launch_count() - l0) * K // (K + W)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        peak, peak_src = _peak()
+        rois = nms_all()
+        t_nms = _dev_time(nms_all, 5, dev)
+        t_roi = _dev_time(lambda: ops.roi_extract(feats, rois, scales, 7), 10, dev)
+        rois_h = rois.cpu().numpy()
+        feat_bytes = sum(f.numel() * 4 for f in feats)
+        nbytes = rois_h.shape[0] * C * 49 * 4 + min(roi_footprint_bytes(rois_h, sizes, C), feat_bytes)
+        ach = nbytes / (t_roi * 1e-3) / 1e9
+        print(json.dumps({
+            'metric': 'proposal stress images/s', 'value': B * world * K / (ms * 1e-3),
+            'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': dict(workload=f'proposal stress: 5 levels x 4000 pre-NMS boxes, 2000 post-NMS '
+                                    f'RoIs/img, {B} images per GPU', images_per_gpu=B,
+                           rois=int(rois_h.shape[0])),
+            'gpu_launches': int(launches), 'clocks': clocks,
+            'roofline': dict(kernel='roi_align_fwd_tma_kernel', bound='hbm', achieved=ach, peak=peak,
+                             unit='GB/s', frac=ach / peak, traffic=None, peak_source=peak_src,
+                             algorithmic_bytes_per_launch=nbytes, ms_per_launch=t_roi),
+            'stages_ms': {'batched_nms_x%d' % B: t_nms, 'roi_align_fwd': t_roi}}))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get('RANK', 0))
@@ -203,6 +465,9 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     if world > 1 and args.impl == 'reference' and rank != 0:
         return 0  # the CPU arm runs on rank 0 only
+    if args.impl == 'b200' and args.mode != 'infer':
+        assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+        return (bench_train if args.mode == 'train' else bench_stress)(args, rank, world, local_rank)
 
     from boosting_rcnn_b200 import configs
     geom = configs.IMAGE_GEOMETRY[args.cfg]

@@ -149,6 +149,7 @@ roi_align_fwd_tma_kernel(const __grid_constant__ RoiArgs a, const float* __restr
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < 8) { s_xs[tid] = fw; s_xe[tid] = -1; }
   __syncthreads();
 
   if (warp == RT_CONS_WARPS) {
@@ -186,14 +187,12 @@ roi_align_fwd_tma_kernel(const __grid_constant__ RoiArgs a, const float* __restr
     }
     for (int i = tid; i < a.PW * fw; i += NCT) {
       const int pw = i / fw, dx = i - pw * fw;
-      wx[pw * a.max_w + dx] = roi_axis_weight(g.start_w, g.bin_w, g.gw, g.W, pw, xlo + dx);
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
-    if (tid < a.PW) {
-      int xs = fw, xe = -1;
-      for (int dx = 0; dx < fw; ++dx)
-        if (wx[tid * a.max_w + dx] != 0.f) { xs = min(xs, dx); xe = dx; }
-      s_xs[tid] = xs; s_xe[tid] = xe;
+      const float w = roi_axis_weight(g.start_w, g.bin_w, g.gw, g.W, pw, xlo + dx);
+      wx[pw * a.max_w + dx] = w;
+      if (w != 0.f) {  // non-zero band of pooled column pw
+        atomicMin(&s_xs[pw], dx);
+        atomicMax(&s_xe[pw], dx);
+      }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
 
@@ -241,6 +240,7 @@ roi_align_fwd_tma_kernel(const __grid_constant__ RoiArgs a, const float* __restr
 #pragma unroll
           for (int ph = 0; ph < RT_P; ++ph) {
             const float w = wv[ph];
+            if (w == 0.f) continue;   // warp-uniform: Wy[ph][y] is zero outside the band
             acc0[ph].x = fmaf(w, h0.x, acc0[ph].x); acc0[ph].y = fmaf(w, h0.y, acc0[ph].y);
             acc0[ph].z = fmaf(w, h0.z, acc0[ph].z); acc0[ph].w = fmaf(w, h0.w, acc0[ph].w);
             acc1[ph].x = fmaf(w, h1.x, acc1[ph].x); acc1[ph].y = fmaf(w, h1.y, acc1[ph].y);

@@ -209,10 +209,38 @@ rpn_topk_decode_kernel(const __grid_constant__ RpnArgs a,
   // ---- collect every composite >= the threshold bin ----
   if (tid == 0) s_ncand = 0;
   __syncthreads();
-  scan((uint32_t)(pmask >> 32), (uint32_t)(prefix >> 32), [&](int e, uint32_t key) {
-    const u64 c = composite(e, key);
-    if ((c & pmask) >= prefix) cand[atomicAdd(&s_ncand, 1)] = c;
-  });
+  {
+    // warp-converged scan with ONE shared-memory atomic per warp per key slot
+    // (a per-key atomicAdd on a single counter serialises ~2k survivors)
+    const uint32_t pm_hi = (uint32_t)(pmask >> 32), pr_hi = (uint32_t)(prefix >> 32);
+    const uint4* k4 = reinterpret_cast<const uint4*>(kseg);
+    const int nvec = (total + 3) >> 2;
+    for (int vb = tid - lane; vb < nvec; vb += 2 * RPN_TOPK_THREADS) {
+      const int v0 = vb + lane, v1 = v0 + RPN_TOPK_THREADS;
+      uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = q0;
+      if (v0 < nvec) q0 = __ldg(k4 + v0);
+      if (v1 < nvec) q1 = __ldg(k4 + v1);
+      const uint32_t kk[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = ((j < 4) ? v0 : v1) * 4 + (j & 3);
+        u64 c = 0ull;
+        bool take = false;
+        if (e < total && (kk[j] & pm_hi) >= pr_hi) {
+          c = composite(e, kk[j]);
+          take = (c & pmask) >= prefix;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (m) {
+          const int leader = __ffs(m) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(&s_ncand, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (take) cand[base + __popc(m & ((1u << lane) - 1u))] = c;
+        }
+      }
+    }
+  }
   __syncthreads();
   const int ncand = s_ncand;
   int np = 1;
