@@ -14,6 +14,7 @@
 #include "roi_align_bwd.cuh"
 #include "roi_align_tma.cuh"
 #include "rpn.cuh"
+#include "rpn_nms.cuh"
 
 namespace brcnn {
 static std::atomic<int64_t> g_launches{0};
@@ -339,6 +340,29 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
     BRCNN_CUDA_CHECK_LAST();
   }
 
+  // per-image NMS in global score order with early stop (rpn_nms.cuh); the
+  // per-(image, level) segment kernels + merge remain as the large-capacity path
+  {
+    static const bool force_segments = [] {
+      const char* e = getenv("BRCNN_RPN_NMS");
+      return e && e[0] == 's';
+    }();
+    const RpnNmsImageSmem lay = rpn_nms_image_smem(p->num_levels, p->max_per_img);
+    if (!force_segments && lay.total <= 180 * 1024 && p->max_per_img <= 65535) {
+      if (lay.total > 32 * 1024) {
+        e = cudaFuncSetAttribute(rpn_nms_image_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+        if (e != cudaSuccess) return (int)e;
+      }
+      rpn_nms_image_kernel<<<p->batch, RNI_THREADS, lay.total, stream>>>(
+          cand_boxes, cand_key, cand_valid, cand_count, p->num_levels, d.Kc,
+          p->iou_threshold, (const float*)img_maxc, p->max_per_img, proposals, num_proposals,
+          lay);
+      g_launch_count_add(1);
+      BRCNN_CUDA_CHECK_LAST();
+      return BRCNN_OK;
+    }
+  }
   rc = launch_nms_segments(cand_boxes, cand_valid, cand_count, S, d.Kc,
                            p->iou_threshold, 0.f, (const float*)img_maxc,
                            p->num_levels, mask, cand_key, kept_pos, kept_key,

@@ -126,3 +126,40 @@ def test_rpn_determinism(cuda):
     b = _run_case(cuda, batch=2, pad_hw=(256, 320), img_hw=(250, 317), nms_pre=300,
                   max_per_img=100, iou_thr=0.7, seed=11, duplicate_frac=0.5)
     np.testing.assert_array_equal(a[0].view(np.uint32), b[0].view(np.uint32))
+
+
+def test_rpn_image_kernel_equals_segment_path(cuda):
+    """BRCNN_RPN_NMS=segments (per-level NMS to completion + merge) vs the default
+    per-image global-order kernel with early stop: identical proposals."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = '''
+import sys, numpy as np, torch
+sys.path[:0] = [%r, %r]
+import synth
+from boosting_rcnn_b200 import ops
+from boosting_rcnn_b200.anchors import AnchorGenerator
+gen = AnchorGenerator(strides=list(synth.STRIDES), ratios=[0.5, 1.0, 2.0], octave_base_scale=4,
+                      scales_per_octave=3)
+sizes = synth.featmap_sizes(800, 1344)
+cls, box, iou = synth.rpn_outputs(2, sizes, 9, seed=77, duplicate_frac=0.2)
+t = lambda arrs: [torch.from_numpy(a).cuda() for a in arrs]
+hw = torch.tensor([[800., 1333.]] * 2).cuda()
+res = []
+for nms_pre, mx in ((1000, 256), (4000, 2000), (300, 3000)):
+    p = ops.make_rpn_params(2, sizes, synth.STRIDES, 9, nms_pre, mx, 0.7, 0.0)
+    pr, n = ops.rpn_get_bboxes(p, t(cls), t(box), t(iou), gen.base_anchor_table().cuda(), hw)
+    res += [pr.cpu().numpy().reshape(-1), n.cpu().numpy().astype(np.float32)]
+np.save(sys.argv[1], np.concatenate(res))
+''' % (os.path.dirname(here), here)
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for mode in ('segments', 'image'):
+            path = os.path.join(d, mode + '.npy')
+            subprocess.run([sys.executable, '-c', code, path], check=True,
+                           env=dict(os.environ, BRCNN_RPN_NMS=mode))
+            outs.append(np.load(path))
+    np.testing.assert_array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
