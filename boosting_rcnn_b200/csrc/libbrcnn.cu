@@ -12,6 +12,7 @@
 #include "rcnn_post.cuh"
 #include "roi_align.cuh"
 #include "roi_align_bwd.cuh"
+#include "roi_align_bwd2.cuh"
 #include "roi_align_tma.cuh"
 #include "rpn.cuh"
 #include "rpn_nms.cuh"
@@ -340,24 +341,57 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
     BRCNN_CUDA_CHECK_LAST();
   }
 
-  // per-image NMS in global score order with early stop (rpn_nms.cuh); the
-  // per-(image, level) segment kernels + merge remain as the large-capacity path
+  // per-image NMS in global score order with early stop (rpn_nms.cuh), one
+  // cluster of 8 CTAs per image; the per-(image, level) segment kernels + merge
+  // remain as the fallback (BRCNN_RPN_NMS=segments | image1 select them for A/B)
   {
-    static const bool force_segments = [] {
+    static const int mode = [] {
       const char* e = getenv("BRCNN_RPN_NMS");
-      return e && e[0] == 's';
+      if (e && e[0] == 's') return 0;                       // segments + merge
+      if (e && e[0] == 'i' && strchr(e, '1')) return 1;     // single CTA per image
+      return 2;                                             // cluster
     }();
-    const RpnNmsImageSmem lay = rpn_nms_image_smem(p->num_levels, p->max_per_img);
-    if (!force_segments && lay.total <= 180 * 1024 && p->max_per_img <= 65535) {
-      if (lay.total > 32 * 1024) {
-        e = cudaFuncSetAttribute(rpn_nms_image_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
-        if (e != cudaSuccess) return (int)e;
+    const int cs = (mode == 2) ? RNI_CLUSTER : 1;
+    const RpnNmsImageSmem lay = rpn_nms_image_smem(p->num_levels, p->max_per_img, cs);
+    if (mode != 0 && lay.total <= 160 * 1024 && lay.kp <= 65535) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)(p->batch * cs));
+      cfg.blockDim = dim3(RNI_THREADS);
+      cfg.dynamicSmemBytes = (size_t)lay.total;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)cs;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      const float* maxc_f = (const float*)img_maxc;
+      if (cs > 1) {
+        if (lay.total > 32 * 1024) {
+          e = cudaFuncSetAttribute(rpn_nms_image_kernel<RNI_CLUSTER>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+          if (e != cudaSuccess) return (int)e;
+        }
+        e = cudaLaunchKernelEx(&cfg, rpn_nms_image_kernel<RNI_CLUSTER>,
+                               (const float4*)cand_boxes, (const u64*)cand_key,
+                               (const uint8_t*)cand_valid, (const int32_t*)cand_count,
+                               (int)p->num_levels, (int)d.Kc, p->iou_threshold, maxc_f,
+                               (int)p->max_per_img, proposals, num_proposals, lay);
+      } else {
+        if (lay.total > 32 * 1024) {
+          e = cudaFuncSetAttribute(rpn_nms_image_kernel<1>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+          if (e != cudaSuccess) return (int)e;
+        }
+        e = cudaLaunchKernelEx(&cfg, rpn_nms_image_kernel<1>,
+                               (const float4*)cand_boxes, (const u64*)cand_key,
+                               (const uint8_t*)cand_valid, (const int32_t*)cand_count,
+                               (int)p->num_levels, (int)d.Kc, p->iou_threshold, maxc_f,
+                               (int)p->max_per_img, proposals, num_proposals, lay);
       }
-      rpn_nms_image_kernel<<<p->batch, RNI_THREADS, lay.total, stream>>>(
-          cand_boxes, cand_key, cand_valid, cand_count, p->num_levels, d.Kc,
-          p->iou_threshold, (const float*)img_maxc, p->max_per_img, proposals, num_proposals,
-          lay);
+      if (e != cudaSuccess) return (int)e;
       g_launch_count_add(1);
       BRCNN_CUDA_CHECK_LAST();
       return BRCNN_OK;
@@ -580,11 +614,68 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
   return BRCNN_OK;
 }
 
+static bool roi_bwd_use_v2(const RoiArgs& a) {
+  static const bool force_v1 = [] {
+    const char* e = getenv("BRCNN_ROI_BWD");
+    return e && e[0] == 'v' && e[1] == '1';
+  }();
+  return !force_v1 && a.PH <= B2_P && a.PW <= B2_P && (long long)a.B * a.L < 65535;
+}
+
 size_t brcnn_roi_extract_backward_workspace_bytes(const brcnn_roi_params* p,
                                                   int32_t R) {
   RoiArgs a;
   if (roi_args_from(p, &a) || R < 0) return 0;
-  return roi_bwd_ws(a, R).total;
+  return roi_bwd_use_v2(a) ? roi_bwd2_ws(a, R).total : roi_bwd_ws(a, R).total;
+}
+
+static int roi_bwd2_launch(RoiArgs a, const float* grad_out, const float* rois, int R,
+                           float* const* grad_feats, void* workspace, size_t workspace_bytes,
+                           cudaStream_t stream) {
+  const RoiBwd2Ws w = roi_bwd2_ws(a, R);
+  if (!workspace || workspace_bytes < w.total) return BRCNN_ERR_WORKSPACE;
+  if (misaligned16(workspace)) return BRCNN_ERR_ARG;
+  RoiBwd2Args ba;
+  memset(&ba, 0, sizeof(ba));
+  for (int l = 0; l < a.L; ++l) {
+    if (a.H[l] > a.max_h) a.max_h = a.H[l];
+    if (a.W[l] > a.max_w) a.max_w = a.W[l];
+  }
+  ba.a = a;
+  ba.TR = a.max_h + a.max_w;
+  long long base = 0;
+  for (int l = 0; l < a.L; ++l) {
+    if (!grad_feats[l] || misaligned16(grad_feats[l])) return BRCNN_ERR_ARG;
+    ba.grad[l] = grad_feats[l];
+    ba.tiles_x[l] = (a.W[l] + B2_TS - 1) / B2_TS;
+    ba.tiles_y[l] = (a.H[l] + B2_TS - 1) / B2_TS;
+    ba.tile_base[l] = (int)base;
+    base += (long long)ba.tiles_x[l] * ba.tiles_y[l] * a.B;
+    if (base > 0x7fffffffLL) return BRCNN_ERR_UNSUPPORTED;
+  }
+  ba.tile_base[a.L] = (int)base;
+  char* ws = (char*)workspace;
+  RoiBwdRec* recs = (RoiBwdRec*)(ws + w.recs);
+  unsigned short* keys = (unsigned short*)(ws + w.keys);
+  float* tab = (float*)(ws + w.tab);
+  float* gt = (float*)(ws + w.gt);
+  const int nbins = a.PH * a.PW;
+  if (R > 0) {
+    roi_bwd_prep_kernel<<<R, 128, 0, stream>>>(ba.a, rois, R, ba.TR, recs, keys, tab);
+    g_launch_count_add(1);
+    BRCNN_CUDA_CHECK_LAST();
+    const float* tin[1] = {grad_out};
+    float* tout[1] = {gt};
+    const int trows[1] = {a.C}, tcols[1] = {nbins};
+    const int rc = transpose_launch_multi(tin, tout, 1, R, trows, tcols, stream);
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)base, (a.C + B2_CCH - 1) / B2_CCH);
+  if (grid.y > 65535) return BRCNN_ERR_UNSUPPORTED;
+  roi_bwd_gather2_kernel<<<grid, B2_THREADS, 0, stream>>>(ba, recs, keys, R, tab, gt);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
 }
 
 int brcnn_roi_extract_backward(const brcnn_roi_params* p, const float* grad_out,
@@ -597,6 +688,9 @@ int brcnn_roi_extract_backward(const brcnn_roi_params* p, const float* grad_out,
   if (rc) return rc;
   if (R < 0 || !grad_feats_nhwc_host) return BRCNN_ERR_ARG;
   if (R > 0 && (!grad_out || !rois)) return BRCNN_ERR_ARG;
+  if (roi_bwd_use_v2(a))
+    return roi_bwd2_launch(a, grad_out, rois, R, grad_feats_nhwc_host, workspace,
+                           workspace_bytes, stream);
   return roi_bwd_launch(a, grad_out, rois, R, grad_feats_nhwc_host, workspace,
                         workspace_bytes, stream);
 }

@@ -19,34 +19,45 @@
 //   4. diag   : 64x64 same-level suppression bits among the survivors
 //   5. resolve: greedy order as a ballot fix-point (see nms_fused_kernel),
 //               append keeps, emit proposals rows directly in final order.
+// A thread-block CLUSTER of CS CTAs works on one image: the kept list is
+// distributed round-robin over the CTAs' shared memories, every CTA pulls the
+// tile against its share, the 64-bit dead masks are OR-combined through
+// distributed shared memory (one cluster barrier per round, masks double
+// buffered), and the cheap, deterministic steps (windows, ranks, diag,
+// resolve) are replicated in every CTA so no result ever has to be broadcast.
 // IoU arithmetic: mmcv nms_cpu division form on boxes + level*(max_coord+1)
 // added in fp32 (DESIGN.md "Pinned arithmetic"), identical to the segment
 // kernels, so results are bit-identical to them.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "nms_kernels.cuh"
 
 namespace brcnn {
 
+namespace cg = cooperative_groups;
+
 constexpr int RNI_THREADS = 512;
 constexpr int RNI_TILE = 64;
+constexpr int RNI_CLUSTER = 8;
 
 struct RpnNmsImageSmem {
-  // byte offsets into dynamic smem
-  int kbox, karea, lidx, total;
+  int kp;                     // local kept capacity (multiple of 8)
+  int kbox, lidx, total;      // byte offsets into dynamic smem
 };
-inline RpnNmsImageSmem rpn_nms_image_smem(int L, int max_out) {
+inline RpnNmsImageSmem rpn_nms_image_smem(int L, int max_out, int cs) {
   RpnNmsImageSmem s;
-  const int kp = (max_out + 7) & ~7;
+  s.kp = (((max_out + cs - 1) / cs) + 7) & ~7;
   int o = 0;
-  s.kbox = o;  o += kp * 16;
-  s.karea = o; o += kp * 4;
-  s.lidx = o;  o += L * kp * 2;
+  s.kbox = o;  o += s.kp * 16;
+  s.lidx = o;  o += L * s.kp * 2;
   s.total = (o + 15) & ~15;
   return s;
 }
 
-// grid B, block RNI_THREADS.  L <= BRCNN_MAX_LEVELS.
+// grid B*CS (cluster dims CS x 1 x 1), block RNI_THREADS.  L <= BRCNN_MAX_LEVELS.
+template <int CS>
 __global__ void __launch_bounds__(RNI_THREADS)
 rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restrict__ cand_key,
                      const uint8_t* __restrict__ cand_valid,
@@ -55,10 +66,9 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
                      float* __restrict__ proposals, int32_t* __restrict__ num_proposals,
                      RpnNmsImageSmem lay) {
   extern __shared__ __align__(16) unsigned char rni_smem[];
-  float4* kbox = reinterpret_cast<float4*>(rni_smem + lay.kbox);
-  float* karea = reinterpret_cast<float*>(rni_smem + lay.karea);
+  float4* kbox = reinterpret_cast<float4*>(rni_smem + lay.kbox);            // local share
   unsigned short* lidx = reinterpret_cast<unsigned short*>(rni_smem + lay.lidx);
-  const int kp = (max_out + 7) & ~7;
+  const int kp = lay.kp;
 
   __shared__ u64 w_key[BRCNN_MAX_LEVELS][RNI_TILE];      // level windows
   __shared__ float4 w_box[BRCNN_MAX_LEVELS][RNI_TILE];
@@ -69,12 +79,17 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
   __shared__ int tlvl[RNI_TILE];
   __shared__ u64 diag[RNI_TILE];
   __shared__ u64 s_lmask[BRCNN_MAX_LEVELS];
-  __shared__ unsigned s_dead[2];
+  __shared__ unsigned s_lmask32[BRCNN_MAX_LEVELS][2];
+  __shared__ u64 s_hit[2];          // this CTA's pull hits, double buffered by round parity
+  __shared__ u64 s_alive;
+  __shared__ unsigned s_dead[2], s_hitw[2];
   __shared__ int s_cursor[BRCNN_MAX_LEVELS], s_count[BRCNN_MAX_LEVELS], s_wn[BRCNN_MAX_LEVELS];
-  __shared__ int s_lcnt[BRCNN_MAX_LEVELS], s_taken[BRCNN_MAX_LEVELS];
-  __shared__ int s_nkept;
+  __shared__ int s_lcnt[BRCNN_MAX_LEVELS];   // LOCAL kept count per level
+  __shared__ int s_taken[BRCNN_MAX_LEVELS];
+  __shared__ int s_nkept;                    // GLOBAL kept count (same in every CTA)
 
-  const int b = blockIdx.x;
+  const int crank = (CS > 1) ? (int)cg::this_cluster().block_rank() : 0;
+  const int b = blockIdx.x / CS;
   const int tid = threadIdx.x, lane = tid & 31;
   const float maxc1 = img_maxc[b] + 1.0f;
   if (tid < BRCNN_MAX_LEVELS) {
@@ -85,63 +100,90 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
   if (tid == 0) s_nkept = 0;
   __syncthreads();
 
-  while (true) {
-    // ---- 1. windows ----
-    {
-      const int l = tid >> 6, i = tid & 63;
-      if (l < L) {
-        const int pos = s_cursor[l] + i;
-        const bool present = pos < s_count[l];
-        if (present) {
-          const size_t g = ((size_t)b * L + l) * Kc + pos;
-          w_key[l][i] = cand_key[g];
-          w_box[l][i] = cand_boxes[g];
-          w_valid[l][i] = cand_valid != nullptr ? cand_valid[g] : 1;
-        }
-        if (i == 0) {
-          s_wn[l] = max(0, min(RNI_TILE, s_count[l] - s_cursor[l]));
-          s_taken[l] = 0;
-        }
-      } else if (l < BRCNN_MAX_LEVELS && i == 0) {
-        s_wn[l] = 0; s_taken[l] = 0;
-      }
-      if (tid < 2) s_dead[tid] = 0xffffffffu;
-      if (tid < BRCNN_MAX_LEVELS) s_lmask[tid] = 0ull;
+  // window element (l, i) of this thread, prefetched one round ahead
+  const int wl = tid >> 6, wi = tid & 63;
+  u64 pk = 0ull;
+  float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint8_t pv = 0;
+  auto prefetch = [&](int cursor) {
+    const int pos = cursor + wi;
+    if (wl < L && pos < s_count[wl]) {
+      const size_t g = ((size_t)b * L + wl) * Kc + pos;
+      pk = cand_key[g];
+      pb = cand_boxes[g];
+      pv = cand_valid != nullptr ? cand_valid[g] : 1;
     }
+  };
+  if (wl < BRCNN_MAX_LEVELS) prefetch(0);
+
+  for (int round = 0;; ++round) {
+    // ---- 1. windows: registers -> smem ----
+    if (wl < BRCNN_MAX_LEVELS) {
+      w_key[wl][wi] = pk; w_box[wl][wi] = pb; w_valid[wl][wi] = pv;
+      if (wi == 0) {
+        s_wn[wl] = (wl < L) ? max(0, min(RNI_TILE, s_count[wl] - s_cursor[wl])) : 0;
+        s_taken[wl] = 0;
+      }
+    }
+    if (tid < 2) { s_dead[tid] = 0xffffffffu; s_hitw[tid] = 0u; }
+    if (tid < RNI_TILE) tlvl[tid] = -1;
     __syncthreads();
     int remaining = 0;
     for (int l = 0; l < L; ++l) remaining += s_wn[l];
-    if (remaining == 0) break;                      // block-uniform
+    if (remaining == 0) break;                      // cluster-uniform
     const int ntile = min(RNI_TILE, remaining);
     // ---- 2. rank inside the union of the windows ----
-    {
-      const int l = tid >> 6, i = tid & 63;
-      if (l < L && i < s_wn[l]) {
-        const u64 key = w_key[l][i];
-        int rank = i;
-        for (int l2 = 0; l2 < L && rank < RNI_TILE; ++l2) {
-          if (l2 == l || s_wn[l2] == 0) continue;
-          rank += count_greater_desc(w_key[l2], s_wn[l2], key);
+    if (wl < L && wi < s_wn[wl]) {
+      const u64 key = w_key[wl][wi];
+      // L interleaved binary searches (independent chains -> ILP): lo[l2] ends
+      // as #keys of window l2 greater than `key`
+      int lo[BRCNN_MAX_LEVELS], hi[BRCNN_MAX_LEVELS];
+#pragma unroll
+      for (int l2 = 0; l2 < BRCNN_MAX_LEVELS; ++l2) {
+        lo[l2] = 0;
+        hi[l2] = (l2 < L && l2 != wl) ? s_wn[l2] : 0;
+      }
+#pragma unroll
+      for (int step = 0; step < 7; ++step) {   // windows hold <= 64 keys
+#pragma unroll
+        for (int l2 = 0; l2 < BRCNN_MAX_LEVELS; ++l2) {
+          if (lo[l2] < hi[l2]) {
+            const int mid = (lo[l2] + hi[l2]) >> 1;
+            if (w_key[l2][mid] > key) lo[l2] = mid + 1; else hi[l2] = mid;
+          }
         }
-        if (rank < RNI_TILE) {
-          const float4 raw = w_box[l][i];
-          const float4 ob = add_seg_offset(raw, (float)l * maxc1);
-          traw[rank] = raw;
-          tb[rank] = ob;
-          ta[rank] = (ob.z - ob.x) * (ob.w - ob.y);
-          tkey[rank] = key;
-          tlvl[rank] = l;
-          atomicAdd(&s_taken[l], 1);
-          atomicOr(&s_lmask[l], 1ull << rank);
-          if (w_valid[l][i]) atomicAnd(&s_dead[rank >> 5], ~(1u << (rank & 31)));
-        }
+      }
+      int rank = wi;
+#pragma unroll
+      for (int l2 = 0; l2 < BRCNN_MAX_LEVELS; ++l2) rank += lo[l2];
+      if (rank < RNI_TILE) {
+        const float4 raw = w_box[wl][wi];
+        const float4 ob = add_seg_offset(raw, (float)wl * maxc1);
+        traw[rank] = raw;
+        tb[rank] = ob;
+        ta[rank] = (ob.z - ob.x) * (ob.w - ob.y);
+        tkey[rank] = key;
+        tlvl[rank] = wl;
+        atomicAdd(&s_taken[wl], 1);
+        if (w_valid[wl][wi]) atomicAnd(&s_dead[rank >> 5], ~(1u << (rank & 31)));
       }
     }
     __syncthreads();
+    // next round's windows start at cursor + taken: issue the global loads now
+    // so that their latency hides behind pull / diag / resolve
+    if (wl < L) prefetch(s_cursor[wl] + s_taken[wl]);
     const int nkept = s_nkept;
-    // ---- 3. pull: candidate c vs the kept boxes of its level ----
+    // per-level membership masks of the tile (ballots, no 64-bit smem atomics)
+    if (tid < RNI_TILE) {
+      const int l = tlvl[tid];
+      for (int l2 = 0; l2 < L; ++l2) {
+        const unsigned m = __ballot_sync(0xffffffffu, l == l2);
+        if (lane == 0) s_lmask32[l2][tid >> 5] = m;
+      }
+    }
+    // ---- 3. pull: candidate c vs this CTA's share of its level's kept boxes ----
     {
-      const int c = tid & 63, g = tid >> 6;
+      const int c = tid & 63, g = tid >> 6;   // 8 groups
       bool hit = false;
       if (c < ntile && !((s_dead[c >> 5] >> (c & 31)) & 1u)) {
         const int l = tlvl[c];
@@ -149,18 +191,44 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
         const float ba = ta[c];
         const unsigned short* li = lidx + (size_t)l * kp;
         const int n = s_lcnt[l];
-        for (int q = g; q < n && !hit; q += 8) {
-          const int k = li[q];
-          hit = nms_suppresses(kbox[k], karea[k], bx, ba, thr, 0.f);
+        int q = g;
+        for (; q + 24 < n && !hit; q += 32) {
+          const float4 k0 = kbox[li[q]], k1 = kbox[li[q + 8]], k2 = kbox[li[q + 16]],
+                       k3 = kbox[li[q + 24]];
+          const bool h0 = nms_suppresses(k0, (k0.z - k0.x) * (k0.w - k0.y), bx, ba, thr, 0.f);
+          const bool h1 = nms_suppresses(k1, (k1.z - k1.x) * (k1.w - k1.y), bx, ba, thr, 0.f);
+          const bool h2 = nms_suppresses(k2, (k2.z - k2.x) * (k2.w - k2.y), bx, ba, thr, 0.f);
+          const bool h3 = nms_suppresses(k3, (k3.z - k3.x) * (k3.w - k3.y), bx, ba, thr, 0.f);
+          hit = h0 | h1 | h2 | h3;
+        }
+        for (; q < n && !hit; q += 8) {
+          const float4 k0 = kbox[li[q]];
+          hit = nms_suppresses(k0, (k0.z - k0.x) * (k0.w - k0.y), bx, ba, thr, 0.f);
         }
       }
       const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      if (lane == 0 && bal) atomicOr(&s_dead[(tid >> 5) & 1], bal);
+      if (lane == 0 && bal) atomicOr(&s_hitw[(tid >> 5) & 1], bal);
     }
     __syncthreads();
-    const u64 alive = ~(((u64)s_dead[1] << 32) | (u64)s_dead[0]);
-    u64 keep = 0ull;
-    if (alive != 0ull) {   // block-uniform
+    if (tid < L) s_lmask[tid] = ((u64)s_lmask32[tid][1] << 32) | (u64)s_lmask32[tid][0];
+    // ---- combine the pull hits of the cluster ----
+    if (CS > 1) {
+      if (tid == 0) s_hit[round & 1] = ((u64)s_hitw[1] << 32) | (u64)s_hitw[0];
+      cg::this_cluster().sync();
+      if (tid < 32) {
+        u64 h = 0ull;
+        if (lane < CS) h = *cg::this_cluster().map_shared_rank(&s_hit[round & 1], lane);
+#pragma unroll
+        for (int o = 1; o < CS; o <<= 1) h |= __shfl_xor_sync(0xffffffffu, h, o);
+        if (lane == 0) s_alive = ~((((u64)s_dead[1] << 32) | (u64)s_dead[0]) | h);
+      }
+    } else if (tid == 0) {
+      s_alive = ~((((u64)s_dead[1] << 32) | (u64)s_dead[0]) |
+                  (((u64)s_hitw[1] << 32) | (u64)s_hitw[0]));
+    }
+    __syncthreads();
+    const u64 alive = s_alive;
+    if (alive != 0ull) {   // cluster-uniform
       // ---- 4. diag: row r vs earlier same-level alive candidates ----
       {
         const int r = tid >> 3, g = tid & 7;
@@ -184,11 +252,11 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
         if (g == 0) diag[r] = word;
       }
       __syncthreads();
-      // ---- 5. resolve (warp 0) ----
+      // ---- 5. resolve (warp 0; identical in every CTA) ----
       if (tid < 32) {
         const u64 c0 = diag[lane], c1 = diag[lane + 32];
         const bool a0 = (alive >> lane) & 1ull, a1 = (alive >> (lane + 32)) & 1ull;
-        keep = alive;
+        u64 keep = alive;
         for (int it = 0; it < 64; ++it) {
           const unsigned k0 = __ballot_sync(0xffffffffu, a0 && !(c0 & keep));
           const unsigned k1 = __ballot_sync(0xffffffffu, a1 && !(c1 & keep));
@@ -196,18 +264,33 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
           if (kn == keep) break;
           keep = kn;
         }
+        // kept box with global rank q lives in CTA q % CS
+        u64 mine = 0ull;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int r = lane + 32 * h;
-          if ((keep >> r) & 1ull) {
-            const u64 below = keep & ((1ull << r) - 1ull);
-            const int q = nkept + __popcll(below);
+          const bool kept = (keep >> r) & 1ull;
+          const int q = nkept + __popcll(keep & ((1ull << r) - 1ull));
+          const bool own = kept && (q < max_out) && ((CS == 1) || (q % CS == crank));
+          const unsigned ob = __ballot_sync(0xffffffffu, own);
+          mine |= (u64)ob << (32 * h);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = lane + 32 * h;
+          if ((mine >> r) & 1ull) {
+            const u64 below = mine & ((1ull << r) - 1ull);
+            const int l = tlvl[r];
+            int slot = 0;
+            for (int l2 = 0; l2 < L; ++l2) slot += s_lcnt[l2];   // local kept so far
+            slot += __popcll(below);
+            kbox[slot] = tb[r];
+            lidx[(size_t)l * kp + s_lcnt[l] + __popcll(below & s_lmask[l])] =
+                (unsigned short)slot;
+          }
+          if (crank == 0 && ((keep >> r) & 1ull)) {
+            const int q = nkept + __popcll(keep & ((1ull << r) - 1ull));
             if (q < max_out) {
-              const int l = tlvl[r];
-              kbox[q] = tb[r];
-              karea[q] = ta[r];
-              lidx[(size_t)l * kp + s_lcnt[l] + __popcll(below & s_lmask[l])] =
-                  (unsigned short)q;
               const float4 raw = traw[r];
               float* o = proposals + ((size_t)b * max_out + q) * 5;
               o[0] = raw.x; o[1] = raw.y; o[2] = raw.z; o[3] = raw.w;
@@ -216,19 +299,23 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
           }
         }
         __syncwarp();
-        if (lane < L) s_lcnt[lane] += __popcll(keep & s_lmask[lane]);
+        if (lane < L) s_lcnt[lane] += __popcll(mine & s_lmask[lane]);
         if (lane == 0) s_nkept = nkept + __popcll(keep);
       }
     }
     if (tid < L) s_cursor[tid] += s_taken[tid];
     __syncthreads();
-    if (s_nkept >= max_out) break;
+    if (s_nkept >= max_out) break;                  // cluster-uniform
   }
   __syncthreads();
-  const int nk = min(s_nkept, max_out);
-  if (tid == 0) num_proposals[b] = nk;
-  for (int i = nk * 5 + tid; i < max_out * 5; i += RNI_THREADS)
-    proposals[(size_t)b * max_out * 5 + i] = 0.f;
+  if (crank == 0) {
+    const int nk = min(s_nkept, max_out);
+    if (tid == 0) num_proposals[b] = nk;
+    for (int i = nk * 5 + tid; i < max_out * 5; i += RNI_THREADS)
+      proposals[(size_t)b * max_out * 5 + i] = 0.f;
+  }
+  // nobody leaves while a peer may still read its hit masks
+  if (CS > 1) cg::this_cluster().sync();
 }
 
 }  // namespace brcnn

@@ -223,3 +223,19 @@ np.save(sys.argv[1], out.cpu().numpy())
             subprocess.run([sys.executable, '-c', code, path], check=True, env=env)
             outs.append(np.load(path))
     _close(outs[0], outs[1], 'v1 vs v2')
+
+
+@pytest.mark.parametrize('C,n', [(4, 40), (132, 60), (320, 1500)])
+def test_roi_backward_channel_slabs_and_long_lists(cuda, C, n):
+    # partial / multiple 128-channel slabs; > 1024 RoIs on one tile (list rounds);
+    # padding rows, degenerate and whole-image RoIs in the backward pass
+    ex = np.array([[-1, 0, 0, 0, 0], [0, 5, 5, 5, 5], [0, 0, 0, 320, 256], [0, 2, 2, 318, 6],
+                   [0, 300, 250, 330, 270]], dtype=np.float32)
+    tf, feats, rois, scales, out = _case(cuda, 1, (256, 320), C, n, seed=40 + C, clustered=True,
+                                         extra_rois=ex)
+    g = np.random.RandomState(41).normal(0, 1, out.shape).astype(np.float32)
+    out.backward(torch.from_numpy(g).to(cuda))
+    live = rois[:, 0] >= 0
+    ref = oracle.roi_extract_backward(g[live], rois[live], [f.shape for f in feats], scales)
+    for l, (t, r) in enumerate(zip(tf, ref)):
+        _close(t.grad.cpu().numpy(), r, f'grad level {l}')

@@ -129,8 +129,9 @@ def test_rpn_determinism(cuda):
 
 
 def test_rpn_image_kernel_equals_segment_path(cuda):
-    """BRCNN_RPN_NMS=segments (per-level NMS to completion + merge) vs the default
-    per-image global-order kernel with early stop: identical proposals."""
+    """BRCNN_RPN_NMS=segments (per-level NMS to completion + merge) vs image1 (one CTA
+    per image, global score order, early stop) vs the default 8-CTA cluster version:
+    identical proposals."""
     import os
     import subprocess
     import sys
@@ -157,9 +158,10 @@ np.save(sys.argv[1], np.concatenate(res))
 ''' % (os.path.dirname(here), here)
     outs = []
     with tempfile.TemporaryDirectory() as d:
-        for mode in ('segments', 'image'):
+        for mode in ('segments', 'image1', 'cluster'):
             path = os.path.join(d, mode + '.npy')
             subprocess.run([sys.executable, '-c', code, path], check=True,
                            env=dict(os.environ, BRCNN_RPN_NMS=mode))
             outs.append(np.load(path))
     np.testing.assert_array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    np.testing.assert_array_equal(outs[0].view(np.uint32), outs[2].view(np.uint32))
