@@ -80,6 +80,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
   __shared__ u64 diag[RNI_TILE];
   __shared__ u64 s_lmask[BRCNN_MAX_LEVELS];
   __shared__ unsigned s_lmask32[BRCNN_MAX_LEVELS][2];
+  __shared__ unsigned s_dslice[2][RNI_TILE / CS][2];   // this CTA's diag rows (double buffered)
   __shared__ u64 s_hit[2];          // this CTA's pull hits, double buffered by round parity
   __shared__ u64 s_alive;
   __shared__ unsigned s_dead[2], s_hitw[2];
@@ -135,21 +136,34 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
     // ---- 2. rank inside the union of the windows ----
     if (wl < L && wi < s_wn[wl]) {
       const u64 key = w_key[wl][wi];
-      // L interleaved binary searches (independent chains -> ILP): lo[l2] ends
-      // as #keys of window l2 greater than `key`
+      // interleaved binary searches over the other levels' windows (independent
+      // chains -> ILP); lo[j] ends as #keys of that window greater than `key`
       int lo[BRCNN_MAX_LEVELS], hi[BRCNN_MAX_LEVELS];
 #pragma unroll
       for (int l2 = 0; l2 < BRCNN_MAX_LEVELS; ++l2) {
         lo[l2] = 0;
         hi[l2] = (l2 < L && l2 != wl) ? s_wn[l2] : 0;
       }
+      if (L <= 5) {
 #pragma unroll
-      for (int step = 0; step < 7; ++step) {   // windows hold <= 64 keys
+        for (int step = 0; step < 7; ++step) {   // windows hold <= 64 keys
 #pragma unroll
-        for (int l2 = 0; l2 < BRCNN_MAX_LEVELS; ++l2) {
-          if (lo[l2] < hi[l2]) {
-            const int mid = (lo[l2] + hi[l2]) >> 1;
-            if (w_key[l2][mid] > key) lo[l2] = mid + 1; else hi[l2] = mid;
+          for (int l2 = 0; l2 < 5; ++l2) {
+            if (lo[l2] < hi[l2]) {
+              const int mid = (lo[l2] + hi[l2]) >> 1;
+              if (w_key[l2][mid] > key) lo[l2] = mid + 1; else hi[l2] = mid;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int step = 0; step < 7; ++step) {
+#pragma unroll
+          for (int l2 = 0; l2 < BRCNN_MAX_LEVELS; ++l2) {
+            if (lo[l2] < hi[l2]) {
+              const int mid = (lo[l2] + hi[l2]) >> 1;
+              if (w_key[l2][mid] > key) lo[l2] = mid + 1; else hi[l2] = mid;
+            }
           }
         }
       }
@@ -173,14 +187,6 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
     // so that their latency hides behind pull / diag / resolve
     if (wl < L) prefetch(s_cursor[wl] + s_taken[wl]);
     const int nkept = s_nkept;
-    // per-level membership masks of the tile (ballots, no 64-bit smem atomics)
-    if (tid < RNI_TILE) {
-      const int l = tlvl[tid];
-      for (int l2 = 0; l2 < L; ++l2) {
-        const unsigned m = __ballot_sync(0xffffffffu, l == l2);
-        if (lane == 0) s_lmask32[l2][tid >> 5] = m;
-      }
-    }
     // ---- 3. pull: candidate c vs this CTA's share of its level's kept boxes ----
     {
       const int c = tid & 63, g = tid >> 6;   // 8 groups
@@ -209,9 +215,27 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
       const unsigned bal = __ballot_sync(0xffffffffu, hit);
       if (lane == 0 && bal) atomicOr(&s_hitw[(tid >> 5) & 1], bal);
     }
+    // ---- 4. diag slice: rows [crank*RPC, crank*RPC + RPC) of the 64x64 same-level
+    // suppression matrix, one pair test per thread (all rows when CS == 1).  It does
+    // not depend on the pull result: bits of candidates that turn out dead are
+    // simply ignored by the resolve step.
+    {
+      constexpr int RPC = RNI_TILE / CS;               // rows per CTA
+      constexpr int PASSES = (RPC * RNI_TILE) / RNI_THREADS > 0 ? (RPC * RNI_TILE) / RNI_THREADS : 1;
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int rl = (tid >> 6) + ps * (RNI_THREADS / RNI_TILE);   // local row
+        const int r = crank * RPC + rl, cc = tid & 63;
+        bool sup = false;
+        if (rl < RPC && r < ntile && cc < r && tlvl[cc] == tlvl[r] &&
+            !((s_dead[cc >> 5] >> (cc & 31)) & 1u) && !((s_dead[r >> 5] >> (r & 31)) & 1u))
+          sup = nms_suppresses(tb[cc], ta[cc], tb[r], ta[r], thr, 0.f);
+        const unsigned bal = __ballot_sync(0xffffffffu, sup);
+        if (lane == 0 && rl < RPC) s_dslice[round & 1][rl][(tid >> 5) & 1] = bal;
+      }
+    }
     __syncthreads();
-    if (tid < L) s_lmask[tid] = ((u64)s_lmask32[tid][1] << 32) | (u64)s_lmask32[tid][0];
-    // ---- combine the pull hits of the cluster ----
+    // ---- combine pull hits and diag rows of the cluster (one cluster barrier) ----
     if (CS > 1) {
       if (tid == 0) s_hit[round & 1] = ((u64)s_hitw[1] << 32) | (u64)s_hitw[0];
       cg::this_cluster().sync();
@@ -221,39 +245,37 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
 #pragma unroll
         for (int o = 1; o < CS; o <<= 1) h |= __shfl_xor_sync(0xffffffffu, h, o);
         if (lane == 0) s_alive = ~((((u64)s_dead[1] << 32) | (u64)s_dead[0]) | h);
+      } else if (tid >= 64 && tid < 64 + RNI_TILE) {
+        constexpr int RPC = RNI_TILE / CS;
+        const int r = tid - 64;
+        const unsigned* src = cg::this_cluster().map_shared_rank(
+            &s_dslice[round & 1][r % RPC][0], r / RPC);
+        diag[r] = ((u64)src[1] << 32) | (u64)src[0];
       }
-    } else if (tid == 0) {
-      s_alive = ~((((u64)s_dead[1] << 32) | (u64)s_dead[0]) |
-                  (((u64)s_hitw[1] << 32) | (u64)s_hitw[0]));
+    } else {
+      if (tid == 0)
+        s_alive = ~((((u64)s_dead[1] << 32) | (u64)s_dead[0]) |
+                    (((u64)s_hitw[1] << 32) | (u64)s_hitw[0]));
+      if (tid >= 64 && tid < 64 + RNI_TILE) {
+        const int r = tid - 64;
+        diag[r] = ((u64)s_dslice[round & 1][r][1] << 32) | (u64)s_dslice[round & 1][r][0];
+      }
+    }
+    if (tid >= 128 && tid < 128 + RNI_TILE) {
+      // per-level membership masks of the tile
+      const int l = tlvl[tid - 128];
+      for (int l2 = 0; l2 < L; ++l2) {
+        const unsigned m = __ballot_sync(0xffffffffu, l == l2);
+        if (lane == 0) s_lmask32[l2][(tid >> 5) & 1] = m;
+      }
     }
     __syncthreads();
     const u64 alive = s_alive;
     if (alive != 0ull) {   // cluster-uniform
-      // ---- 4. diag: row r vs earlier same-level alive candidates ----
-      {
-        const int r = tid >> 3, g = tid & 7;
-        unsigned bits8 = 0;
-        if ((alive >> r) & 1ull) {
-          const float4 a4 = tb[r];
-          const float aa = ta[r];
-          const u64 same = s_lmask[tlvl[r]] & alive;
-#pragma unroll
-          for (int cc8 = 0; cc8 < 8; ++cc8) {
-            const int cc = g * 8 + cc8;
-            if (cc < r && ((same >> cc) & 1ull) &&
-                nms_suppresses(tb[cc], ta[cc], a4, aa, thr, 0.f))
-              bits8 |= (1u << cc8);
-          }
-        }
-        u64 word = (u64)bits8 << (8 * g);
-        word |= __shfl_xor_sync(0xffffffffu, word, 1);
-        word |= __shfl_xor_sync(0xffffffffu, word, 2);
-        word |= __shfl_xor_sync(0xffffffffu, word, 4);
-        if (g == 0) diag[r] = word;
-      }
-      __syncthreads();
       // ---- 5. resolve (warp 0; identical in every CTA) ----
       if (tid < 32) {
+        if (lane < L) s_lmask[lane] = ((u64)s_lmask32[lane][1] << 32) | (u64)s_lmask32[lane][0];
+        __syncwarp();
         const u64 c0 = diag[lane], c1 = diag[lane + 32];
         const bool a0 = (alive >> lane) & 1ull, a1 = (alive >> (lane + 32)) & 1ull;
         u64 keep = alive;
