@@ -108,9 +108,10 @@ SIGNATURES = {
                                            c_int32, POINTER(c_int32), c_void_p]),
     'brcnn_nhwc_to_nchw_multi': (c_int32, [POINTER(c_void_p), POINTER(c_void_p), c_int32, c_int32,
                                            c_int32, POINTER(c_int32), c_void_p]),
+    'brcnn_boost_loss_workspace_bytes': (c_size_t, [POINTER(LossParams)]),
     'brcnn_boost_loss': (c_int32, [
         POINTER(LossParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'brcnn_rcnn_workspace_layout': (c_int32, [POINTER(RcnnParams), POINTER(RcnnWsLayout)]),
     'brcnn_rcnn_workspace_bytes': (c_size_t, [POINTER(RcnnParams)]),
     'brcnn_rcnn_get_bboxes': (c_int32, [

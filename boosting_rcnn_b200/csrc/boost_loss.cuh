@@ -13,9 +13,11 @@
 //               (or .mean() when reg_norm == 'mean')
 //   acc = 100 * mean(argmax_c x_ic == label_i)
 //
-// One CTA: the whole problem is <= a few hundred KB and needs two global
-// sums before any gradient can be written; a fixed warp->row mapping and a
-// fixed-order cross-warp reduction make the result bit-reproducible.
+// Two launches over up to one CTA per SM (the problem needs two global sums
+// before any gradient can be written): part 1 = softmax / CE / L1 per row and
+// one partial-sum record per CTA, part 2 = fixed-order reduction of the records
+// (identical in every CTA) + gradients.  Row -> (CTA, warp) mapping and both
+// reduction trees are fixed, so the result is bit-reproducible run to run.
 #pragma once
 #include "common.cuh"
 
@@ -37,28 +39,29 @@ __device__ __forceinline__ float boost_weight(float prior, float gamma, float al
   return w;
 }
 
-__global__ void __launch_bounds__(1024)
-boost_loss_kernel(const LossArgs a, const float* __restrict__ cls_score,
-                  const int64_t* __restrict__ labels,
-                  const float* __restrict__ label_weights,
-                  const float* __restrict__ prior,
-                  const float* __restrict__ bbox_pred,
-                  const float* __restrict__ bbox_targets,
-                  const float* __restrict__ bbox_weights,
-                  float* __restrict__ out, float* __restrict__ grad_cls,
-                  float* __restrict__ grad_bbox) {
-  constexpr int NW = 32;
-  __shared__ float s_l[NW], s_wl[NW], s_lb[NW];
-  __shared__ int s_correct[NW], s_npos[NW];
-  __shared__ float s_scale, s_bden;
+constexpr int BL_THREADS = 256;
+constexpr int BL_NW = BL_THREADS / 32;
+constexpr int BL_REC = 8;   // floats per partial record: sl, swl, slb, corr, npos
+
+// grid G; CTA g owns rows [g*rpc, min(N, (g+1)*rpc))
+__global__ void __launch_bounds__(BL_THREADS)
+boost_loss_part1_kernel(const LossArgs a, int rpc, const float* __restrict__ cls_score,
+                        const int64_t* __restrict__ labels,
+                        const float* __restrict__ label_weights,
+                        const float* __restrict__ prior,
+                        const float* __restrict__ bbox_pred,
+                        const float* __restrict__ bbox_targets,
+                        const float* __restrict__ bbox_weights,
+                        float* __restrict__ partials, float* __restrict__ grad_cls) {
+  __shared__ float s_l[BL_NW], s_wl[BL_NW], s_lb[BL_NW];
+  __shared__ int s_correct[BL_NW], s_npos[BL_NW];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int C1 = a.C + 1;
-  const int N = a.N;
+  const int r0 = blockIdx.x * rpc, r1 = min(a.N, r0 + rpc);
 
-  // ---- pass 1: softmax / CE per row (one warp per row) ----
   float acc_l = 0.f, acc_wl = 0.f;
   int acc_correct = 0;
-  for (int i = wid; i < N; i += NW) {
+  for (int i = r0 + wid; i < r1; i += BL_NW) {
     const float* x = cls_score + (size_t)i * C1;
     float m = -INFINITY;
     int am = 0x7fffffff;
@@ -78,7 +81,7 @@ boost_loss_kernel(const LossArgs a, const float* __restrict__ cls_score,
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.0f / sum;
     float* g = grad_cls + (size_t)i * C1;
-    for (int c = lane; c < C1; c += 32) g[c] = expf(x[c] - m) * inv;
+    for (int c = lane; c < C1; c += 32) g[c] = expf(x[c] - m) * inv;   // softmax, scaled in part 2
     if (lane == 0) {
       const int64_t lab = labels[i];
       const float lw = label_weights ? label_weights[i] : 1.0f;
@@ -95,10 +98,9 @@ boost_loss_kernel(const LossArgs a, const float* __restrict__ cls_score,
   }
   if (lane == 0) { s_l[wid] = acc_l; s_wl[wid] = acc_wl; s_correct[wid] = acc_correct; }
 
-  // ---- bbox L1 part: thread-strided over rows ----
   float acc_lb = 0.f;
   int acc_npos = 0;
-  for (int i = tid; i < N; i += blockDim.x) {
+  for (int i = r0 + tid; i < r1; i += BL_THREADS) {
     const int64_t lab = labels[i];
     if (lab >= 0 && lab < a.C) {
       ++acc_npos;
@@ -120,24 +122,65 @@ boost_loss_kernel(const LossArgs a, const float* __restrict__ cls_score,
   if (tid == 0) {
     float sl = 0.f, swl = 0.f, slb = 0.f;
     int corr = 0, npos = 0;
-    for (int w = 0; w < NW; ++w) {
+    for (int w = 0; w < BL_NW; ++w) {
       sl += s_l[w]; swl += s_wl[w]; slb += s_lb[w];
       corr += s_correct[w]; npos += s_npos[w];
     }
-    const float s = sl / swl;
-    // loss_cls = sum(l * (w*s)) / N  ==  (s * swl) / N
-    const float bden = a.reg_norm_mean ? (npos > 0 ? (float)(npos * 4) : 1.0f) : (float)N;
-    out[0] = N > 0 ? (s * swl) / (float)N : 0.f;
-    out[1] = npos > 0 ? slb / bden : 0.f;
-    out[2] = N > 0 ? 100.0f * (float)corr / (float)N : 0.f;
-    out[3] = sl; out[4] = swl; out[5] = (float)npos; out[6] = s; out[7] = 0.f;
-    s_scale = s; s_bden = bden;
+    float* rec = partials + (size_t)blockIdx.x * BL_REC;
+    rec[0] = sl; rec[1] = swl; rec[2] = slb;
+    rec[3] = __int_as_float(corr); rec[4] = __int_as_float(npos);
+  }
+}
+
+// grid G (same as part 1)
+__global__ void __launch_bounds__(BL_THREADS)
+boost_loss_part2_kernel(const LossArgs a, int rpc, int G, const float* __restrict__ partials,
+                        const int64_t* __restrict__ labels,
+                        const float* __restrict__ label_weights,
+                        const float* __restrict__ prior,
+                        const float* __restrict__ bbox_pred,
+                        const float* __restrict__ bbox_targets,
+                        const float* __restrict__ bbox_weights,
+                        float* __restrict__ out, float* __restrict__ grad_cls,
+                        float* __restrict__ grad_bbox) {
+  __shared__ float s_scale, s_bden;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int C1 = a.C + 1, N = a.N;
+  if (wid == 0) {
+    // fixed-order reduction of the G records: lane-strided serial sums, then a
+    // fixed shuffle tree (same in every CTA -> same bits everywhere)
+    float sl = 0.f, swl = 0.f, slb = 0.f;
+    int corr = 0, npos = 0;
+    for (int g = lane; g < G; g += 32) {
+      const float* rec = partials + (size_t)g * BL_REC;
+      sl += rec[0]; swl += rec[1]; slb += rec[2];
+      corr += __float_as_int(rec[3]); npos += __float_as_int(rec[4]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sl += __shfl_xor_sync(0xffffffffu, sl, o);
+      swl += __shfl_xor_sync(0xffffffffu, swl, o);
+      slb += __shfl_xor_sync(0xffffffffu, slb, o);
+      corr += __shfl_xor_sync(0xffffffffu, corr, o);
+      npos += __shfl_xor_sync(0xffffffffu, npos, o);
+    }
+    if (lane == 0) {
+      const float s = sl / swl;
+      const float bden = a.reg_norm_mean ? (npos > 0 ? (float)(npos * 4) : 1.0f) : (float)N;
+      if (blockIdx.x == 0) {
+        // loss_cls = sum(l * (w*s)) / N  ==  (s * swl) / N
+        out[0] = N > 0 ? (s * swl) / (float)N : 0.f;
+        out[1] = npos > 0 ? slb / bden : 0.f;
+        out[2] = N > 0 ? 100.0f * (float)corr / (float)N : 0.f;
+        out[3] = sl; out[4] = swl; out[5] = (float)npos; out[6] = s; out[7] = 0.f;
+      }
+      s_scale = s; s_bden = bden;
+    }
   }
   __syncthreads();
   const float s = s_scale, bden = s_bden;
-
-  // ---- pass 2: gradients ----
-  for (int i = wid; i < N; i += NW) {
+  const int r0 = blockIdx.x * rpc, r1 = min(N, r0 + rpc);
+  for (int i = r0 + wid; i < r1; i += BL_NW) {
     const int64_t lab = labels[i];
     const float lw = label_weights ? label_weights[i] : 1.0f;
     const float w = boost_weight(prior[i], a.gamma, a.alpha);
@@ -150,7 +193,7 @@ boost_loss_kernel(const LossArgs a, const float* __restrict__ cls_score,
     }
   }
   if (grad_bbox != nullptr) {
-    for (int i = tid; i < N; i += blockDim.x) {
+    for (int i = r0 + tid; i < r1; i += BL_THREADS) {
       const int64_t lab = labels[i];
       if (lab >= 0 && lab < a.C) {
         const size_t o = a.agnostic ? (size_t)i * 4 : ((size_t)i * a.C + lab) * 4;
@@ -163,6 +206,16 @@ boost_loss_kernel(const LossArgs a, const float* __restrict__ cls_score,
       }
     }
   }
+}
+
+// launch geometry shared by the workspace query and the launcher
+inline void boost_loss_grid(int N, int* G, int* rpc) {
+  int g = (N + BL_NW - 1) / BL_NW;
+  if (g > 148) g = 148;
+  if (g < 1) g = 1;
+  *rpc = (N + g - 1) / g;
+  if (*rpc < 1) *rpc = 1;
+  *G = N > 0 ? (N + *rpc - 1) / *rpc : 1;
 }
 
 }  // namespace brcnn

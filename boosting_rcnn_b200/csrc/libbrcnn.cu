@@ -2,6 +2,7 @@
 // Single translation unit: nvcc -gencode arch=compute_100a,code=sm_100a
 //   -fmad=false -O3 -lineinfo -shared -Xcompiler -fPIC
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -368,6 +369,13 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       const float* maxc_f = (const float*)img_maxc;
+      // BRCNN_DEBUG_TIMING=1: per-phase cycle counters of CTA 0 (debug only; allocates)
+      static long long* dbg_buf = [] {
+        long long* pbuf = nullptr;
+        if (getenv("BRCNN_DEBUG_TIMING")) cudaMalloc(&pbuf, 64);
+        return pbuf;
+      }();
+      long long* dbg = dbg_buf;
       if (cs > 1) {
         if (lay.total > 32 * 1024) {
           e = cudaFuncSetAttribute(rpn_nms_image_kernel<RNI_CLUSTER>,
@@ -378,7 +386,7 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
                                (const float4*)cand_boxes, (const u64*)cand_key,
                                (const uint8_t*)cand_valid, (const int32_t*)cand_count,
                                (int)p->num_levels, (int)d.Kc, p->iou_threshold, maxc_f,
-                               (int)p->max_per_img, proposals, num_proposals, lay);
+                               (int)p->max_per_img, proposals, num_proposals, lay, dbg);
       } else {
         if (lay.total > 32 * 1024) {
           e = cudaFuncSetAttribute(rpn_nms_image_kernel<1>,
@@ -389,9 +397,16 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
                                (const float4*)cand_boxes, (const u64*)cand_key,
                                (const uint8_t*)cand_valid, (const int32_t*)cand_count,
                                (int)p->num_levels, (int)d.Kc, p->iou_threshold, maxc_f,
-                               (int)p->max_per_img, proposals, num_proposals, lay);
+                               (int)p->max_per_img, proposals, num_proposals, lay, dbg);
       }
       if (e != cudaSuccess) return (int)e;
+      if (dbg != nullptr) {
+        long long h[8];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[rpn_nms_image cs=%d] rounds=%lld cycles: windows=%lld rank=%lld pull+diag=%lld "
+                "combine=%lld resolve=%lld\n", cs, h[5], h[0], h[1], h[2], h[3], h[4]);
+      }
       g_launch_count_add(1);
       BRCNN_CUDA_CHECK_LAST();
       return BRCNN_OK;
@@ -725,17 +740,27 @@ int brcnn_nhwc_to_nchw_multi(const float* const* in_host, float* const* out_host
 }
 
 // ------------------------------- loss -------------------------------------
+size_t brcnn_boost_loss_workspace_bytes(const brcnn_loss_params* p) {
+  if (!p || p->num_rois < 0) return 0;
+  int G, rpc;
+  boost_loss_grid(p->num_rois, &G, &rpc);
+  return align256((size_t)G * BL_REC * 4);
+}
+
 int brcnn_boost_loss(const brcnn_loss_params* p, const float* cls_score,
                      const int64_t* labels, const float* label_weights,
                      const float* prior, const float* bbox_pred,
                      const float* bbox_targets, const float* bbox_weights,
                      float* out_scalars, float* grad_cls_score,
-                     float* grad_bbox_pred, brcnn_stream_t stream_) {
+                     float* grad_bbox_pred, void* workspace, size_t workspace_bytes,
+                     brcnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!p || p->num_rois < 0 || p->num_classes <= 0 || !out_scalars) return BRCNN_ERR_ARG;
   if (p->num_rois > 0 && (!cls_score || !labels || !prior || !bbox_pred ||
                           !bbox_targets || !bbox_weights || !grad_cls_score))
     return BRCNN_ERR_ARG;
+  if (!workspace || workspace_bytes < brcnn_boost_loss_workspace_bytes(p))
+    return BRCNN_ERR_WORKSPACE;
   LossArgs a;
   a.N = p->num_rois; a.C = p->num_classes; a.agnostic = p->reg_class_agnostic;
   a.reg_norm_mean = p->reg_norm_mean; a.gamma = p->gamma; a.alpha = p->alpha;
@@ -745,9 +770,17 @@ int brcnn_boost_loss(const brcnn_loss_params* p, const float* cls_score,
     cudaError_t e = cudaMemsetAsync(grad_bbox_pred, 0, nb, stream);
     if (e != cudaSuccess) return (int)e;
   }
-  boost_loss_kernel<<<1, 1024, 0, stream>>>(a, cls_score, labels, label_weights, prior,
-                                            bbox_pred, bbox_targets, bbox_weights,
-                                            out_scalars, grad_cls_score, grad_bbox_pred);
+  int G, rpc;
+  boost_loss_grid(a.N, &G, &rpc);
+  float* partials = (float*)workspace;
+  boost_loss_part1_kernel<<<G, BL_THREADS, 0, stream>>>(
+      a, rpc, cls_score, labels, label_weights, prior, bbox_pred, bbox_targets, bbox_weights,
+      partials, grad_cls_score);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  boost_loss_part2_kernel<<<G, BL_THREADS, 0, stream>>>(
+      a, rpc, G, partials, labels, label_weights, prior, bbox_pred, bbox_targets, bbox_weights,
+      out_scalars, grad_cls_score, grad_bbox_pred);
   g_launch_count_add(1);
   BRCNN_CUDA_CHECK_LAST();
   return BRCNN_OK;

@@ -64,7 +64,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
                      const int32_t* __restrict__ cand_count, int L, int Kc, float thr,
                      const float* __restrict__ img_maxc, int max_out,
                      float* __restrict__ proposals, int32_t* __restrict__ num_proposals,
-                     RpnNmsImageSmem lay) {
+                     RpnNmsImageSmem lay, long long* __restrict__ dbg) {
   extern __shared__ __align__(16) unsigned char rni_smem[];
   float4* kbox = reinterpret_cast<float4*>(rni_smem + lay.kbox);            // local share
   unsigned short* lidx = reinterpret_cast<unsigned short*>(rni_smem + lay.lidx);
@@ -88,6 +88,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
   __shared__ int s_lcnt[BRCNN_MAX_LEVELS];   // LOCAL kept count per level
   __shared__ int s_taken[BRCNN_MAX_LEVELS];
   __shared__ int s_nkept;                    // GLOBAL kept count (same in every CTA)
+  __shared__ int s_lkept;                    // LOCAL kept count (all levels)
 
   const int crank = (CS > 1) ? (int)cg::this_cluster().block_rank() : 0;
   const int b = blockIdx.x / CS;
@@ -98,7 +99,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
     s_count[tid] = (tid < L) ? min(cand_count[b * L + tid], Kc) : 0;
     s_lcnt[tid] = 0;
   }
-  if (tid == 0) s_nkept = 0;
+  if (tid == 0) { s_nkept = 0; s_lkept = 0; }
   __syncthreads();
 
   // window element (l, i) of this thread, prefetched one round ahead
@@ -117,7 +118,12 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
   };
   if (wl < BRCNN_MAX_LEVELS) prefetch(0);
 
+  long long t_prev = 0, t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int n_rounds = 0;
+#define RNI_MARK(i) do { if (dbg != nullptr && tid == 0) { const long long t_now = clock64(); t_acc[i] += t_now - t_prev; t_prev = t_now; } } while (0)
+  if (dbg != nullptr && tid == 0) t_prev = clock64();
   for (int round = 0;; ++round) {
+    ++n_rounds;
     // ---- 1. windows: registers -> smem ----
     if (wl < BRCNN_MAX_LEVELS) {
       w_key[wl][wi] = pk; w_box[wl][wi] = pb; w_valid[wl][wi] = pv;
@@ -129,6 +135,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
     if (tid < 2) { s_dead[tid] = 0xffffffffu; s_hitw[tid] = 0u; }
     if (tid < RNI_TILE) tlvl[tid] = -1;
     __syncthreads();
+    RNI_MARK(0);
     int remaining = 0;
     for (int l = 0; l < L; ++l) remaining += s_wn[l];
     if (remaining == 0) break;                      // cluster-uniform
@@ -144,29 +151,20 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
         lo[l2] = 0;
         hi[l2] = (l2 < L && l2 != wl) ? s_wn[l2] : 0;
       }
-      if (L <= 5) {
-#pragma unroll
-        for (int step = 0; step < 7; ++step) {   // windows hold <= 64 keys
-#pragma unroll
-          for (int l2 = 0; l2 < 5; ++l2) {
-            if (lo[l2] < hi[l2]) {
-              const int mid = (lo[l2] + hi[l2]) >> 1;
-              if (w_key[l2][mid] > key) lo[l2] = mid + 1; else hi[l2] = mid;
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int step = 0; step < 7; ++step) {
-#pragma unroll
-          for (int l2 = 0; l2 < BRCNN_MAX_LEVELS; ++l2) {
-            if (lo[l2] < hi[l2]) {
-              const int mid = (lo[l2] + hi[l2]) >> 1;
-              if (w_key[l2][mid] > key) lo[l2] = mid + 1; else hi[l2] = mid;
-            }
-          }
-        }
+      // branch-free steps: a finished search (lo == hi) re-reads a clamped slot and
+      // keeps its bounds
+#define RNI_SEARCH(NL)                                                        \
+      _Pragma("unroll") for (int step = 0; step < 7; ++step) {                \
+        _Pragma("unroll") for (int l2 = 0; l2 < NL; ++l2) {                   \
+          const int mid = (lo[l2] + hi[l2]) >> 1;                             \
+          const bool open = lo[l2] < hi[l2];                                  \
+          const bool gt = w_key[l2][min(mid, RNI_TILE - 1)] > key;            \
+          lo[l2] = (open && gt) ? mid + 1 : lo[l2];                           \
+          hi[l2] = (open && !gt) ? mid : hi[l2];                              \
+        }                                                                     \
       }
+      if (L <= 5) { RNI_SEARCH(5) } else { RNI_SEARCH(BRCNN_MAX_LEVELS) }
+#undef RNI_SEARCH
       int rank = wi;
 #pragma unroll
       for (int l2 = 0; l2 < BRCNN_MAX_LEVELS; ++l2) rank += lo[l2];
@@ -183,6 +181,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
       }
     }
     __syncthreads();
+    RNI_MARK(1);
     // next round's windows start at cursor + taken: issue the global loads now
     // so that their latency hides behind pull / diag / resolve
     if (wl < L) prefetch(s_cursor[wl] + s_taken[wl]);
@@ -235,6 +234,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
       }
     }
     __syncthreads();
+    RNI_MARK(2);
     // ---- combine pull hits and diag rows of the cluster (one cluster barrier) ----
     if (CS > 1) {
       if (tid == 0) s_hit[round & 1] = ((u64)s_hitw[1] << 32) | (u64)s_hitw[0];
@@ -270,6 +270,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
       }
     }
     __syncthreads();
+    RNI_MARK(3);
     const u64 alive = s_alive;
     if (alive != 0ull) {   // cluster-uniform
       // ---- 5. resolve (warp 0; identical in every CTA) ----
@@ -303,9 +304,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
           if ((mine >> r) & 1ull) {
             const u64 below = mine & ((1ull << r) - 1ull);
             const int l = tlvl[r];
-            int slot = 0;
-            for (int l2 = 0; l2 < L; ++l2) slot += s_lcnt[l2];   // local kept so far
-            slot += __popcll(below);
+            const int slot = s_lkept + __popcll(below);      // local kept so far
             kbox[slot] = tb[r];
             lidx[(size_t)l * kp + s_lcnt[l] + __popcll(below & s_lmask[l])] =
                 (unsigned short)slot;
@@ -322,11 +321,12 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
         }
         __syncwarp();
         if (lane < L) s_lcnt[lane] += __popcll(mine & s_lmask[lane]);
-        if (lane == 0) s_nkept = nkept + __popcll(keep);
+        if (lane == 0) { s_nkept = nkept + __popcll(keep); s_lkept += __popcll(mine); }
       }
     }
     if (tid < L) s_cursor[tid] += s_taken[tid];
     __syncthreads();
+    RNI_MARK(4);
     if (s_nkept >= max_out) break;                  // cluster-uniform
   }
   __syncthreads();
@@ -335,6 +335,10 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
     if (tid == 0) num_proposals[b] = nk;
     for (int i = nk * 5 + tid; i < max_out * 5; i += RNI_THREADS)
       proposals[(size_t)b * max_out * 5 + i] = 0.f;
+  }
+  if (dbg != nullptr && tid == 0 && blockIdx.x == 0) {
+    for (int i = 0; i < 5; ++i) dbg[i] = t_acc[i];
+    dbg[5] = n_rounds;
   }
   // nobody leaves while a peer may still read its hit masks
   if (CS > 1) cg::this_cluster().sync();

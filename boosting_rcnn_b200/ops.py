@@ -450,12 +450,13 @@ class _BoostLossFunction(Function):
         out = torch.empty((8,), dtype=torch.float32, device=cls_score.device)
         g_cls = torch.empty_like(cls_score)
         g_box = torch.empty_like(bbox_pred)
+        ws = _ws(lib.brcnn_boost_loss_workspace_bytes(p), cls_score.device)
         check(lib.brcnn_boost_loss(
             p, cls_score.data_ptr(), labels.data_ptr(),
             label_weights.data_ptr() if label_weights is not None else None,
             prior.data_ptr(), bbox_pred.data_ptr(), bbox_targets.data_ptr(),
             bbox_weights.data_ptr(), out.data_ptr(), g_cls.data_ptr(),
-            g_box.data_ptr(), _stream()), 'brcnn_boost_loss')
+            g_box.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), 'brcnn_boost_loss')
         ctx.save_for_backward(g_cls, g_box)
         loss_cls, loss_bbox, acc = out[0], out[1], out[2]
         ctx.mark_non_differentiable(acc)

@@ -218,12 +218,14 @@ typedef struct brcnn_loss_params {
  *                          weight_scale s, 0}
  * grad_cls_score (N,C+1) and grad_bbox_pred (N,4C | N,4) are d(loss_cls)/d.
  * and d(loss_bbox)/d. for an upstream gradient of 1.                       */
+size_t brcnn_boost_loss_workspace_bytes(const brcnn_loss_params* p);
 int brcnn_boost_loss(const brcnn_loss_params* p, const float* cls_score,
                      const int64_t* labels, const float* label_weights,
                      const float* prior, const float* bbox_pred,
                      const float* bbox_targets, const float* bbox_weights,
                      float* out_scalars, float* grad_cls_score,
-                     float* grad_bbox_pred, brcnn_stream_t stream);
+                     float* grad_bbox_pred, void* workspace, size_t workspace_bytes,
+                     brcnn_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * (5) Probabilistic score fusion + per-class decode + class-wise NMS
