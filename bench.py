@@ -36,7 +36,7 @@ SCALE_FACTOR = (1.6662, 1.6667, 1.6662, 1.6667)
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=16, help='images per GPU per step')
@@ -146,7 +146,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(['nvidia-smi', f'--id={gpu_index}', f'--query-gpu={self.Q}',
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                       '--format=csv,noheader,nounits', '-lms', '50'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -518,7 +518,6 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     from boosting_rcnn_b200 import _lib, ops
     from boosting_rcnn_b200.registry import ConfigDict
-    from boosting_rcnn_b200.roi_head import padded_rois
     lib = _lib.load()
     rpn_head, roi_head = rpn_head.to(dev).eval(), roi_head.to(dev).eval()
     sizes, h_feats, h_cls, h_box, h_iou = make_inputs(B, pad_hw, A, C, seed=1234 + rank, pin=True)
@@ -598,14 +597,14 @@ def main():
             torch.cuda.current_stream().wait_stream(pipe.compute_stream)
 
     W, K = max(args.warmup, 3), args.steps
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # covers all three timed loops
     ms = timed(step, K, W)
     launches = launches_per_step * K
-    clocks = sampler.stop() if sampler else None
     ms_cl = timed(step_cl, K, W)
     e2e = E2E()
     k_e2e = max(K // 2, 4)
     ms_e2e = timed(e2e.step, k_e2e, 3, drain=e2e.drain)
+    clocks = sampler.stop() if sampler else None
 
     # -------------------------------------------------- per-stage device times
     stage_ms, roof = {}, None
@@ -671,7 +670,7 @@ def main():
             traffic = json.load(open(tpath)).get(f'{args.cfg}_b{B}', {})
         # algorithmic bytes per launch (DESIGN.md §4 / SURVEY.md §8d)
         kern = {
-            'roi_align_fwd_kernel': dict(bytes=out_bytes + min(fp, feat_bytes),
+            'roi_align_fwd_tma_kernel': dict(bytes=out_bytes + min(fp, feat_bytes),
                                          ms=stage_ms['roi_align_fwd'], live_rois=n_live,
                                          rois=int(rois_h.shape[0])),
             'transpose_multi_kernel': dict(bytes=2 * feat_bytes, ms=stage_ms['nchw_to_nhwc_x5']),

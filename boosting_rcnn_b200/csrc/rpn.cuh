@@ -166,15 +166,31 @@ rpn_topk_decode_kernel(const __grid_constant__ RpnArgs a,
       }
     }
   };
+  // e = an*P + p  ->  concatenated anchor index idx_base + p*A + an.  The
+  // division by the per-level constant P is a float reciprocal + fix-up while
+  // e is exactly representable in fp32 (e < 2^24), an integer division otherwise.
+  const float inv_P = 1.0f / (float)P;
+  const bool small_e = total < (1 << 24);
   auto composite = [&](int e, uint32_t key) {
-    const int an = e / P, p = e - an * P;
+    int an;
+    if (small_e) {
+      an = __float2int_rz(__int2float_rn(e) * inv_P);
+      const int rem = e - an * P;
+      an += (rem >= P) - (rem < 0);
+    } else {
+      an = e / P;
+    }
+    const int p = e - an * P;
     return rpn_make_key(key, (uint32_t)(lv.idx_base + p * A + an));
   };
 
   // ---- exact selection threshold on the 64-bit composite ----
   // stop refining once the survivors fit the sort we would do anyway
+  // (the bitonic sort pads to a power of two: refining until the survivors fit
+  // next_pow2(k) halves the sort compared with stopping at 2*next_pow2(k))
   int sort_cap = 2;
-  while (sort_cap < 2 * k) sort_cap <<= 1;
+  while (sort_cap < k) sort_cap <<= 1;
+  if (sort_cap - k < 64) sort_cap <<= 1;   // too little slack: an extra key scan costs more
   if (sort_cap > a.cand_cap) sort_cap = a.cand_cap;
   u64 prefix = 0, pmask = 0;
   if (k < n) {
