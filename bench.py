@@ -383,59 +383,51 @@ def bench_train(args, rank, world, local_rank):
 
 
 def bench_stress(args, rank, world, local_rank):
-    """configs[4]: 5 levels x 4000 pre-NMS boxes per image, batched NMS
-    (ids = level, IoU 0.7), keep 2000, then 2000 RoIs/img through RoIAlign."""
-    from boosting_rcnn_b200 import _lib, ops
+    """configs[4]: proposal stress test — 5 FPN levels, 4000 pre-NMS proposals per
+    level, 2000 post-NMS RoIs per image, then all RoIs through RoIAlign.  One CUDA
+    graph: brcnn_rpn_get_bboxes (nms_pre 4000 / max 2000) -> bbox2roi -> RoIAlign."""
+    from boosting_rcnn_b200 import _lib, configs, ops
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     dist = _dist_setup(world, dev)
     lib = _lib.load()
-    B, C = args.batch, 256
-    pad_hw, img_hw = (800, 1344), (800, 1333)
-    sizes = [(-(-pad_hw[0] // s), -(-pad_hw[1] // s)) for s in STRIDES]
-    rng = np.random.RandomState(99 + rank)
-    boxes, scores, ids = [], [], []
-    for b in range(B):
-        bl, il = [], []
-        for l in range(5):
-            ctr = rng.rand(4000, 2) * [img_hw[1], img_hw[0]]
-            wh = np.exp(rng.uniform(np.log(8 * 2 ** l), np.log(64 * 2 ** l), (4000, 2)))
-            bx = np.concatenate([ctr - wh / 2, ctr + wh / 2], 1)
-            bx[:, 0::2] = bx[:, 0::2].clip(0, img_hw[1])
-            bx[:, 1::2] = bx[:, 1::2].clip(0, img_hw[0])
-            bl.append(bx)
-            il.append(np.full(4000, l))
-        boxes.append(torch.from_numpy(np.concatenate(bl).astype(np.float32)).to(dev))
-        ids.append(torch.from_numpy(np.concatenate(il)).to(dev))
-        scores.append(torch.from_numpy(rng.permutation(20000).astype(np.float32) / 20000).to(dev))
-    g = torch.Generator().manual_seed(5 + rank)
-    feats = [torch.randn(B, C, h, w, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
-             for h, w in sizes]
+    geom = configs.IMAGE_GEOMETRY['coco']
+    B = args.batch
+    rpn_head, roi_head, model = configs.build_hot_path('coco')
+    rpn_head = rpn_head.to(dev).eval()
+    A, C = rpn_head.num_anchors, 256
+    sizes, h_feats, h_cls, h_box, h_iou = make_inputs(B, geom['pad_shape'][:2], A, C,
+                                                      seed=99 + rank, pin=False)
+    metas = img_metas_for(B, geom)
+    feats = [t.to(dev).contiguous(memory_format=torch.channels_last) for t in h_feats]
+    cls, box, iou = ([t.to(dev) for t in ts] for ts in (h_cls, h_box, h_iou))
+    cfg = dict(nms_pre=4000, max_per_img=2000, nms=dict(type='nms', iou_threshold=0.7),
+               min_bbox_size=0)
     scales = [1.0 / s for s in STRIDES]
-    nms_cfg = dict(type='nms', iou_threshold=0.7)
 
-    def nms_all():
-        rois = []
-        for b in range(B):
-            dets, _ = ops.batched_nms(boxes[b], scores[b], ids[b], nms_cfg)
-            d = dets[:2000]
-            rois.append(torch.cat([d.new_full((d.size(0), 1), float(b)), d[:, :4]], 1))
-        return torch.cat(rois)
+    @torch.no_grad()
+    def fn():
+        props = rpn_head.get_bboxes_padded(cls, box, iou, metas, cfg=cfg)
+        rois, _ = ops.bbox2roi_padded(props.boxes, props.num)
+        return props, rois, ops.roi_extract(feats, rois, scales, 7)
 
-    def step():
-        return ops.roi_extract(feats, nms_all(), scales, 7)
-
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    l0 = lib.brcnn_launch_count()
+    with torch.cuda.graph(g):
+        props, rois, rf = fn()
+    per_step = int(lib.brcnn_launch_count() - l0)
     K, W = args.steps, max(args.warmup, 3)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    l0 = lib.brcnn_launch_count()
-    ms = _timed_steps(step, K, W, world, dist, dev)
-    launches = (lib.brcnn_launch_count() - l0) * K // (K + W)
+    ms = _timed_steps(g.replay, K, W, world, dist, dev)
     clocks = sampler.stop() if sampler else None
     if rank == 0:
         peak, peak_src = _peak()
-        rois = nms_all()
-        t_nms = _dev_time(nms_all, 5, dev)
-        t_roi = _dev_time(lambda: ops.roi_extract(feats, rois, scales, 7), 10, dev)
+        with torch.no_grad():
+            t_rpn = _dev_time(lambda: rpn_head.get_bboxes_padded(cls, box, iou, metas, cfg=cfg), 10, dev)
+            t_roi = _dev_time(lambda: ops.roi_extract(feats, rois, scales, 7), 10, dev)
         rois_h = rois.cpu().numpy()
         feat_bytes = sum(f.numel() * 4 for f in feats)
         nbytes = rois_h.shape[0] * C * 49 * 4 + min(roi_footprint_bytes(rois_h, sizes, C), feat_bytes)
@@ -445,14 +437,15 @@ def bench_stress(args, rank, world, local_rank):
             'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': dict(workload=f'proposal stress: 5 levels x 4000 pre-NMS boxes, 2000 post-NMS '
-                                    f'RoIs/img, {B} images per GPU', images_per_gpu=B,
-                           rois=int(rois_h.shape[0])),
-            'gpu_launches': int(launches), 'clocks': clocks,
+            'config': dict(workload=f'proposal stress: 5 levels x 4000 pre-NMS proposals, 2000 '
+                                    f'post-NMS RoIs/img through RoIAlign, {B} images per GPU',
+                           images_per_gpu=B, rpn=cfg, rois=int(rois_h.shape[0]),
+                           live_rois=int((rois_h[:, 0] >= 0).sum())),
+            'gpu_launches': per_step * K, 'clocks': clocks,
             'roofline': dict(kernel='roi_align_fwd_tma_kernel', bound='hbm', achieved=ach, peak=peak,
                              unit='GB/s', frac=ach / peak, traffic=None, peak_source=peak_src,
                              algorithmic_bytes_per_launch=nbytes, ms_per_launch=t_roi),
-            'stages_ms': {'batched_nms_x%d' % B: t_nms, 'roi_align_fwd': t_roi}}))
+            'stages_ms': {'rpn_get_bboxes_4000_2000': t_rpn, 'roi_align_fwd': t_roi}}))
     if dist:
         dist.destroy_process_group()
     return 0
@@ -547,6 +540,12 @@ def main():
                             rcnn_test_cfg=test_rcnn, rescale=True)
         step, step_cl = g_nchw.replay, g_cl.replay
         launches_per_step = g_nchw.launches_per_replay
+        # informational only: the reference pins PyTorch 1.7, whose default lets cuBLAS use
+        # TF32 for the 2-fc head on Ampere+; the headline keeps IEEE fp32 GEMMs
+        torch.backends.cuda.matmul.allow_tf32 = True
+        g_tf32 = HotPathGraph(rpn_head, roi_head, metas, d_feats, d_cls, d_box, d_iou,
+                              rcnn_test_cfg=test_rcnn, rescale=True)
+        torch.backends.cuda.matmul.allow_tf32 = False
 
     # end to end: pinned host buffers -> H2D -> graph -> D2H, double buffered
     pipe = HostPipeline(rpn_head, roi_head, metas, (h_feats, h_cls, h_box, h_iou),
@@ -601,6 +600,7 @@ def main():
     ms = timed(step, K, W)
     launches = launches_per_step * K
     ms_cl = timed(step_cl, K, W)
+    ms_tf32 = None if args.no_graph else timed(g_tf32.replay, K, W)
     e2e = E2E()
     k_e2e = max(K // 2, 4)
     ms_e2e = timed(e2e.step, k_e2e, 3, drain=e2e.drain)
@@ -717,6 +717,7 @@ def main():
             'config': dict(base_cfg, feat_layout='NCHW-contiguous FPN maps in (reference neck '
                            'layout); NCHW->NHWC conversion kernels are inside the timed step'),
             'value_channels_last_feats': B * world * K / (ms_cl * 1e-3),
+            'value_tf32_head_informational': (B * world * K / (ms_tf32 * 1e-3)) if ms_tf32 else None,
             'e2e': {'value': B * world * k_e2e / (ms_e2e * 1e-3), 'unit': 'images/s',
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / k_e2e},
