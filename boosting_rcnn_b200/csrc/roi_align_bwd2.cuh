@@ -29,7 +29,8 @@
 namespace brcnn {
 
 constexpr int B2_TS = 8;            // tile side in pixels
-constexpr int B2_CCH = 128;         // channels per CTA (32 quads: 4 groups x 8)
+constexpr int B2_QPT = 8;           // channel quads per thread
+constexpr int B2_CCH = 16 * B2_QPT;  // channels per CTA (4 quad groups x B2_QPT quads)
 constexpr int B2_THREADS = 256;     // 8 rows x 8 px x 4 quad groups
 constexpr int B2_LIST = 1024;       // RoIs gathered per round
 constexpr int B2_P = 7;             // max pooled side on this path
@@ -119,17 +120,17 @@ roi_bwd_gather2_kernel(const __grid_constant__ RoiBwd2Args ba,
   const int c0 = blockIdx.y * B2_CCH;
   const int PW = a.PW, nbins = a.PH * a.PW;
   const unsigned short mykey = (unsigned short)(b * a.L + lvl);
-  // warp = tile row, lane = (x, quad group); thread owns quads qg + 4*k, k < 8
+  // warp = tile row, lane = (x, quad group); thread owns quads qg + 4*k, k < B2_QPT
   const int y = y0 + wid;
   const int x = x0 + (lane >> 2);
   const int qg = lane & 3;
   const int cbase = c0 + qg * 4;            // channel of quad k: cbase + 16*k
-  const int nq = max(0, min(8, (C - cbase + 15) / 16));  // valid quads of this thread
+  const int nq = max(0, min(B2_QPT, (C - cbase + 15) / 16));  // valid quads of this thread
   const int TR = ba.TR;
 
-  float4 acc[8];
+  float4 acc[B2_QPT];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < B2_QPT; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   int r_next = 0;
   while (r_next < R) {
@@ -188,7 +189,7 @@ roi_bwd_gather2_kernel(const __grid_constant__ RoiBwd2Args ba,
             const float w = wy * __ldg(tx_row + pw);
             const float* gp = gr + (size_t)(ph * PW + pw) * C;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < B2_QPT; ++k) {
               if (k < nq) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(gp + 16 * k));
                 acc[k].x = fmaf(w, v.x, acc[k].x);
@@ -206,7 +207,7 @@ roi_bwd_gather2_kernel(const __grid_constant__ RoiBwd2Args ba,
   if (y < H && x < W) {
     float* gout = ba.grad[lvl] + (((size_t)b * H + y) * W + x) * C + cbase;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < B2_QPT; ++k)
       if (k < nq) *reinterpret_cast<float4*>(gout + 16 * k) = acc[k];
   }
 }
