@@ -176,7 +176,7 @@ static int rpn_derive(const brcnn_rpn_params* p, RpnDerived* d) {
 
 struct RpnWsInternal {
   brcnn_rpn_ws_layout pub;
-  size_t mask, kept_key, keys, ghist, zero_bytes;
+  size_t mask, kept_key, keys, ghist, cand_n, cand_raw, zero_bytes;
 };
 static int rpn_ws(const brcnn_rpn_params* p, RpnWsInternal* w) {
   RpnDerived d;
@@ -192,7 +192,9 @@ static int rpn_ws(const brcnn_rpn_params* p, RpnWsInternal* w) {
   w->pub.cand_count = o; o = align256(o + S * 4);
   w->pub.img_maxc = o;   o = align256(o + (size_t)p->batch * 4);
   w->ghist = o;          o = align256(o + S * RPN_BINS * 4);
-  w->zero_bytes = o - (size_t)w->pub.img_maxc;  // img_maxc + ghist, zeroed per call
+  w->cand_n = o;         o = align256(o + S * 4);
+  w->zero_bytes = o - (size_t)w->pub.img_maxc;  // img_maxc + ghist + cand_n, zeroed per call
+  w->cand_raw = o;       o = align256(o + S * (size_t)d.cand_cap * 8);
   w->keys = o;           o = align256(o + (size_t)p->batch * d.key_stride * 4);
   w->pub.kept_pos = o;   o = align256(o + S * d.keep_cap * 4);
   w->pub.kept_count = o; o = align256(o + S * 4);
@@ -316,6 +318,8 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
   u64* mask = (u64*)(ws + w.mask);
   uint32_t* keys = (uint32_t*)(ws + w.keys);
   uint32_t* ghist = (uint32_t*)(ws + w.ghist);
+  int32_t* cand_n = (int32_t*)(ws + w.cand_n);
+  u64* cand_raw = (u64*)(ws + w.cand_raw);
   const int S = p->batch * p->num_levels;
 
   // img_maxc and ghist are adjacent in the workspace: one memset
@@ -324,6 +328,9 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
   {
     dim3 grid(chunk_base, p->batch);
     rpn_score_kernel<<<grid, RPN_SCORE_THREADS, 0, stream>>>(a, keys, ghist);
+    g_launch_count_add(1);
+    BRCNN_CUDA_CHECK_LAST();
+    rpn_collect_kernel<<<grid, RPN_SCORE_THREADS, 0, stream>>>(a, keys, ghist, cand_raw, cand_n);
     g_launch_count_add(1);
     BRCNN_CUDA_CHECK_LAST();
   }
@@ -337,7 +344,7 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
     dim3 grid(p->batch, p->num_levels);
     rpn_topk_decode_kernel<<<grid, RPN_TOPK_THREADS, smem, stream>>>(
         a, keys, ghist, base_anchors, img_hw, cand_boxes, cand_key, cand_valid, cand_count,
-        img_maxc);
+        img_maxc, cand_raw, cand_n);
     g_launch_count_add(1);
     BRCNN_CUDA_CHECK_LAST();
   }

@@ -2,16 +2,21 @@
 //
 //   rpn_score_kernel        whole-GPU pass over the RPN outputs: key =
 //       bits(sqrt(sigmoid(cls) * sigmoid(iou))) written once (plane order,
-//       coalesced) plus a 2048-bin histogram of the top 11 key bits per
-//       (image, level) segment (shared-memory privatised, flushed with
-//       integer atomics).
-//   rpn_topk_decode_kernel  one CTA per segment: exact top-k by radix
-//       selection on the 64-bit composite (score_bits << 32 | ~anchor_index),
-//       i.e. (score desc, index asc) with no ties; pass 0 reuses the
-//       histogram of the score kernel, further passes (only needed when the
-//       scores are concentrated) re-scan the L2-resident keys.  The <= cap
-//       survivors are bitonic-sorted in shared memory and the first k decoded
-//       (anchor built on the fly + delta2bbox + clip + min-size flag).
+//       coalesced) plus a 2048-bin histogram of the score VALUE
+//       (bin = floor(s * 2048), uniform over [0,1]) per (image, level)
+//       segment (shared-memory privatised, flushed with integer atomics).
+//   rpn_collect_kernel      whole-GPU pass over the L2-resident keys: every CTA
+//       re-derives its segment's threshold bin d (#(bins > d) < k <= #(bins >=
+//       d)) from the histogram and appends the keys with s >= d/2048 -- a
+//       superset of the top-k, typically k + ~100 -- as 64-bit composites
+//       (score_bits << 32 | ~anchor_index) to the segment's candidate buffer
+//       (CTA-aggregated: one global atomic per CTA).
+//   rpn_topk_decode_kernel  one CTA per segment: bitonic sort of the collected
+//       composites in shared memory = (score desc, index asc) with no ties,
+//       first k decoded (anchor built on the fly + delta2bbox + clip +
+//       min-size flag).  If the threshold bin is over-populated (degenerate
+//       score distributions) the CTA falls back to an exact radix selection
+//       on the composite by re-scanning the keys itself.
 //   nms_fused / nms_mask+sweep / nms_merge (nms_kernels.cuh) finish the job.
 //
 // Reference behaviour: atss_rpn_head.py:688-760.
@@ -48,6 +53,17 @@ struct RpnArgs {
   float max_ratio, min_size;
 };
 
+// histogram bin of a score: monotone in s on [0,1]; NaN (largest key bits) -> top bin
+__device__ __forceinline__ uint32_t rpn_value_bin(float s) {
+  if (!(s == s)) return RPN_BINS - 1;
+  const int bin = (int)(s * (float)RPN_BINS);   // exact scaling by a power of two
+  return (uint32_t)min(max(bin, 0), RPN_BINS - 1);
+}
+// key bits of the lower edge of bin d: bin(s) >= d  <=>  key_bits(s) >= this (s >= 0 or NaN)
+__device__ __forceinline__ uint32_t rpn_bin_floor_bits(int d) {
+  return __float_as_uint((float)d / (float)RPN_BINS);
+}
+
 __device__ __forceinline__ u64 rpn_make_key(uint32_t score_bits, uint32_t concat_idx) {
   return ((u64)score_bits << 32) | (u64)(0xFFFFFFFFu - concat_idx);
 }
@@ -74,7 +90,7 @@ rpn_score_kernel(const __grid_constant__ RpnArgs a, uint32_t* __restrict__ keys,
       const float s = sqrtf(pinned_sigmoid(__ldg(cls + e)) * pinned_sigmoid(__ldg(iou + e)));
       const uint32_t key = __float_as_uint(s);
       kout[e] = key;
-      atomicAdd(&sh[key >> 21], 1u);
+      atomicAdd(&sh[rpn_value_bin(s)], 1u);
     }
   }
   __syncthreads();
@@ -123,6 +139,103 @@ __device__ __forceinline__ void rpn_find_digit(const uint32_t* sh, int nb, uint3
   __syncthreads();
 }
 
+// Same search with 256 threads (8 digits per thread, descending).
+__device__ __forceinline__ void rpn_find_digit_256(const uint32_t* __restrict__ hist, int nb,
+                                                   uint32_t krem, uint32_t* s_warp, int* out) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint32_t c[8];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int d = nb - 1 - 8 * tid - j;
+    c[j] = (d >= 0) ? hist[d] : 0u;
+    sum += c[j];
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (int w = 0; w < wid; ++w) wbase += s_warp[w];
+  uint32_t run = incl - sum + wbase;   // #(digits above this thread's first digit)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (run < krem && krem <= run + c[j]) {
+      out[0] = nb - 1 - 8 * tid - j; out[1] = (int)run; out[2] = (int)c[j];
+    }
+    run += c[j];
+  }
+  __syncthreads();
+}
+
+// grid (chunks_per_image, B), same chunking as the score kernel
+__global__ void __launch_bounds__(RPN_SCORE_THREADS)
+rpn_collect_kernel(const __grid_constant__ RpnArgs a, const uint32_t* __restrict__ keys,
+                   const uint32_t* __restrict__ ghist, u64* __restrict__ cand_raw,
+                   int32_t* __restrict__ cand_n) {
+  __shared__ u64 s_buf[RPN_SCORE_CHUNK];
+  __shared__ uint32_t s_warp[RPN_SCORE_THREADS / 32];
+  __shared__ int s_out[3];
+  __shared__ int s_cnt, s_base;
+  const int b = blockIdx.y;
+  int l = 0;
+  while (l + 1 < a.L && (int)blockIdx.x >= a.lv[l + 1].chunk_base) ++l;
+  const RpnLevel& lv = a.lv[l];
+  const int seg = b * a.L + l;
+  const int n = lv.n, k = lv.k, P = lv.H * lv.W, A = a.A;
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint32_t thr = 0u;
+  if (k < n) {
+    rpn_find_digit_256(ghist + (size_t)seg * RPN_BINS, RPN_BINS, (uint32_t)k, s_warp, s_out);
+    if (s_out[1] + s_out[2] > a.cand_cap) return;   // over-populated bin: slow path (block-uniform)
+    thr = rpn_bin_floor_bits(s_out[0]);
+  } else if (n > a.cand_cap) {
+    return;
+  }
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  const int e0 = ((int)blockIdx.x - lv.chunk_base) * RPN_SCORE_CHUNK;
+  const uint32_t* kseg = keys + (size_t)b * a.key_stride + lv.key_off;
+  const float inv_P = 1.0f / (float)P;
+#pragma unroll 4
+  for (int j = 0; j < RPN_SCORE_CHUNK / RPN_SCORE_THREADS; ++j) {
+    const int e = e0 + j * RPN_SCORE_THREADS + tid;
+    uint32_t key = 0u;
+    bool take = false;
+    if (e < n) {
+      key = __ldg(kseg + e);
+      take = key >= thr;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&s_cnt, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (take) {
+        // e = an*P + p -> concatenated anchor index idx_base + p*A + an
+        int an = (n < (1 << 24)) ? __float2int_rz(__int2float_rn(e) * inv_P) : e / P;
+        int rem = e - an * P;
+        an += (rem >= P) - (rem < 0);
+        const int p = e - an * P;
+        s_buf[base + __popc(m & ((1u << lane) - 1u))] =
+            rpn_make_key(key, (uint32_t)(lv.idx_base + p * A + an));
+      }
+    }
+  }
+  __syncthreads();
+  const int cnt = s_cnt;
+  if (cnt == 0) return;
+  if (tid == 0) s_base = atomicAdd(cand_n + seg, cnt);
+  __syncthreads();
+  u64* dst = cand_raw + (size_t)seg * a.cand_cap + s_base;
+  for (int i = tid; i < cnt; i += RPN_SCORE_THREADS) dst[i] = s_buf[i];
+}
+
 // grid (B, L): x = image so that the heavy level-0 CTAs are scheduled first.
 // dynamic smem: cand_cap u64
 __global__ void __launch_bounds__(RPN_TOPK_THREADS)
@@ -133,7 +246,8 @@ rpn_topk_decode_kernel(const __grid_constant__ RpnArgs a,
                        const float* __restrict__ img_hw,
                        float4* __restrict__ cand_boxes, u64* __restrict__ cand_key,
                        uint8_t* __restrict__ cand_valid, int32_t* __restrict__ cand_count,
-                       int* __restrict__ img_maxc_bits) {
+                       int* __restrict__ img_maxc_bits, const u64* __restrict__ cand_raw,
+                       const int32_t* __restrict__ cand_n) {
   extern __shared__ __align__(16) u64 cand[];
   __shared__ uint32_t sh[RPN_BINS];
   __shared__ uint32_t s_warp[32];
@@ -184,7 +298,25 @@ rpn_topk_decode_kernel(const __grid_constant__ RpnArgs a,
     return rpn_make_key(key, (uint32_t)(lv.idx_base + p * A + an));
   };
 
-  // ---- exact selection threshold on the 64-bit composite ----
+  // ---- fast path: the collect kernel already gathered a superset of the top-k ----
+  bool fast;
+  if (k < n) {
+    for (int i = tid; i < RPN_BINS; i += RPN_TOPK_THREADS) sh[i] = ghist[(size_t)seg * RPN_BINS + i];
+    __syncthreads();
+    rpn_find_digit(sh, RPN_BINS, (uint32_t)k, s_warp, s_out);
+    fast = (s_out[1] + s_out[2] <= a.cand_cap);   // same rule as rpn_collect_kernel
+    __syncthreads();
+  } else {
+    fast = (n <= a.cand_cap);
+  }
+  if (fast) {
+    const int nc = cand_n[seg];
+    const u64* src = cand_raw + (size_t)seg * a.cand_cap;
+    for (int i = tid; i < nc; i += RPN_TOPK_THREADS) cand[i] = src[i];
+    if (tid == 0) s_ncand = nc;
+    __syncthreads();
+  } else {
+  // ---- slow path: exact selection threshold on the 64-bit composite ----
   // stop refining once the survivors fit the sort we would do anyway
   // (the bitonic sort pads to a power of two: refining until the survivors fit
   // next_pow2(k) halves the sort compared with stopping at 2*next_pow2(k))
@@ -199,17 +331,12 @@ rpn_topk_decode_kernel(const __grid_constant__ RpnArgs a,
     for (int pass = 0; pass < 6; ++pass) {
       const int shift = (pass < 5) ? 53 - 11 * pass : 0;
       const int nb = (pass < 5) ? RPN_BINS : 512;
-      if (pass == 0) {
-        const uint32_t* gh = ghist + (size_t)seg * RPN_BINS;
-        for (int i = tid; i < RPN_BINS; i += RPN_TOPK_THREADS) sh[i] = gh[i];
-      } else {
-        for (int i = tid; i < RPN_BINS; i += RPN_TOPK_THREADS) sh[i] = 0;
-        __syncthreads();
-        scan((uint32_t)(pmask >> 32), (uint32_t)(prefix >> 32), [&](int e, uint32_t key) {
-          const u64 c = composite(e, key);
-          if ((c & pmask) == prefix) atomicAdd(&sh[(uint32_t)(c >> shift) & (nb - 1)], 1u);
-        });
-      }
+      for (int i = tid; i < RPN_BINS; i += RPN_TOPK_THREADS) sh[i] = 0;
+      __syncthreads();
+      scan((uint32_t)(pmask >> 32), (uint32_t)(prefix >> 32), [&](int e, uint32_t key) {
+        const u64 c = composite(e, key);
+        if ((c & pmask) == prefix) atomicAdd(&sh[(uint32_t)(c >> shift) & (nb - 1)], 1u);
+      });
       __syncthreads();
       rpn_find_digit(sh, nb, krem, s_warp, s_out);
       const int d = s_out[0], excl = s_out[1], cnt = s_out[2];
@@ -258,6 +385,7 @@ rpn_topk_decode_kernel(const __grid_constant__ RpnArgs a,
     }
   }
   __syncthreads();
+  }  // slow path
   const int ncand = s_ncand;
   int np = 1;
   while (np < ncand) np <<= 1;

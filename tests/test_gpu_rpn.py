@@ -23,12 +23,14 @@ def _anchor_gen(num_scales=3, ratios=(0.5, 1.0, 2.0)):
 
 def _run_case(dev, batch, pad_hw, img_hw, nms_pre, max_per_img, iou_thr, seed,
               num_scales=3, ratios=(0.5, 1.0, 2.0), duplicate_frac=0.0, box_std=0.3,
-              min_bbox_size=0.0):
+              min_bbox_size=0.0, cls_std=1.5, mutate=None):
     gen = _anchor_gen(num_scales, ratios)
     A = gen.num_base_anchors[0]
     sizes = synth.featmap_sizes(*pad_hw)
-    cls, box, iou = synth.rpn_outputs(batch, sizes, A, seed=seed,
+    cls, box, iou = synth.rpn_outputs(batch, sizes, A, seed=seed, cls_std=cls_std,
                                       duplicate_frac=duplicate_frac, box_std=box_std)
+    if mutate is not None:
+        mutate(cls, iou)
     base = gen.base_anchor_table()
     img_hw_arr = np.array([img_hw] * batch, dtype=np.float32)
     p = ops.make_rpn_params(batch, sizes, synth.STRIDES, A, nms_pre, max_per_img,
@@ -90,6 +92,27 @@ def test_rpn_small_duplicates(cuda):
     # heavy exact ties in the scores: tie-break (score desc, index asc)
     _run_case(cuda, batch=3, pad_hw=(192, 256), img_hw=(192, 250), nms_pre=200,
               max_per_img=64, iou_thr=0.7, seed=2, duplicate_frac=0.9)
+
+
+def test_rpn_concentrated_scores_slow_path(cuda):
+    # degenerate score distributions over-populate the threshold bin of the value
+    # histogram (> smem candidate slots): the top-k kernel must fall back to the exact
+    # radix selection.  (a) every logit identical, (b) a narrow spread, (c) one level
+    # constant and the others random
+    def const(cls, iou):
+        for c, u in zip(cls, iou):
+            c[...] = 0.25
+            u[...] = -0.5
+    _run_case(cuda, batch=2, pad_hw=(256, 320), img_hw=(250, 317), nms_pre=300,
+              max_per_img=100, iou_thr=0.7, seed=21, mutate=const)
+    _run_case(cuda, batch=1, pad_hw=(512, 640), img_hw=(500, 600), nms_pre=1000,
+              max_per_img=300, iou_thr=0.7, seed=22, cls_std=1e-4)
+
+    def level0_const(cls, iou):
+        cls[0][...] = 1.0
+        iou[0][...] = 1.0
+    _run_case(cuda, batch=2, pad_hw=(256, 320), img_hw=(250, 317), nms_pre=300,
+              max_per_img=100, iou_thr=0.7, seed=23, mutate=level0_const)
 
 
 def test_rpn_single_anchor_voc_like(cuda):
