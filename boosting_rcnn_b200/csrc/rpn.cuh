@@ -83,11 +83,20 @@ rpn_score_kernel(const __grid_constant__ RpnArgs a, uint32_t* __restrict__ keys,
   const float* cls = lv.cls + (size_t)b * lv.n;
   const float* iou = lv.iou + (size_t)b * lv.n;
   uint32_t* kout = keys + (size_t)b * a.key_stride + lv.key_off;
-#pragma unroll 4
-  for (int j = 0; j < RPN_SCORE_CHUNK / RPN_SCORE_THREADS; ++j) {
+  // all 16 loads of the thread in flight before the (ALU-heavy) sigmoids
+  constexpr int NJ = RPN_SCORE_CHUNK / RPN_SCORE_THREADS;
+  float vc[NJ], vi[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int e = e0 + j * RPN_SCORE_THREADS + threadIdx.x;
+    vc[j] = 0.f; vi[j] = 0.f;
+    if (e < lv.n) { vc[j] = __ldcs(cls + e); vi[j] = __ldcs(iou + e); }
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
     const int e = e0 + j * RPN_SCORE_THREADS + threadIdx.x;
     if (e < lv.n) {
-      const float s = sqrtf(pinned_sigmoid(__ldg(cls + e)) * pinned_sigmoid(__ldg(iou + e)));
+      const float s = sqrtf(pinned_sigmoid(vc[j]) * pinned_sigmoid(vi[j]));
       const uint32_t key = __float_as_uint(s);
       kout[e] = key;
       atomicAdd(&sh[rpn_value_bin(s)], 1u);
@@ -188,6 +197,16 @@ rpn_collect_kernel(const __grid_constant__ RpnArgs a, const uint32_t* __restrict
   const int seg = b * a.L + l;
   const int n = lv.n, k = lv.k, P = lv.H * lv.W, A = a.A;
   const int tid = threadIdx.x, lane = tid & 31;
+  // this thread's keys: loads issued before the (latency-bound) threshold search
+  constexpr int NJ = RPN_SCORE_CHUNK / RPN_SCORE_THREADS;
+  const int e0 = ((int)blockIdx.x - lv.chunk_base) * RPN_SCORE_CHUNK;
+  const uint32_t* kseg = keys + (size_t)b * a.key_stride + lv.key_off;
+  uint32_t kreg[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int e = e0 + j * RPN_SCORE_THREADS + tid;
+    kreg[j] = (e < n) ? __ldg(kseg + e) : 0u;
+  }
   uint32_t thr = 0u;
   if (k < n) {
     rpn_find_digit_256(ghist + (size_t)seg * RPN_BINS, RPN_BINS, (uint32_t)k, s_warp, s_out);
@@ -198,18 +217,12 @@ rpn_collect_kernel(const __grid_constant__ RpnArgs a, const uint32_t* __restrict
   }
   if (tid == 0) s_cnt = 0;
   __syncthreads();
-  const int e0 = ((int)blockIdx.x - lv.chunk_base) * RPN_SCORE_CHUNK;
-  const uint32_t* kseg = keys + (size_t)b * a.key_stride + lv.key_off;
   const float inv_P = 1.0f / (float)P;
-#pragma unroll 4
-  for (int j = 0; j < RPN_SCORE_CHUNK / RPN_SCORE_THREADS; ++j) {
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
     const int e = e0 + j * RPN_SCORE_THREADS + tid;
-    uint32_t key = 0u;
-    bool take = false;
-    if (e < n) {
-      key = __ldg(kseg + e);
-      take = key >= thr;
-    }
+    const uint32_t key = kreg[j];
+    const bool take = (e < n) && (key >= thr);
     const unsigned m = __ballot_sync(0xffffffffu, take);
     if (m) {
       const int leader = __ffs(m) - 1;
