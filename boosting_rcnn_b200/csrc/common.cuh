@@ -175,25 +175,102 @@ __device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
 
 // In-place bitonic sort (descending) of n_pow2 u64 keys in shared memory by
 // the whole CTA.  n_pow2 must be a power of two; pad with 0.
+//
+// Hybrid network: every warp owns 64-key blocks (lane holds keys lane and
+// lane+32 of the block); all compare-exchange stages with partner distance
+// j <= 32 run in registers (j == 32 inside the lane, j < 32 through warp
+// shuffles) without any block barrier, only the stages with j >= 64 go through
+// shared memory.  For 2048 keys that is 21 block barriers instead of 66.
+__device__ __forceinline__ void bitonic_cmpx_lane(unsigned long long& x, int gi, int k, int j) {
+  const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, j);
+  const bool desc = ((gi & k) == 0);
+  const bool lower = ((gi & j) == 0);
+  const bool take_max = (desc == lower);
+  const unsigned long long mx = x > y ? x : y, mn = x > y ? y : x;
+  x = take_max ? mx : mn;
+}
+
+__device__ __forceinline__ void bitonic_block_tail(unsigned long long& x0, unsigned long long& x1,
+                                                   int gi0, int k) {
+  // j = 32: the pair lives in one lane
+  {
+    const bool desc = ((gi0 & k) == 0);
+    const unsigned long long mx = x0 > x1 ? x0 : x1, mn = x0 > x1 ? x1 : x0;
+    x0 = desc ? mx : mn;
+    x1 = desc ? mn : mx;
+  }
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    bitonic_cmpx_lane(x0, gi0, k, j);
+    bitonic_cmpx_lane(x1, gi0 + 32, k, j);
+  }
+}
+
 __device__ __forceinline__ void bitonic_sort_desc_u64(unsigned long long* keys,
                                                       int n_pow2) {
-  for (int k = 2; k <= n_pow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (n_pow2 < 64) {   // tiny: plain shared-memory network
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
+          int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          int ixj = i + j;
+          unsigned long long a = keys[i];
+          unsigned long long b = keys[ixj];
+          bool desc = ((i & k) == 0);
+          bool swap = desc ? (a < b) : (a > b);
+          if (swap) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    return;
+  }
+  const int nblk = n_pow2 >> 6;
+  __syncthreads();
+  // merge sizes 2..64: entirely inside the 64-key blocks
+  for (int blk = warp; blk < nblk; blk += nwarps) {
+    const int gi0 = blk * 64 + lane;
+    unsigned long long x0 = keys[gi0], x1 = keys[gi0 + 32];
+    for (int k = 2; k <= 32; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        bitonic_cmpx_lane(x0, gi0, k, j);
+        bitonic_cmpx_lane(x1, gi0 + 32, k, j);
+      }
+    }
+    bitonic_block_tail(x0, x1, gi0, 64);
+    keys[gi0] = x0;
+    keys[gi0 + 32] = x1;
+  }
+  for (int k = 128; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j >= 64; j >>= 1) {
       __syncthreads();
       for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
         // index of the lower element of the t-th compare-exchange pair
         // (j is a power of two: t/j*2j + t%j without integer division)
-        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        int ixj = i + j;
-        unsigned long long a = keys[i];
-        unsigned long long b = keys[ixj];
-        bool desc = ((i & k) == 0);
-        bool swap = desc ? (a < b) : (a > b);
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int ixj = i + j;
+        const unsigned long long a = keys[i];
+        const unsigned long long b = keys[ixj];
+        const bool desc = ((i & k) == 0);
+        const bool swap = desc ? (a < b) : (a > b);
         if (swap) {
           keys[i] = b;
           keys[ixj] = a;
         }
       }
+    }
+    __syncthreads();
+    for (int blk = warp; blk < nblk; blk += nwarps) {
+      const int gi0 = blk * 64 + lane;
+      unsigned long long x0 = keys[gi0], x1 = keys[gi0 + 32];
+      bitonic_block_tail(x0, x1, gi0, k);
+      keys[gi0] = x0;
+      keys[gi0 + 32] = x1;
     }
   }
   __syncthreads();
