@@ -59,6 +59,22 @@ class LossParams(Structure):
     ]
 
 
+class AssignParams(Structure):
+    _fields_ = [
+        ('batch', c_int32), ('max_props', c_int32), ('max_gts', c_int32),
+        ('pos_iou_thr', c_float), ('neg_iou_thr', c_float), ('min_pos_iou', c_float),
+        ('match_low_quality', c_int32),
+    ]
+
+
+class SampleParams(Structure):
+    _fields_ = [
+        ('batch', c_int32), ('max_props', c_int32), ('max_gts', c_int32),
+        ('num_classes', c_int32), ('perm_cap', c_int32), ('max_sel', c_int32),
+        ('means', c_float * 4), ('stds', c_float * 4), ('pos_weight', c_float),
+    ]
+
+
 class RcnnParams(Structure):
     _fields_ = [
         ('batch', c_int32), ('rois_per_img', c_int32), ('num_classes', c_int32),
@@ -112,6 +128,9 @@ SIGNATURES = {
     'brcnn_boost_loss': (c_int32, [
         POINTER(LossParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'brcnn_rcnn_assign': (c_int32, [POINTER(AssignParams), c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
+    'brcnn_rcnn_sample_targets': (c_int32, [POINTER(SampleParams)] + [c_void_p] * 16),
     'brcnn_rcnn_workspace_layout': (c_int32, [POINTER(RcnnParams), POINTER(RcnnWsLayout)]),
     'brcnn_rcnn_workspace_bytes': (c_size_t, [POINTER(RcnnParams)]),
     'brcnn_rcnn_get_bboxes': (c_int32, [

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "nms_kernels.cuh"
 #include "rcnn_post.cuh"
+#include "rcnn_train_prep.cuh"
 #include "roi_align.cuh"
 #include "roi_align_bwd.cuh"
 #include "roi_align_bwd2.cuh"
@@ -788,6 +789,68 @@ int brcnn_boost_loss(const brcnn_loss_params* p, const float* cls_score,
   boost_loss_part2_kernel<<<G, BL_THREADS, 0, stream>>>(
       a, rpc, G, partials, labels, label_weights, prior, bbox_pred, bbox_targets, bbox_weights,
       out_scalars, grad_cls_score, grad_bbox_pred);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+// --------------------------- RCNN train front-end -------------------------
+int brcnn_rcnn_assign(const brcnn_assign_params* p, const float* proposals,
+                      const int32_t* num_props, const float* gt_boxes, const int32_t* num_gt,
+                      int32_t* gt_inds, int32_t* counts, brcnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!p || p->batch <= 0 || p->max_props <= 0 || p->max_gts < 0) return BRCNN_ERR_ARG;
+  if (p->match_low_quality) return BRCNN_ERR_UNSUPPORTED;
+  if (!proposals || !num_props || !num_gt || !gt_inds || !counts) return BRCNN_ERR_ARG;
+  if (p->max_gts > 0 && (!gt_boxes || misaligned16(gt_boxes))) return BRCNN_ERR_ARG;
+  if (p->batch > 65535 || p->max_gts > 2048) return BRCNN_ERR_UNSUPPORTED;
+  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)p->batch * 2 * 4, stream);
+  if (e != cudaSuccess) return (int)e;
+  AssignArgs a;
+  a.B = p->batch; a.M = p->max_props; a.Gmax = p->max_gts;
+  a.pos_iou_thr = p->pos_iou_thr; a.neg_iou_thr = p->neg_iou_thr;
+  const int slots = a.Gmax + a.M;
+  dim3 grid((slots + 255) / 256, p->batch);
+  const size_t smem = (size_t)(a.Gmax > 0 ? a.Gmax : 1) * 16;
+  rcnn_assign_kernel<<<grid, 256, smem, stream>>>(a, proposals, num_props, gt_boxes, num_gt,
+                                                  gt_inds, counts);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+int brcnn_rcnn_sample_targets(const brcnn_sample_params* p, const float* proposals,
+                              const int32_t* num_props, const float* gt_boxes,
+                              const int64_t* gt_labels, const int32_t* num_gt,
+                              const int32_t* gt_inds, const int32_t* plan,
+                              const int32_t* perm_pos, const int32_t* perm_neg,
+                              float* rois, int64_t* labels, float* label_weights,
+                              float* bbox_targets, float* bbox_weights, float* prior,
+                              brcnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!p || p->batch <= 0 || p->max_props <= 0 || p->max_gts < 0 || p->max_sel <= 0 ||
+      p->perm_cap <= 0)
+    return BRCNN_ERR_ARG;
+  if (!proposals || !num_props || !num_gt || !gt_inds || !plan || !perm_pos || !perm_neg ||
+      !rois || !labels || !label_weights || !bbox_targets || !bbox_weights || !prior)
+    return BRCNN_ERR_ARG;
+  if (p->max_gts > 0 && (!gt_boxes || !gt_labels || misaligned16(gt_boxes))) return BRCNN_ERR_ARG;
+  if (misaligned16(bbox_targets) || misaligned16(bbox_weights)) return BRCNN_ERR_ARG;
+  SampleArgs a;
+  a.B = p->batch; a.M = p->max_props; a.Gmax = p->max_gts; a.num_classes = p->num_classes;
+  a.perm_cap = p->perm_cap; a.pos_weight = p->pos_weight;
+  for (int i = 0; i < 4; ++i) { a.means[i] = p->means[i]; a.stds[i] = p->stds[i]; }
+  const int sel_cap = next_pow2(p->max_sel);
+  const size_t smem = (size_t)sel_cap * 8 + (size_t)(a.Gmax + a.M) * 4;
+  if (smem > 200 * 1024) return BRCNN_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(rcnn_sample_target_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  rcnn_sample_target_kernel<<<p->batch, ST_THREADS, smem, stream>>>(
+      a, proposals, num_props, gt_boxes, gt_labels, num_gt, gt_inds, plan, perm_pos, perm_neg,
+      sel_cap, rois, labels, label_weights, bbox_targets, bbox_weights, prior);
   g_launch_count_add(1);
   BRCNN_CUDA_CHECK_LAST();
   return BRCNN_OK;

@@ -19,8 +19,8 @@ from torch.autograd import Function
 from torch.nn.modules.utils import _pair
 
 from . import _lib
-from ._lib import (LossParams, RcnnParams, RcnnWsLayout, RoiParams, RpnParams,
-                   RpnWsLayout, check, ptr_array)
+from ._lib import (AssignParams, LossParams, RcnnParams, RcnnWsLayout, RoiParams, RpnParams,
+                   RpnWsLayout, SampleParams, check, ptr_array)
 
 
 def _stream():
@@ -422,6 +422,93 @@ class RoIAlign(nn.Module):
                 f'spatial_scale={self.spatial_scale}, '
                 f'sampling_ratio={self.sampling_ratio}, pool_mode={self.pool_mode}, '
                 f'aligned={self.aligned}, use_torchvision={self.use_torchvision})')
+
+
+# --------------------------------------------------------------------------
+# R-CNN training front-end: assign + sample + targets + prior (two launches)
+# --------------------------------------------------------------------------
+def rcnn_assign_sample(proposals, num_props, gt_bboxes, gt_labels, num_classes,
+                       pos_iou_thr, neg_iou_thr, min_pos_iou=0., num=512, pos_fraction=0.25,
+                       neg_pos_ub=-1, means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.),
+                       pos_weight=-1):
+    """MaxIoUAssigner(match_low_quality=False) + RandomSampler(add_gt_as_proposals=True) +
+    BBoxHead.get_targets + the ProbRoIHead prior vector for a whole batch.
+
+    proposals (B,M,5) padded + num_props (B,) int32 (the layout of rpn_get_bboxes);
+    gt_bboxes / gt_labels: per-image lists of (G_b,4) / (G_b,) device tensors.
+    The permutations are drawn with torch.randperm on the CPU generator in the
+    reference's order (random_sampler.py:58): per image positives, then negatives.
+    Returns rois (N,5), labels (N,), label_weights (N,), bbox_targets (N,4),
+    bbox_weights (N,4), prior (N,), rows_per_image (list)."""
+    lib = _lib.load()
+    proposals = _f32c(proposals, 'proposals')
+    assert proposals.dim() == 3 and proposals.size(2) == 5
+    dev = proposals.device
+    B, M = proposals.shape[:2]
+    num_props = num_props.to(torch.int32).contiguous()
+    Gs = [int(g.size(0)) for g in gt_bboxes]
+    Gmax = max(1, max(Gs))
+    gtb = torch.zeros((B, Gmax, 4), dtype=torch.float32, device=dev)
+    gtl = torch.zeros((B, Gmax), dtype=torch.int64, device=dev)
+    for b in range(B):
+        if Gs[b]:
+            gtb[b, :Gs[b]] = gt_bboxes[b].float()
+            gtl[b, :Gs[b]] = gt_labels[b].long()
+    num_gt = torch.tensor(Gs, dtype=torch.int32).to(dev)
+    gt_inds = torch.empty((B, Gmax + M), dtype=torch.int32, device=dev)
+    counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    ap = AssignParams(B, M, Gmax, float(pos_iou_thr), float(neg_iou_thr), float(min_pos_iou), 0)
+    check(lib.brcnn_rcnn_assign(ap, proposals.data_ptr(), num_props.data_ptr(), gtb.data_ptr(),
+                                num_gt.data_ptr(), gt_inds.data_ptr(), counts.data_ptr(),
+                                _stream()), 'brcnn_rcnn_assign')
+    cnt = counts.cpu().tolist()          # the one host sync of the training front-end
+    n_exp_pos = int(num * pos_fraction)
+    cap = max(1, num)
+    plan = torch.zeros((B, 5), dtype=torch.int32)
+    perm_pos = torch.zeros((B, cap), dtype=torch.int32)
+    perm_neg = torch.zeros((B, cap), dtype=torch.int32)
+    rows, base = [], 0
+    for b in range(B):
+        n_pos_c, n_neg_c = cnt[b]
+        if n_pos_c > n_exp_pos:
+            perm_pos[b, :n_exp_pos] = torch.randperm(n_pos_c)[:n_exp_pos].to(torch.int32)
+            n_pos, use_p = n_exp_pos, 1
+        else:
+            n_pos, use_p = n_pos_c, 0
+        n_exp_neg = num - n_pos
+        if neg_pos_ub >= 0:
+            n_exp_neg = min(n_exp_neg, int(neg_pos_ub * max(1, n_pos)))
+        if n_neg_c > n_exp_neg:
+            perm_neg[b, :n_exp_neg] = torch.randperm(n_neg_c)[:n_exp_neg].to(torch.int32)
+            n_neg, use_n = n_exp_neg, 1
+        else:
+            n_neg, use_n = n_neg_c, 0
+        plan[b] = torch.tensor([n_pos, n_neg, base, use_p, use_n], dtype=torch.int32)
+        rows.append(n_pos + n_neg)
+        base += n_pos + n_neg
+    N = base
+    to = lambda t: t.to(dev, non_blocking=True)
+    plan_d, pp_d, pn_d = to(plan), to(perm_pos), to(perm_neg)
+    rois = torch.empty((N, 5), dtype=torch.float32, device=dev)
+    labels = torch.empty((N,), dtype=torch.int64, device=dev)
+    label_weights = torch.empty((N,), dtype=torch.float32, device=dev)
+    bbox_targets = torch.empty((N, 4), dtype=torch.float32, device=dev)
+    bbox_weights = torch.empty((N, 4), dtype=torch.float32, device=dev)
+    prior = torch.empty((N,), dtype=torch.float32, device=dev)
+    if N > 0:
+        sp = SampleParams()
+        sp.batch, sp.max_props, sp.max_gts, sp.num_classes = B, M, Gmax, int(num_classes)
+        sp.perm_cap, sp.max_sel = cap, cap
+        for i in range(4):
+            sp.means[i], sp.stds[i] = float(means[i]), float(stds[i])
+        sp.pos_weight = 1.0 if pos_weight <= 0 else float(pos_weight)
+        check(lib.brcnn_rcnn_sample_targets(
+            sp, proposals.data_ptr(), num_props.data_ptr(), gtb.data_ptr(), gtl.data_ptr(),
+            num_gt.data_ptr(), gt_inds.data_ptr(), plan_d.data_ptr(), pp_d.data_ptr(),
+            pn_d.data_ptr(), rois.data_ptr(), labels.data_ptr(), label_weights.data_ptr(),
+            bbox_targets.data_ptr(), bbox_weights.data_ptr(), prior.data_ptr(), _stream()),
+            'brcnn_rcnn_sample_targets')
+    return rois, labels, label_weights, bbox_targets, bbox_weights, prior, rows
 
 
 # --------------------------------------------------------------------------

@@ -107,6 +107,11 @@ class ProbRoIHead(nn.Module):
         num_imgs = len(img_metas)
         if gt_bboxes_ignore is None:
             gt_bboxes_ignore = [None for _ in range(num_imgs)]
+        if self._fused_train_prep_ok(gt_bboxes_ignore):
+            return self._forward_train_fused(x, proposal_list, gt_bboxes, gt_labels)
+        if isinstance(proposal_list, PaddedProposals):
+            n = proposal_list.num.tolist()
+            proposal_list = [proposal_list.boxes[b, :k] for b, k in enumerate(n)]
         sampling_results, priors = [], []
         for i in range(num_imgs):
             assign_result = self.bbox_assigner.assign(proposal_list[i], gt_bboxes[i],
@@ -127,6 +132,31 @@ class ProbRoIHead(nn.Module):
         bbox_results = self._bbox_forward_train_boost(x, sampling_results, gt_bboxes, gt_labels,
                                                       img_metas, priors)
         return dict(bbox_results['loss_bbox'])
+
+    def _fused_train_prep_ok(self, gt_bboxes_ignore):
+        """The two-launch assign+sample+targets path (ops.rcnn_assign_sample) covers the
+        train_cfg of every boosting_rcnn config: MaxIoUAssigner(match_low_quality=False,
+        scalar neg_iou_thr) + RandomSampler(add_gt_as_proposals=True), no ignore regions."""
+        from .sampling import MaxIoUAssigner, RandomSampler
+        a, s = self.bbox_assigner, self.bbox_sampler
+        return (self.boost and type(a) is MaxIoUAssigner and type(s) is RandomSampler
+                and not a.match_low_quality and isinstance(a.neg_iou_thr, float)
+                and s.add_gt_as_proposals and all(g is None for g in gt_bboxes_ignore)
+                and not getattr(self, 'force_python_train_prep', False))
+
+    def _forward_train_fused(self, x, proposal_list, gt_bboxes, gt_labels):
+        props = proposal_list if isinstance(proposal_list, PaddedProposals) \
+            else pad_proposals(proposal_list)
+        a, s, h = self.bbox_assigner, self.bbox_sampler, self.bbox_head
+        rois, labels, label_weights, bbox_targets, bbox_weights, prior, _ = \
+            ops.rcnn_assign_sample(
+                props.boxes, props.num, gt_bboxes, gt_labels, h.num_classes, a.pos_iou_thr,
+                a.neg_iou_thr, a.min_pos_iou, s.num, s.pos_fraction, s.neg_pos_ub,
+                h.bbox_coder.means, h.bbox_coder.stds, self.train_cfg.pos_weight)
+        bbox_results = self._bbox_forward(x, rois)
+        return h.boost_loss(bbox_results['cls_score'], bbox_results['bbox_pred'], labels,
+                            label_weights, bbox_targets, bbox_weights, prior, self.gamma,
+                            self.alpha, self.reg_norm)
 
     def _bbox_forward_train_boost(self, x, sampling_results, gt_bboxes, gt_labels, img_metas,
                                   priors, ious=None):

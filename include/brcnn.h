@@ -228,6 +228,63 @@ int brcnn_boost_loss(const brcnn_loss_params* p, const float* cls_score,
                      brcnn_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * (4b) R-CNN training front-end: assign + sample + targets + prior
+ * (the caller side of the RoI kernels)
+ * replaces MaxIoUAssigner.assign (core/bbox/assigners/max_iou_assigner.py:61-212,
+ *   match_low_quality=False as in every boosting_rcnn R-CNN train_cfg),
+ *   AssignResult.add_gt_ (assign_result.py:191-205), the index bookkeeping of
+ *   RandomSampler.sample / SamplingResult (samplers/random_sampler.py:32-82,
+ *   base_sampler.py:35-102, sampling_result.py:26-55), BBoxHead.get_targets
+ *   (roi_heads/bbox_heads/bbox_head.py:122-253), bbox2delta
+ *   (coder/delta_xywh_bbox_coder.py:98-141) and the prior vector of
+ *   ProbRoIHead.forward_train (roi_heads/prob_roi_head.py:51-64).
+ * The random permutations stay on the host: the reference draws them with
+ * torch.randperm on the CPU generator (random_sampler.py:58).
+ * Proposals are in the padded layout of brcnn_rpn_get_bboxes.
+ * ---------------------------------------------------------------------- */
+typedef struct brcnn_assign_params {
+  int32_t batch;
+  int32_t max_props;           /* M: row capacity of proposals per image       */
+  int32_t max_gts;             /* Gmax: row capacity of gt_boxes per image     */
+  float pos_iou_thr, neg_iou_thr, min_pos_iou;
+  int32_t match_low_quality;   /* must be 0 (else BRCNN_ERR_UNSUPPORTED)       */
+} brcnn_assign_params;
+
+/* gt_inds: int32 (B, Gmax + M) in the sampler's index space after add_gt_
+ *   (slot g < num_gt[b]: GT g, value g+1; slot num_gt[b] + j: proposal j;
+ *   values: >0 assigned GT index + 1, 0 background, -1 ignore, -2 unused slot)
+ * counts:  int32 (B, 2) = number of positive / negative candidates (zeroed here) */
+int brcnn_rcnn_assign(const brcnn_assign_params* p, const float* proposals,
+                      const int32_t* num_props, const float* gt_boxes,
+                      const int32_t* num_gt, int32_t* gt_inds, int32_t* counts,
+                      brcnn_stream_t stream);
+
+typedef struct brcnn_sample_params {
+  int32_t batch, max_props, max_gts;
+  int32_t num_classes;         /* background label                             */
+  int32_t perm_cap;            /* columns of perm_pos / perm_neg               */
+  int32_t max_sel;             /* max rows selected per image per list         */
+  float means[4], stds[4];     /* bbox_coder target_means / target_stds        */
+  float pos_weight;            /* label weight of positives (1 if cfg <= 0)    */
+} brcnn_sample_params;
+
+/* plan: int32 (B,5) written by the host from `counts`:
+ *   [n_pos_selected, n_neg_selected, first output row, use perm_pos, use perm_neg]
+ * perm_pos / perm_neg: int32 (B, perm_cap), torch.randperm(n_candidates)[:n_selected]
+ *   when the candidate list is longer than the quota (use flag = 1).
+ * Output rows per image: positives then negatives, each index-ascending
+ * (SamplingResult.bboxes): rois (N,5), labels int64 (N), label_weights (N),
+ * bbox_targets (N,4), bbox_weights (N,4), prior (N).                          */
+int brcnn_rcnn_sample_targets(const brcnn_sample_params* p, const float* proposals,
+                              const int32_t* num_props, const float* gt_boxes,
+                              const int64_t* gt_labels, const int32_t* num_gt,
+                              const int32_t* gt_inds, const int32_t* plan,
+                              const int32_t* perm_pos, const int32_t* perm_neg,
+                              float* rois, int64_t* labels, float* label_weights,
+                              float* bbox_targets, float* bbox_weights, float* prior,
+                              brcnn_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * (5) Probabilistic score fusion + per-class decode + class-wise NMS
  * replaces ProbRoIHead.simple_test_bboxes fusion (prob_roi_head.py:232-240),
  *   ProbConvFCBBoxHead.get_bboxes (convfc_bbox_head.py:294-330) and

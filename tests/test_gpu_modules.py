@@ -262,3 +262,69 @@ def test_cuda_graph_replay_equals_eager_and_pipeline(cuda):
         assert torch.equal(a, b.cpu()) and torch.equal(c, b.cpu())
     for a, b in zip(r1, second):
         assert torch.equal(a, b.cpu())
+
+
+@pytest.mark.parametrize('case', ['plenty', 'few_negatives', 'no_gt_image', 'many_positives'])
+def test_fused_assign_sample_targets_equals_python_path(cuda, case):
+    """ops.rcnn_assign_sample (2 launches + host randperm) vs the reference-shaped
+    Python path (MaxIoUAssigner / RandomSampler / get_targets / prior extraction of
+    sampling.py, bbox_head.py, roi_head.py) under the same CPU RNG seed: identical
+    rows, labels and priors; bbox targets within 1e-6 (logf)."""
+    torch.manual_seed(3)
+    _, roi, m = configs.build_hot_path('coco', train=True)
+    roi = roi.to(cuda).train()
+    rng = np.random.RandomState(11)
+    B = 3
+    gts, labels, plist = [], [], []
+    for b in range(B):
+        G = 6 if case != 'no_gt_image' or b != 1 else 0
+        g = synth.random_boxes(max(G, 1), 250, 317, seed=40 + b)[:G]
+        gts.append(torch.from_numpy(g.reshape(-1, 4)).to(cuda))
+        labels.append(torch.from_numpy(rng.randint(0, 80, G)).to(cuda))
+        n_jit = {'plenty': 10, 'few_negatives': 60, 'no_gt_image': 10, 'many_positives': 60}[case]
+        n_rnd = {'plenty': 900, 'few_negatives': 40, 'no_gt_image': 500, 'many_positives': 700}[case]
+        parts = [g + rng.normal(0, 1.5, g.shape) for _ in range(n_jit)] if G else []
+        parts.append(synth.random_boxes(n_rnd, 250, 317, seed=60 + b))
+        bx = np.concatenate(parts).astype(np.float32)
+        bx = bx[rng.permutation(len(bx))]
+        sc = np.sort(rng.rand(len(bx)).astype(np.float32))[::-1].copy()
+        plist.append(torch.from_numpy(np.concatenate([bx, sc[:, None]], 1)).to(cuda))
+    # ---- Python path, exactly the body of ProbRoIHead.forward_train ----
+    torch.manual_seed(123)
+    results, priors = [], []
+    for i in range(B):
+        ar = roi.bbox_assigner.assign(plist[i], gts[i], None, labels[i])
+        res = roi.bbox_sampler.sample(ar, plist[i], gts[i], labels[i])
+        results.append(res)
+        G = ar.num_gts
+        pos_prior = plist[i][res.pos_inds[G:] - G, -1]
+        neg_prior = 1 - plist[i][res.neg_inds - G, -1]
+        priors.append(torch.cat([pos_prior.new_zeros(G), pos_prior, neg_prior]))
+    ref_rois = bbox2roi([r.bboxes for r in results])
+    ref_lab, ref_lw, ref_bt, ref_bw = roi.bbox_head.get_targets(results, gts, labels, roi.train_cfg)
+    ref_prior = torch.cat(priors)
+    # ---- fused path, same CPU RNG state ----
+    torch.manual_seed(123)
+    a, s, h = roi.bbox_assigner, roi.bbox_sampler, roi.bbox_head
+    pp = pad_proposals(plist)
+    rois, lab, lw, bt, bw, prior, rows = ops.rcnn_assign_sample(
+        pp.boxes, pp.num, gts, labels, h.num_classes, a.pos_iou_thr, a.neg_iou_thr, a.min_pos_iou,
+        s.num, s.pos_fraction, s.neg_pos_ub, h.bbox_coder.means, h.bbox_coder.stds,
+        roi.train_cfg.pos_weight)
+    assert rows == [r.bboxes.size(0) for r in results]
+    assert torch.equal(rois, ref_rois)
+    assert torch.equal(lab, ref_lab) and torch.equal(lw, ref_lw) and torch.equal(bw, ref_bw)
+    assert torch.equal(prior, ref_prior)
+    assert torch.allclose(bt, ref_bt, rtol=1e-6, atol=1e-6)
+    if case == 'many_positives':
+        assert any(r.pos_inds.numel() == 128 for r in results)   # randperm on the positives too
+    # and through the module: same losses either way
+    sizes = synth.featmap_sizes(256, 320)
+    feats = [torch.from_numpy(f).to(cuda) for f in synth.fpn_feats(B, 256, sizes, seed=4)]
+    out = []
+    for force in (True, False):
+        roi.force_python_train_prep = force
+        torch.manual_seed(77)
+        out.append(roi.forward_train(feats, _metas(B), plist, gts, labels))
+    for k in ('loss_cls', 'loss_bbox', 'acc'):
+        assert torch.allclose(out[0][k], out[1][k], rtol=1e-6, atol=1e-7), k
