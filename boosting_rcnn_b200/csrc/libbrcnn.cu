@@ -88,6 +88,48 @@ nms_rank_scatter_kernel(const float* __restrict__ boxes,
   if (i == 0) count[0] = K;
 }
 
+// Sort by (id asc, score desc, index asc) by counting: position of box i =
+// #{j : id_j < id_i} + #{j : id_j == id_i, key_j > key_i}.  Writes the raw boxes
+// and keys in that order plus the start / size of every id's list (ids in
+// [0, num_ids); idxs == nullptr: one list).
+__global__ void __launch_bounds__(256)
+nms_id_rank_scatter_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                           const int64_t* __restrict__ idxs, int K, int num_ids,
+                           float4* __restrict__ sorted_boxes, u64* __restrict__ sorted_key,
+                           int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_count) {
+  __shared__ u64 t_key[256];
+  __shared__ int t_id[256];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  u64 mine = 0;
+  int my_id = 0;
+  if (i < K) {
+    mine = ((u64)ordered_bits(scores[i]) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)i);
+    if (idxs != nullptr) my_id = (int)idxs[i];
+  }
+  int lt = 0, rank = 0;
+  for (int j0 = 0; j0 < K; j0 += 256) {
+    const int j = j0 + threadIdx.x;
+    __syncthreads();
+    t_key[threadIdx.x] = (j < K)
+        ? (((u64)ordered_bits(scores[j]) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)j)) : 0ull;
+    t_id[threadIdx.x] = (j < K) ? (idxs != nullptr ? (int)idxs[j] : 0) : 0x7fffffff;
+    __syncthreads();
+    const int m = min(256, K - j0);
+    for (int t = 0; t < m; ++t) {
+      const int id = t_id[t];
+      lt += (id < my_id);
+      rank += (id == my_id) && (t_key[t] > mine);
+    }
+  }
+  if (i < K && my_id >= 0 && my_id < num_ids) {
+    const int pos = lt + rank;
+    sorted_boxes[pos] = reinterpret_cast<const float4*>(boxes)[i];
+    sorted_key[pos] = mine;
+    if (rank == 0) seg_start[my_id] = lt;     // the best box of the id
+    atomicAdd(seg_count + my_id, 1);
+  }
+}
+
 __global__ void nms_finalize_kernel(const float* __restrict__ boxes,
                                     const float* __restrict__ scores,
                                     const int32_t* __restrict__ order,
@@ -126,7 +168,7 @@ __global__ void delta2bbox_kernel(const __grid_constant__ DecodeArgs a,
 }
 
 struct NmsWs {
-  size_t sorted_boxes, sorted_key, order, count, maxc, mask, kept_pos, kept_count, total;
+  size_t sorted_boxes, sorted_key, order, count, maxc, mask, kept_pos, kept_count, seg, total;
 };
 static NmsWs nms_ws(int K) {
   NmsWs w; size_t o = 0;
@@ -139,6 +181,7 @@ static NmsWs nms_ws(int K) {
   w.mask = o;         o = align256(o + (nms_use_fused(K) ? 0 : (size_t)K * W * 8));
   w.kept_pos = o;     o = align256(o + (size_t)K * 4);
   w.kept_count = o;   o = align256(o + 4);
+  w.seg = o;          o = align256(o + 2 * BRCNN_MAX_LEVELS * 4);   // seg_start | seg_count
   w.total = o;
   return w;
 }
@@ -394,7 +437,8 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
                                (const float4*)cand_boxes, (const u64*)cand_key,
                                (const uint8_t*)cand_valid, (const int32_t*)cand_count,
                                (int)p->num_levels, (int)d.Kc, p->iou_threshold, maxc_f,
-                               (int)p->max_per_img, proposals, num_proposals, lay, dbg);
+                               (int)p->max_per_img, proposals, num_proposals, lay, dbg,
+                               (const int32_t*)nullptr, 0.0f, (int64_t*)nullptr);
       } else {
         if (lay.total > 32 * 1024) {
           e = cudaFuncSetAttribute(rpn_nms_image_kernel<1>,
@@ -405,7 +449,8 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
                                (const float4*)cand_boxes, (const u64*)cand_key,
                                (const uint8_t*)cand_valid, (const int32_t*)cand_count,
                                (int)p->num_levels, (int)d.Kc, p->iou_threshold, maxc_f,
-                               (int)p->max_per_img, proposals, num_proposals, lay, dbg);
+                               (int)p->max_per_img, proposals, num_proposals, lay, dbg,
+                               (const int32_t*)nullptr, 0.0f, (int64_t*)nullptr);
       }
       if (e != cudaSuccess) return (int)e;
       if (dbg != nullptr) {
@@ -456,8 +501,22 @@ size_t brcnn_nms_workspace_bytes(int32_t num_boxes) {
   return nms_ws(num_boxes).total;
 }
 
+// device-side tail of the clustered path: dets rows from the keep list
+__global__ void nms_gather_dets_kernel(const float* __restrict__ boxes,
+                                       const float* __restrict__ scores,
+                                       const int64_t* __restrict__ keep,
+                                       const int32_t* __restrict__ num_keep,
+                                       float* __restrict__ dets) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= num_keep[0]) return;
+  const int64_t src = keep[j];
+  const float4 b = reinterpret_cast<const float4*>(boxes)[src];
+  float* o = dets + (size_t)j * 5;
+  o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w; o[4] = scores[src];
+}
+
 int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* idxs,
-                      int32_t K, float iou_threshold, int32_t offset,
+                      int32_t K, int32_t num_ids, float iou_threshold, int32_t offset,
                       int64_t* keep, float* dets, int32_t* num_keep,
                       void* workspace, size_t workspace_bytes,
                       brcnn_stream_t stream_) {
@@ -485,6 +544,62 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
     nms_maxcoord_kernel<<<1, 1024, 0, stream>>>(boxes, K, maxc);
     g_launch_count_add(1);
     BRCNN_CUDA_CHECK_LAST();
+  }
+  // ---- clustered path: the ids are <= BRCNN_MAX_LEVELS sorted lists walked in global
+  // score order by a cluster of 8 CTAs (rpn_nms.cuh); needs the caller's bound on the
+  // id range (num_ids; 1 when idxs == NULL) and a kept list that fits shared memory
+  {
+    static const bool force_old = [] {
+      const char* e = getenv("BRCNN_NMS_OP");
+      return e && e[0] == 'o';
+    }();
+    const int L = (idxs == nullptr) ? 1 : num_ids;
+    const RpnNmsImageSmem lay = rpn_nms_image_smem(L > 0 ? L : 1, K, RNI_CLUSTER);
+    if (!force_old && L >= 1 && L <= BRCNN_MAX_LEVELS && lay.total <= 160 * 1024 &&
+        lay.kp <= 65535) {
+      int32_t* seg_start = (int32_t*)(ws + w.seg);
+      int32_t* seg_count = seg_start + BRCNN_MAX_LEVELS;
+      cudaError_t e = cudaMemsetAsync(seg_start, 0, 2 * BRCNN_MAX_LEVELS * 4, stream);
+      if (e != cudaSuccess) return (int)e;
+      nms_id_rank_scatter_kernel<<<(K + 255) / 256, 256, 0, stream>>>(
+          boxes, scores, idxs, K, L, sboxes, skey, seg_start, seg_count);
+      g_launch_count_add(1);
+      BRCNN_CUDA_CHECK_LAST();
+      if (lay.total > 32 * 1024) {
+        e = cudaFuncSetAttribute(rpn_nms_image_kernel<RNI_CLUSTER>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+        if (e != cudaSuccess) return (int)e;
+      }
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)RNI_CLUSTER);
+      cfg.blockDim = dim3(RNI_THREADS);
+      cfg.dynamicSmemBytes = (size_t)lay.total;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)RNI_CLUSTER;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, rpn_nms_image_kernel<RNI_CLUSTER>, (const float4*)sboxes,
+                             (const u64*)skey, (const uint8_t*)nullptr,
+                             (const int32_t*)seg_count, L, (int)K, iou_threshold,
+                             idxs != nullptr ? (const float*)maxc : (const float*)nullptr,
+                             (int)K, (float*)nullptr, num_keep, lay, (long long*)nullptr,
+                             (const int32_t*)seg_start, (float)offset, keep);
+      if (e != cudaSuccess) return (int)e;
+      g_launch_count_add(1);
+      BRCNN_CUDA_CHECK_LAST();
+      if (dets != nullptr) {
+        nms_gather_dets_kernel<<<(K + 255) / 256, 256, 0, stream>>>(boxes, scores, keep,
+                                                                    num_keep, dets);
+        g_launch_count_add(1);
+        BRCNN_CUDA_CHECK_LAST();
+      }
+      return BRCNN_OK;
+    }
   }
   nms_rank_scatter_kernel<<<(K + 255) / 256, 256, 0, stream>>>(
       boxes, scores, idxs, K, maxc, sboxes, skey, order, count);

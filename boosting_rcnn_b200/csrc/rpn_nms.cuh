@@ -64,7 +64,9 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
                      const int32_t* __restrict__ cand_count, int L, int Kc, float thr,
                      const float* __restrict__ img_maxc, int max_out,
                      float* __restrict__ proposals, int32_t* __restrict__ num_proposals,
-                     RpnNmsImageSmem lay, long long* __restrict__ dbg) {
+                     RpnNmsImageSmem lay, long long* __restrict__ dbg,
+                     const int32_t* __restrict__ seg_start, float off,
+                     int64_t* __restrict__ keep_idx) {
   extern __shared__ __align__(16) unsigned char rni_smem[];
   float4* kbox = reinterpret_cast<float4*>(rni_smem + lay.kbox);            // local share
   unsigned short* lidx = reinterpret_cast<unsigned short*>(rni_smem + lay.lidx);
@@ -93,7 +95,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
   const int crank = (CS > 1) ? (int)cg::this_cluster().block_rank() : 0;
   const int b = blockIdx.x / CS;
   const int tid = threadIdx.x, lane = tid & 31;
-  const float maxc1 = img_maxc[b] + 1.0f;
+  const float maxc1 = img_maxc != nullptr ? img_maxc[b] + 1.0f : 0.0f;   // no ids: no offset
   if (tid < BRCNN_MAX_LEVELS) {
     s_cursor[tid] = 0;
     s_count[tid] = (tid < L) ? min(cand_count[b * L + tid], Kc) : 0;
@@ -110,7 +112,8 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
   auto prefetch = [&](int cursor) {
     const int pos = cursor + wi;
     if (wl < L && pos < s_count[wl]) {
-      const size_t g = ((size_t)b * L + wl) * Kc + pos;
+      const size_t g = (seg_start != nullptr ? (size_t)seg_start[b * L + wl]
+                                             : ((size_t)b * L + wl) * Kc) + pos;
       pk = cand_key[g];
       pb = cand_boxes[g];
       pv = cand_valid != nullptr ? cand_valid[g] : 1;
@@ -173,7 +176,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
         const float4 ob = add_seg_offset(raw, (float)wl * maxc1);
         traw[rank] = raw;
         tb[rank] = ob;
-        ta[rank] = (ob.z - ob.x) * (ob.w - ob.y);
+        ta[rank] = (ob.z - ob.x + off) * (ob.w - ob.y + off);
         tkey[rank] = key;
         tlvl[rank] = wl;
         atomicAdd(&s_taken[wl], 1);
@@ -200,15 +203,15 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
         for (; q + 24 < n && !hit; q += 32) {
           const float4 k0 = kbox[li[q]], k1 = kbox[li[q + 8]], k2 = kbox[li[q + 16]],
                        k3 = kbox[li[q + 24]];
-          const bool h0 = nms_suppresses(k0, (k0.z - k0.x) * (k0.w - k0.y), bx, ba, thr, 0.f);
-          const bool h1 = nms_suppresses(k1, (k1.z - k1.x) * (k1.w - k1.y), bx, ba, thr, 0.f);
-          const bool h2 = nms_suppresses(k2, (k2.z - k2.x) * (k2.w - k2.y), bx, ba, thr, 0.f);
-          const bool h3 = nms_suppresses(k3, (k3.z - k3.x) * (k3.w - k3.y), bx, ba, thr, 0.f);
+          const bool h0 = nms_suppresses(k0, (k0.z - k0.x + off) * (k0.w - k0.y + off), bx, ba, thr, off);
+          const bool h1 = nms_suppresses(k1, (k1.z - k1.x + off) * (k1.w - k1.y + off), bx, ba, thr, off);
+          const bool h2 = nms_suppresses(k2, (k2.z - k2.x + off) * (k2.w - k2.y + off), bx, ba, thr, off);
+          const bool h3 = nms_suppresses(k3, (k3.z - k3.x + off) * (k3.w - k3.y + off), bx, ba, thr, off);
           hit = h0 | h1 | h2 | h3;
         }
         for (; q < n && !hit; q += 8) {
           const float4 k0 = kbox[li[q]];
-          hit = nms_suppresses(k0, (k0.z - k0.x) * (k0.w - k0.y), bx, ba, thr, 0.f);
+          hit = nms_suppresses(k0, (k0.z - k0.x + off) * (k0.w - k0.y + off), bx, ba, thr, off);
         }
       }
       const unsigned bal = __ballot_sync(0xffffffffu, hit);
@@ -228,7 +231,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
         bool sup = false;
         if (rl < RPC && r < ntile && cc < r && tlvl[cc] == tlvl[r] &&
             !((s_dead[cc >> 5] >> (cc & 31)) & 1u) && !((s_dead[r >> 5] >> (r & 31)) & 1u))
-          sup = nms_suppresses(tb[cc], ta[cc], tb[r], ta[r], thr, 0.f);
+          sup = nms_suppresses(tb[cc], ta[cc], tb[r], ta[r], thr, off);
         const unsigned bal = __ballot_sync(0xffffffffu, sup);
         if (lane == 0 && rl < RPC) s_dslice[round & 1][rl][(tid >> 5) & 1] = bal;
       }
@@ -312,10 +315,15 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
           if (crank == 0 && ((keep >> r) & 1ull)) {
             const int q = nkept + __popcll(keep & ((1ull << r) - 1ull));
             if (q < max_out) {
-              const float4 raw = traw[r];
-              float* o = proposals + ((size_t)b * max_out + q) * 5;
-              o[0] = raw.x; o[1] = raw.y; o[2] = raw.z; o[3] = raw.w;
-              o[4] = __uint_as_float((uint32_t)(tkey[r] >> 32));
+              if (proposals != nullptr) {
+                const float4 raw = traw[r];
+                float* o = proposals + ((size_t)b * max_out + q) * 5;
+                o[0] = raw.x; o[1] = raw.y; o[2] = raw.z; o[3] = raw.w;
+                o[4] = __uint_as_float((uint32_t)(tkey[r] >> 32));
+              }
+              if (keep_idx != nullptr)   // low key half = ~original index
+                keep_idx[(size_t)b * max_out + q] =
+                    (int64_t)(0xFFFFFFFFu - (uint32_t)(tkey[r] & 0xFFFFFFFFull));
             }
           }
         }
@@ -333,8 +341,9 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
   if (crank == 0) {
     const int nk = min(s_nkept, max_out);
     if (tid == 0) num_proposals[b] = nk;
-    for (int i = nk * 5 + tid; i < max_out * 5; i += RNI_THREADS)
-      proposals[(size_t)b * max_out * 5 + i] = 0.f;
+    if (proposals != nullptr)
+      for (int i = nk * 5 + tid; i < max_out * 5; i += RNI_THREADS)
+        proposals[(size_t)b * max_out * 5 + i] = 0.f;
   }
   if (dbg != nullptr && tid == 0 && blockIdx.x == 0) {
     for (int i = 0; i < 5; ++i) dbg[i] = t_acc[i];

@@ -151,12 +151,17 @@ def _nms_raw(boxes, scores, idxs, iou_threshold, offset):
     num = torch.zeros((1,), dtype=torch.int32, device=dev)
     if K == 0:
         return dets, keep
+    num_ids = 1
     if idxs is not None:
         idxs = idxs.to(torch.int64).contiguous()
+        # bound on the id range: lets the library walk <= 8 ids (pyramid levels) as sorted
+        # lists on a CTA cluster; costs one host read, like the data-dependent output size
+        lo, hi = int(idxs.min().item()), int(idxs.max().item())
+        num_ids = hi + 1 if lo >= 0 else 0
     ws = _ws(lib.brcnn_nms_workspace_bytes(K), dev)
     rc = lib.brcnn_batched_nms(
         boxes.data_ptr(), scores.data_ptr(),
-        idxs.data_ptr() if idxs is not None else None, K, float(iou_threshold),
+        idxs.data_ptr() if idxs is not None else None, K, num_ids, float(iou_threshold),
         int(offset), keep.data_ptr(), dets.data_ptr(), num.data_ptr(),
         ws.data_ptr(), ws.numel(), _stream())
     check(rc, 'brcnn_batched_nms')

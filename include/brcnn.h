@@ -115,11 +115,14 @@ int brcnn_delta2bbox(const float* rois, const float* deltas, int32_t n,
  * ---------------------------------------------------------------------- */
 size_t brcnn_nms_workspace_bytes(int32_t num_boxes);
 
-/* idxs may be NULL (plain / class-agnostic nms).  keep: int64[num_boxes]
- * (first *num_keep entries valid, score-descending), dets: optional
- * float[num_boxes][5] rows cat(boxes[keep], scores[keep]).                 */
+/* idxs may be NULL (plain / class-agnostic nms).  num_ids: caller's bound on the
+ * id range (idxs in [0, num_ids)); <= 0 = unknown.  With num_ids <= 8 (pyramid
+ * levels; or idxs == NULL) the ids are walked as sorted lists in global score
+ * order by a cluster of 8 CTAs, otherwise as one offset-box segment.
+ * keep: int64[num_boxes] (first *num_keep entries valid, score-descending),
+ * dets: optional float[num_boxes][5] rows cat(boxes[keep], scores[keep]).     */
 int brcnn_batched_nms(const float* boxes, const float* scores,
-                      const int64_t* idxs, int32_t num_boxes,
+                      const int64_t* idxs, int32_t num_boxes, int32_t num_ids,
                       float iou_threshold, int32_t offset, int64_t* keep,
                       float* dets, int32_t* num_keep, void* workspace,
                       size_t workspace_bytes, brcnn_stream_t stream);

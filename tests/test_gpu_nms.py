@@ -82,3 +82,38 @@ def test_batched_nms_class_agnostic_and_empty(cuda):
 def test_nms_rejects_cpu_tensors():
     with pytest.raises(RuntimeError):
         ops.nms(torch.zeros((4, 4)), torch.zeros((4,)), 0.5)
+
+
+def test_nms_operator_cluster_and_segment_paths_agree(cuda):
+    """BRCNN_NMS_OP=old (one offset-box segment) vs the default clustered list walk
+    of brcnn_batched_nms: identical keep lists for plain nms, offset=1, <= 8 ids."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = '''
+import sys, numpy as np, torch
+sys.path[:0] = [%r, %r]
+import synth
+from boosting_rcnn_b200 import ops
+res = []
+for K, nid, clustered in ((700, 1, True), (4693, 5, False), (9000, 8, True), (3000, 3, True)):
+    b = torch.from_numpy(synth.random_boxes(K, 800, 1333, seed=K, clustered=clustered)).cuda()
+    g = torch.Generator().manual_seed(K)
+    s = (torch.randint(0, 400, (K,), generator=g).float() / 400 - 0.2).cuda()   # ties, negatives
+    ids = torch.randint(0, nid, (K,), generator=g).cuda()
+    d, k = ops.batched_nms(b, s, ids, dict(type='nms', iou_threshold=0.6))
+    res += [k.cpu().numpy().astype(np.float64), d.cpu().numpy().reshape(-1).astype(np.float64)]
+    d, k = ops.nms(b, s, 0.5, offset=1)
+    res += [k.cpu().numpy().astype(np.float64)]
+np.save(sys.argv[1], np.concatenate(res))
+''' % (os.path.dirname(here), here)
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for mode in ('old', 'cluster'):
+            path = os.path.join(d, mode + '.npy')
+            subprocess.run([sys.executable, '-c', code, path], check=True,
+                           env=dict(os.environ, BRCNN_NMS_OP=mode))
+            outs.append(np.load(path))
+    np.testing.assert_array_equal(outs[0], outs[1])

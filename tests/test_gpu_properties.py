@@ -45,9 +45,11 @@ def test_rpn_full_size_properties_and_generic_nms_agreement(cuda, B, nms_pre, ma
         assert (bx[:, 1::2] >= 0).all() and (bx[:, 1::2] <= IMG_HW[0]).all()
         assert ((bx[:, 2] - bx[:, 0]) > 0).all() and ((bx[:, 3] - bx[:, 1]) > 0).all()
         assert not P[b, n[b]:].any()
-    # independent path: the generic mmcv-style batched_nms operator on the very same
-    # candidates (one offset-box segment, bitmask + sweep kernels) must give the same
-    # first max_per_img rows as the clustered per-image kernel
+    # second path: the generic mmcv-style batched_nms operator on the very same candidates
+    # (its own id-rank sort + list segmentation + keep-index output, all keeps instead of
+    # an early stop) must give the same first max_per_img rows as brcnn_rpn_get_bboxes;
+    # tests/test_gpu_nms.py and test_gpu_rpn.py pin the clustered walk against the
+    # single-segment and per-level kernels
     wsb = ws.cpu().numpy()
     cb = wsb[lay.cand_boxes:lay.cand_boxes + B * L * Kc * 16].view(np.float32).reshape(B, L, Kc, 4)
     ck = wsb[lay.cand_key:lay.cand_key + B * L * Kc * 8].view(np.uint64).reshape(B, L, Kc)
