@@ -121,12 +121,15 @@ class CpuReference:
                                         self.test_rcnn['max_per_img'], rescale=True)
 
     def run(self, feats, cls, box, iou, n_images):
+        """n_images may exceed the images held in the tensors (one image per host
+        thread on boxes with more threads than images per step): indices wrap."""
         from concurrent.futures import ThreadPoolExecutor
         self._head_cpu()
-        fn = [[f[b].numpy() for f in feats] for b in range(n_images)]
-        cn = [[c[b].numpy() for c in cls] for b in range(n_images)]
-        bn = [[c[b].numpy() for c in box] for b in range(n_images)]
-        un = [[c[b].numpy() for c in iou] for b in range(n_images)]
+        nb = feats[0].shape[0]
+        fn = [[f[b % nb].numpy() for f in feats] for b in range(n_images)]
+        cn = [[c[b % nb].numpy() for c in cls] for b in range(n_images)]
+        bn = [[c[b % nb].numpy() for c in box] for b in range(n_images)]
+        un = [[c[b % nb].numpy() for c in iou] for b in range(n_images)]
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=self.threads) as ex:
             res = list(ex.map(lambda i: self.one_image(fn[i], cn[i], bn[i], un[i]), range(n_images)))
@@ -478,8 +481,8 @@ def main():
 
     # ------------------------------------------------------------------ CPU arm
     if args.impl == 'reference':
-        n_img = args.cpu_images or min(threads, B)
-        sizes, feats, cls, box, iou = make_inputs(n_img, pad_hw, A, C, seed=1234, pin=False)
+        n_img = args.cpu_images or max(threads, B)     # every host thread gets an image
+        sizes, feats, cls, box, iou = make_inputs(min(n_img, B), pad_hw, A, C, seed=1234, pin=False)
         ref = CpuReference(rpn_head, roi_head, model, geom, threads)
         for _ in range(max(args.warmup, 0)):
             ref.run(feats, cls, box, iou, min(n_img, threads))
@@ -690,15 +693,12 @@ def main():
     # ------------------------------------------------------------ CPU baseline
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        n_img = args.cpu_images or min(threads, B)
+        n_img = args.cpu_images or max(threads, B)     # every host thread gets an image
         ref = CpuReference(rpn_head, roi_head, model, geom, threads)
-        hf = [f[:n_img] for f in h_feats]
-        ref.run(hf, [c[:n_img] for c in h_cls], [c[:n_img] for c in h_box],
-                [c[:n_img] for c in h_iou], min(2, n_img))  # warm-up
+        ref.run(h_feats, h_cls, h_box, h_iou, min(2, n_img))  # warm-up
         reps, t = 0, 0.0
         while t < 8.0 and reps < 20:
-            dt, _ = ref.run(hf, [c[:n_img] for c in h_cls], [c[:n_img] for c in h_box],
-                            [c[:n_img] for c in h_iou], n_img)
+            dt, _ = ref.run(h_feats, h_cls, h_box, h_iou, n_img)
             t += dt
             reps += 1
         cpu = {'value': n_img * reps / t, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
