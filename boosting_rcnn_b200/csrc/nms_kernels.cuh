@@ -404,12 +404,72 @@ nms_merge_kernel(const int32_t* __restrict__ kept_pos,
   for (int r = total + threadIdx.x; r < max_out; r += blockDim.x) ep.pad(b, r);
 }
 
+// Same contract, for epilogues that identify the element from its key alone
+// (Epilogue::kNeedsPos == false): the <= Sg * min(keep_cap, max_out) kept keys of
+// image b are gathered into shared memory and bitonic-sorted; the first max_out are
+// the result.  O(n log^2 n) on-chip instead of Sg binary searches per element in
+// global memory -- 80 class lists (COCO) merge in ~20 us instead of ~700 us.
+// Dynamic smem: np2 u64.  Sg <= 1024.
+template <class Epilogue>
+__global__ void __launch_bounds__(1024)
+nms_merge_sort_kernel(const u64* __restrict__ kept_key, const int32_t* __restrict__ kept_count,
+                      int Sg, int keep_cap, int max_out, int np2,
+                      int32_t* __restrict__ num_out, Epilogue ep) {
+  extern __shared__ __align__(16) u64 s_keys[];
+  __shared__ int s_off[1025];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) {
+    int tot = 0;
+    for (int g = 0; g < Sg; ++g) {
+      s_off[g] = tot;
+      tot += min(min(kept_count[b * Sg + g], max_out), keep_cap);
+    }
+    s_off[Sg] = tot;
+    num_out[b] = min(tot, max_out);
+  }
+  __syncthreads();
+  const int total = s_off[Sg];
+  // one warp per list: coalesced copy of its kept keys
+  for (int g = tid >> 5; g < Sg; g += blockDim.x >> 5) {
+    const int o = s_off[g], ng = s_off[g + 1] - o;
+    const u64* src = kept_key + (size_t)(b * Sg + g) * keep_cap;
+    for (int j = tid & 31; j < ng; j += 32) s_keys[o + j] = src[j];
+  }
+  int np = 1;
+  while (np < total) np <<= 1;          // <= np2
+  for (int i = total + tid; i < np; i += blockDim.x) s_keys[i] = 0ull;
+  if (total > 1) bitonic_sort_desc_u64(s_keys, np);
+  else __syncthreads();
+  const int nout = min(total, max_out);
+  for (int r = tid; r < nout; r += blockDim.x) ep(b, r, -1, -1, s_keys[r]);
+  for (int r = nout + tid; r < max_out; r += blockDim.x) ep.pad(b, r);
+  (void)np2;
+}
+
 template <class Epilogue>
 inline int launch_nms_merge(const int32_t* kept_pos, const u64* kept_key,
                             const int32_t* kept_count, int B, int Sg, int keep_cap,
                             int max_out, int32_t* num_out, Epilogue ep,
                             cudaStream_t stream) {
   const int lcap = keep_cap < max_out ? keep_cap : max_out;
+  if (!Epilogue::kNeedsPos && Sg <= 1024) {
+    int np2 = 1;
+    while (np2 < Sg * lcap) np2 <<= 1;
+    const size_t sm = (size_t)np2 * sizeof(u64);
+    if (sm <= 200 * 1024) {
+      if (sm > 32 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(nms_merge_sort_kernel<Epilogue>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sm);
+        if (e != cudaSuccess) return (int)e;
+      }
+      nms_merge_sort_kernel<Epilogue><<<B, 1024, sm, stream>>>(
+          kept_key, kept_count, Sg, keep_cap, max_out, np2, num_out, ep);
+      g_launch_count_add(1);
+      BRCNN_CUDA_CHECK_LAST();
+      return BRCNN_OK;
+    }
+  }
   size_t smem = (size_t)Sg * lcap * sizeof(u64);
   int use_smem = 1;
   if (smem > 200 * 1024) { use_smem = 0; smem = 0; }

@@ -154,6 +154,7 @@ rcnn_class_sort_kernel(const __grid_constant__ RcnnArgs a,
 }
 
 struct RcnnMergeEpilogue {
+  static constexpr bool kNeedsPos = false;   // operator() uses (seg, pos)
   const float4* bboxes;  // [B*Rc][nbox]
   float* det_bboxes;     // (B, max_out, 5)
   int64_t* det_labels;   // (B, max_out)

@@ -445,6 +445,7 @@ rpn_topk_decode_kernel(const __grid_constant__ RpnArgs a,
 
 // epilogue of the per-image merge: proposals[b][rank] = (box, score)
 struct RpnMergeEpilogue {
+  static constexpr bool kNeedsPos = true;   // operator() uses (seg, pos)
   const float4* cand_boxes;
   float* proposals;  // (B, max_out, 5)
   int Kc, max_out;
