@@ -48,6 +48,8 @@ def parse_args():
                     help='images in the CPU-baseline sample (0: one per host thread, <= 16)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch kernels one by one')
+    ap.add_argument('--rpn-max-per-img', type=int, default=0,
+                    help='override test_cfg.rpn.max_per_img (BASELINE configs[3]: VOC at 1000)')
     return ap.parse_args()
 
 
@@ -471,6 +473,9 @@ def main():
     B = args.batch
     torch.manual_seed(0)
     rpn_head, roi_head, model = configs.build_hot_path(args.cfg)
+    if args.rpn_max_per_img > 0:
+        model['test_cfg']['rpn']['max_per_img'] = args.rpn_max_per_img
+        rpn_head.test_cfg.max_per_img = args.rpn_max_per_img
     A, C = rpn_head.num_anchors, roi_head.bbox_roi_extractor.out_channels
     threads = os.cpu_count() or 1
     base_cfg = dict(workload=WORKLOAD if args.cfg == 'utdac' else f'{args.cfg} inference',
