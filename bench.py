@@ -517,6 +517,12 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
+        # NUMA-local pinned buffers for the end-to-end leg (one process per GPU)
+        from boosting_rcnn_b200.dist import bind_to_gpu_cpus
+        orig_affinity = os.sched_getaffinity(0)
+        cpus = bind_to_gpu_cpus(local_rank)
+        if cpus:
+            torch.set_num_threads(max(1, min(len(cpus), 8)))
     from boosting_rcnn_b200 import _lib, ops
     from boosting_rcnn_b200.registry import ConfigDict
     lib = _lib.load()
@@ -697,6 +703,9 @@ def main():
 
     # ------------------------------------------------------------ CPU baseline
     cpu = None
+    if world > 1:
+        os.sched_setaffinity(0, orig_affinity)   # the CPU baseline may use every host core
+        torch.set_num_threads(threads)
     if rank == 0 and not args.no_cpu_baseline:
         n_img = args.cpu_images or max(threads, B)     # every host thread gets an image
         ref = CpuReference(rpn_head, roi_head, model, geom, threads)

@@ -65,3 +65,25 @@ def max_over_ranks(value, device=None):
     t = torch.tensor([float(value)], device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def bind_to_gpu_cpus(gpu_index):
+    """Pin this process to the CPU cores NVML reports as local to ``gpu_index`` (same
+    NUMA node / PCIe root) BEFORE pinned host buffers are allocated, so that first-touch
+    places them next to the GPU and the H2D copies of 8 concurrent ranks do not cross
+    sockets.  Returns the CPU set, or None when NVML / affinity are unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:  # noqa: BLE001 - best effort, never fatal
+        return None
+    return None
