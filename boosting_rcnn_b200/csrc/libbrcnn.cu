@@ -167,9 +167,12 @@ __global__ void delta2bbox_kernel(const __grid_constant__ DecodeArgs a,
   reinterpret_cast<float4*>(out)[i] = make_float4(o.x1, o.y1, o.x2, o.y2);
 }
 
+constexpr int NMS_MAX_IDS = 4096;   // ids of the segmented operator path
 struct NmsWs {
   size_t sorted_boxes, sorted_key, order, count, maxc, mask, kept_pos, kept_count, seg, total;
 };
+static NmsWs nms_ws(int K);
+static inline int32_t* kept_count_ids(char* ws, const NmsWs& w);
 static NmsWs nms_ws(int K) {
   NmsWs w; size_t o = 0;
   const size_t W = (K + 63) / 64;
@@ -178,12 +181,16 @@ static NmsWs nms_ws(int K) {
   w.order = o;        o = align256(o + (size_t)K * 4);
   w.count = o;        o = align256(o + 4);
   w.maxc = o;         o = align256(o + 4);
-  w.mask = o;         o = align256(o + (nms_use_fused(K) ? 0 : (size_t)K * W * 8));
+  w.mask = o;         o = align256(o + (nms_use_fused(K) ? (size_t)K * 8 : (size_t)K * W * 8));
   w.kept_pos = o;     o = align256(o + (size_t)K * 4);
   w.kept_count = o;   o = align256(o + 4);
-  w.seg = o;          o = align256(o + 2 * BRCNN_MAX_LEVELS * 4);   // seg_start | seg_count
+  w.seg = o;          o = align256(o + 3 * NMS_MAX_IDS * 4);   // seg_start | seg_count | kept_count
   w.total = o;
   return w;
+}
+
+static inline int32_t* kept_count_ids(char* ws, const NmsWs& w) {
+  return (int32_t*)(ws + w.seg) + 2 * NMS_MAX_IDS;
 }
 
 // --------------------------------------------------------------------------
@@ -515,6 +522,16 @@ __global__ void nms_gather_dets_kernel(const float* __restrict__ boxes,
   o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w; o[4] = scores[src];
 }
 
+// epilogue of the many-ids operator path: the key's low half is ~original index
+struct OpMergeEpilogue {
+  static constexpr bool kNeedsPos = false;
+  int64_t* keep;
+  __device__ void operator()(int, int rank, int, int, u64 key) const {
+    keep[rank] = (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+  }
+  __device__ void pad(int, int) const {}
+};
+
 int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* idxs,
                       int32_t K, int32_t num_ids, float iou_threshold, int32_t offset,
                       int64_t* keep, float* dets, int32_t* num_keep,
@@ -590,6 +607,59 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
                              (int)K, (float*)nullptr, num_keep, lay, (long long*)nullptr,
                              (const int32_t*)seg_start, (float)offset, keep);
       if (e != cudaSuccess) return (int)e;
+      g_launch_count_add(1);
+      BRCNN_CUDA_CHECK_LAST();
+      if (dets != nullptr) {
+        nms_gather_dets_kernel<<<(K + 255) / 256, 256, 0, stream>>>(boxes, scores, keep,
+                                                                    num_keep, dets);
+        g_launch_count_add(1);
+        BRCNN_CUDA_CHECK_LAST();
+      }
+      return BRCNN_OK;
+    }
+  }
+  // ---- many ids (class-wise NMS at operator level): one fused-NMS CTA per id on the
+  // id-sorted boxes, kept lists merged by an in-smem sort.  The kept list of a segment
+  // lives in shared memory, so every segment must fit it: K <= 8192.
+  {
+    static const bool force_old2 = [] {
+      const char* e = getenv("BRCNN_NMS_OP");
+      return e && e[0] == 'o';
+    }();
+    const int keep_pad = nms_keep_pad(K, K);
+    int np2 = 1;
+    while (np2 < K) np2 <<= 1;
+    if (!force_old2 && idxs != nullptr && num_ids > BRCNN_MAX_LEVELS && num_ids <= 1024 &&
+        (size_t)keep_pad * 20 <= 160 * 1024 && (size_t)np2 * 8 <= 160 * 1024) {
+      int32_t* seg_start = (int32_t*)(ws + w.seg);
+      int32_t* seg_count = seg_start + NMS_MAX_IDS;
+      cudaError_t e = cudaMemsetAsync(seg_start, 0, 2 * NMS_MAX_IDS * 4, stream);
+      if (e != cudaSuccess) return (int)e;
+      nms_id_rank_scatter_kernel<<<(K + 255) / 256, 256, 0, stream>>>(
+          boxes, scores, idxs, K, num_ids, sboxes, skey, seg_start, seg_count);
+      g_launch_count_add(1);
+      BRCNN_CUDA_CHECK_LAST();
+      const size_t smem = (size_t)keep_pad * 20;
+      if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(nms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem);
+        if (e != cudaSuccess) return (int)e;
+      }
+      u64* kept_key = (u64*)(ws + w.mask);   // K u64, the bitmask area is unused on this path
+      nms_fused_kernel<<<num_ids, NMS_FUSED_THREADS, smem, stream>>>(
+          sboxes, nullptr, seg_count, K, iou_threshold, (float)offset, maxc, num_ids, skey,
+          kept_pos, kept_key, kept_count_ids(ws, w), K, K, keep_pad, seg_start);
+      g_launch_count_add(1);
+      BRCNN_CUDA_CHECK_LAST();
+      const size_t sm = (size_t)np2 * 8;
+      if (sm > 32 * 1024) {
+        e = cudaFuncSetAttribute(nms_merge_sort_kernel<OpMergeEpilogue>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return (int)e;
+      }
+      OpMergeEpilogue ep{keep};
+      nms_merge_sort_kernel<OpMergeEpilogue><<<1, 1024, sm, stream>>>(
+          kept_key, kept_count_ids(ws, w), num_ids, K, K, np2, num_keep, ep, seg_start);
       g_launch_count_add(1);
       BRCNN_CUDA_CHECK_LAST();
       if (dets != nullptr) {

@@ -76,7 +76,8 @@ nms_fused_kernel(const float4* __restrict__ boxes, const uint8_t* __restrict__ v
                  const float* __restrict__ img_maxc, int Sg,
                  const u64* __restrict__ cand_key, int32_t* __restrict__ kept_pos,
                  u64* __restrict__ kept_key, int32_t* __restrict__ kept_count,
-                 int keep_cap, int max_keep, int keep_pad) {
+                 int keep_cap, int max_keep, int keep_pad,
+                 const int32_t* __restrict__ seg_start) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
   float4* kbox = reinterpret_cast<float4*>(nms_smem);        // [keep_pad]
   float* karea = reinterpret_cast<float*>(kbox + keep_pad);  // [keep_pad]
@@ -90,7 +91,11 @@ nms_fused_kernel(const float4* __restrict__ boxes, const uint8_t* __restrict__ v
   const int n = min(count[s], cap);
   const int Wn = (n + 63) >> 6;
   const int tid = threadIdx.x, lane = tid & 31;
-  const float4* seg = boxes + (size_t)s * cap;
+  // uniform capacity `cap` per segment, or (seg_start != nullptr) variable-size segments
+  // packed back to back; kept lists then share the segment's offset (kept <= count)
+  const size_t sbase = seg_start != nullptr ? (size_t)seg_start[s] : (size_t)s * cap;
+  const size_t kbase = seg_start != nullptr ? (size_t)seg_start[s] : (size_t)s * keep_cap;
+  const float4* seg = boxes + sbase;
   float segoff = 0.f;
   const bool has_off = (img_maxc != nullptr);
   if (has_off) segoff = (float)(s % Sg) * (img_maxc[s / Sg] + 1.0f);
@@ -100,7 +105,7 @@ nms_fused_kernel(const float4* __restrict__ boxes, const uint8_t* __restrict__ v
   bool ndead = true;
   if (tid < 64 && tid < n) {
     nb = seg[tid];
-    ndead = (valid != nullptr && valid[(size_t)s * cap + tid] == 0);
+    ndead = (valid != nullptr && valid[sbase + tid] == 0);
   }
   __syncthreads();
 
@@ -117,7 +122,7 @@ nms_fused_kernel(const float4* __restrict__ boxes, const uint8_t* __restrict__ v
       ndead = true;
       if (i < n) {
         nb = seg[i];
-        ndead = (valid != nullptr && valid[(size_t)s * cap + i] == 0);
+        ndead = (valid != nullptr && valid[sbase + i] == 0);
       }
     }
     __syncthreads();
@@ -196,7 +201,7 @@ nms_fused_kernel(const float4* __restrict__ boxes, const uint8_t* __restrict__ v
         if ((keep >> r) & 1ull) {
           const int q = nkept + __popcll(keep & ((1ull << r) - 1ull));
           if (q < keep_cap && q < max_keep) {
-            kept_pos[(size_t)s * keep_cap + q] = t * 64 + r;
+            kept_pos[kbase + q] = t * 64 + r;
             kbox[q] = tb[r];
             karea[q] = ta[r];
           }
@@ -212,8 +217,7 @@ nms_fused_kernel(const float4* __restrict__ boxes, const uint8_t* __restrict__ v
   if (tid == 0) kept_count[s] = nk;
   if (cand_key != nullptr)
     for (int i = tid; i < nk; i += NMS_FUSED_THREADS)
-      kept_key[(size_t)s * keep_cap + i] =
-          cand_key[(size_t)s * cap + kept_pos[(size_t)s * keep_cap + i]];
+      kept_key[kbase + i] = cand_key[sbase + kept_pos[kbase + i]];
 }
 
 // ---------------------------------------------------------------------------
@@ -414,7 +418,8 @@ template <class Epilogue>
 __global__ void __launch_bounds__(1024)
 nms_merge_sort_kernel(const u64* __restrict__ kept_key, const int32_t* __restrict__ kept_count,
                       int Sg, int keep_cap, int max_out, int np2,
-                      int32_t* __restrict__ num_out, Epilogue ep) {
+                      int32_t* __restrict__ num_out, Epilogue ep,
+                      const int32_t* __restrict__ seg_start = nullptr) {
   extern __shared__ __align__(16) u64 s_keys[];
   __shared__ int s_off[1025];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -432,7 +437,8 @@ nms_merge_sort_kernel(const u64* __restrict__ kept_key, const int32_t* __restric
   // one warp per list: coalesced copy of its kept keys
   for (int g = tid >> 5; g < Sg; g += blockDim.x >> 5) {
     const int o = s_off[g], ng = s_off[g + 1] - o;
-    const u64* src = kept_key + (size_t)(b * Sg + g) * keep_cap;
+    const u64* src = kept_key + (seg_start != nullptr ? (size_t)seg_start[b * Sg + g]
+                                                      : (size_t)(b * Sg + g) * keep_cap);
     for (int j = tid & 31; j < ng; j += 32) s_keys[o + j] = src[j];
   }
   int np = 1;
@@ -516,7 +522,7 @@ inline int launch_nms_segments(const float4* boxes, const uint8_t* valid,
     }
     nms_fused_kernel<<<S, NMS_FUSED_THREADS, smem, stream>>>(
         boxes, valid, count, cap, thr, off, img_maxc, Sg, cand_key, kept_pos, kept_key,
-        kept_count, keep_cap, max_keep, keep_pad);
+        kept_count, keep_cap, max_keep, keep_pad, (const int32_t*)nullptr);
     g_launch_count_add(1);
     BRCNN_CUDA_CHECK_LAST();
     return BRCNN_OK;

@@ -116,9 +116,12 @@ int brcnn_delta2bbox(const float* rois, const float* deltas, int32_t n,
 size_t brcnn_nms_workspace_bytes(int32_t num_boxes);
 
 /* idxs may be NULL (plain / class-agnostic nms).  num_ids: caller's bound on the
- * id range (idxs in [0, num_ids)); <= 0 = unknown.  With num_ids <= 8 (pyramid
- * levels; or idxs == NULL) the ids are walked as sorted lists in global score
- * order by a cluster of 8 CTAs, otherwise as one offset-box segment.
+ * id range (idxs in [0, num_ids)); <= 0 = unknown.  Three paths, same results:
+ *   num_ids <= 8 (pyramid levels; or idxs == NULL): the ids are walked as sorted
+ *     lists in global score order by a cluster of 8 CTAs (rpn_nms.cuh);
+ *   8 < num_ids <= 1024 and num_boxes <= 8192 (class-wise NMS): one fused-NMS CTA
+ *     per id on the id-sorted boxes, kept lists merged by an in-smem sort;
+ *   otherwise: one segment of offset boxes (mmcv's formulation).
  * keep: int64[num_boxes] (first *num_keep entries valid, score-descending),
  * dets: optional float[num_boxes][5] rows cat(boxes[keep], scores[keep]).     */
 int brcnn_batched_nms(const float* boxes, const float* scores,

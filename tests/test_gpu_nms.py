@@ -86,7 +86,8 @@ def test_nms_rejects_cpu_tensors():
 
 def test_nms_operator_cluster_and_segment_paths_agree(cuda):
     """BRCNN_NMS_OP=old (one offset-box segment) vs the default clustered list walk
-    of brcnn_batched_nms: identical keep lists for plain nms, offset=1, <= 8 ids."""
+    of brcnn_batched_nms (<= 8 ids) and the per-id segmented path (> 8 ids, K <= 8192):
+    identical keep lists for plain nms, offset=1, few and many ids."""
     import os
     import subprocess
     import sys
@@ -98,7 +99,8 @@ sys.path[:0] = [%r, %r]
 import synth
 from boosting_rcnn_b200 import ops
 res = []
-for K, nid, clustered in ((700, 1, True), (4693, 5, False), (9000, 8, True), (3000, 3, True)):
+for K, nid, clustered in ((700, 1, True), (4693, 5, False), (9000, 8, True), (3000, 3, True),
+                          (5000, 80, True), (8192, 9, False), (900, 1000, True)):
     b = torch.from_numpy(synth.random_boxes(K, 800, 1333, seed=K, clustered=clustered)).cuda()
     g = torch.Generator().manual_seed(K)
     s = (torch.randint(0, 400, (K,), generator=g).float() / 400 - 0.2).cuda()   # ties, negatives
