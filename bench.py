@@ -363,7 +363,7 @@ def bench_train(args, rank, world, local_rank):
         feat_bytes = sum(f.numel() * 4 for f in feats)
         bwd_bytes = R * C * 49 * 4 + feat_bytes
         ach = bwd_bytes / (st['roi_align_bwd'] * 1e-3) / 1e9
-        roof = dict(kernel='roi_bwd_gather_kernel (+ geometry, grad_out transpose)', bound='hbm',
+        roof = dict(kernel='roi_bwd_gather2_kernel (+ prep, grad_out transpose)', bound='hbm',
                     achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,
                     peak_source=peak_src, algorithmic_bytes_per_launch=bwd_bytes,
                     ms_per_launch=st['roi_align_bwd'])
