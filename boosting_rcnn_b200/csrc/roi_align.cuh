@@ -1,5 +1,7 @@
-// K3: fused FPN level mapping + multi-level RoIAlign forward (one launch for
-// all levels), NHWC feature maps, NCHW (R,C,ph,pw) output.
+// K3 (v1 register-tile kernel, kept for pooled sizes > 7; roi_align_tma.cuh is the main
+// path) + the shared geometry helpers, bbox2roi, level map and pyramid transposes.
+// Fused FPN level mapping + multi-level RoIAlign forward (one launch for all levels),
+// NHWC feature maps, NCHW (R,C,ph,pw) output.
 //
 // Reference behaviour: single_level_roi_extractor.py:36-115 + mmcv RoIAlign
 // (aligned=True, pool_mode='avg', sampling_ratio=0), SURVEY.md App. A5/A6.

@@ -1,6 +1,6 @@
 // K4 (v1, kept for pooled sizes > 7; roi_align_bwd2.cuh is the main path):
-// multi-level RoIAlign backward as a deterministic gather (no float atomics).  Reference: autograd of mmcv RoIAlign (roi_align_backward, 4
-// atomicAdd per sample) reached from single_level_roi_extractor.py:79,103;
+// multi-level RoIAlign backward as a deterministic gather (no float atomics).
+// Reference: autograd of mmcv RoIAlign (roi_align_backward, 4 atomicAdd per sample) reached from single_level_roi_extractor.py:79,103;
 // empty levels still receive a (zero) gradient like :105-114.
 //
 // Because bilinear weights are separable, the gradient a RoI sends to the
