@@ -61,3 +61,45 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         _lib.load()
+
+
+def _build_c_consumer(tmp_path):
+    """gcc-compile tests/c_abi/abi_smoke.c against include/brcnn.h + libbrcnn.so."""
+    import shutil
+    import subprocess
+    src = os.path.join(ROOT, 'tests', 'c_abi', 'abi_smoke.c')
+    exe = str(tmp_path / 'abi_smoke')
+    cuda = os.environ.get('CUDA_HOME', '/usr/local/cuda')
+    if shutil.which('gcc') is None or not os.path.isdir(os.path.join(cuda, 'include')):
+        pytest.skip('gcc / CUDA toolkit headers not available')
+    cmd = ['gcc', '-O1', '-Wall', '-Werror', src, '-I' + os.path.join(ROOT, 'include'),
+           '-I' + os.path.join(cuda, 'include'), '-L' + os.path.dirname(_lib.LIB_PATH),
+           '-L' + os.path.join(cuda, 'lib64'), '-lbrcnn', '-lcudart', '-lm', '-o', exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    env = dict(os.environ)
+    env['LD_LIBRARY_PATH'] = os.pathsep.join(
+        [os.path.dirname(_lib.LIB_PATH), os.path.join(cuda, 'lib64'), env.get('LD_LIBRARY_PATH', '')])
+    return exe, env
+
+
+def test_plain_c_consumer_compiles_and_links(tmp_path):
+    """The boundary is a C ABI: a C translation unit that includes only brcnn.h and the CUDA
+    runtime compiles with -Wall -Werror, links against libbrcnn.so and loads (exit code 77 =
+    'no CUDA device', the expected answer in the CPU-only build container)."""
+    import subprocess
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    exe, env = _build_c_consumer(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, env=env)
+    assert res.returncode in (0, 77), (res.returncode, res.stdout, res.stderr)
+    assert 'sm_100a' in res.stdout or 'abi_smoke ok' in res.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_consumer_runs_on_gpu(tmp_path):
+    import subprocess
+    exe, env = _build_c_consumer(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, env=env)
+    assert res.returncode == 0, (res.stdout, res.stderr)
+    assert 'abi_smoke ok' in res.stdout
