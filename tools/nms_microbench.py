@@ -1,5 +1,8 @@
-import sys, time, numpy as np, torch
-sys.path[:0] = ['/root/repo', '/root/repo/tests']
+"""Wall-clock per call of the mmcv-style batched_nms operator (ops.py) at detection sizes.
+  gpurun -- 'python tools/nms_microbench.py'"""
+import os, sys, time, numpy as np, torch
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [_ROOT, os.path.join(_ROOT, 'tests')]
 import synth
 from boosting_rcnn_b200 import ops
 dev = torch.device('cuda')
