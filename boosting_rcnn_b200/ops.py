@@ -432,6 +432,44 @@ class RoIAlign(nn.Module):
 # --------------------------------------------------------------------------
 # R-CNN training front-end: assign + sample + targets + prior (two launches)
 # --------------------------------------------------------------------------
+def sample_plan(counts, num, pos_fraction, neg_pos_ub=-1):
+    """Host half of RandomSampler.sample (samplers/base_sampler.py:35-102,
+    random_sampler.py:32-82) for a batch: from the per-image numbers of positive /
+    negative candidates decide how many rows each image contributes and draw the
+    permutations exactly like the reference — ``torch.randperm(n)[:k]`` on the CPU
+    generator, only when a list is longer than its quota, positives before negatives,
+    image by image.  Pure host code (unit-tested without a GPU).
+
+    Returns plan (B,5) int32 [n_pos, n_neg, first_row, use_perm_pos, use_perm_neg],
+    perm_pos / perm_neg (B, max(1,num)) int32, rows per image."""
+    B = len(counts)
+    n_exp_pos = int(num * pos_fraction)
+    cap = max(1, num)
+    plan = torch.zeros((B, 5), dtype=torch.int32)
+    perm_pos = torch.zeros((B, cap), dtype=torch.int32)
+    perm_neg = torch.zeros((B, cap), dtype=torch.int32)
+    rows, base = [], 0
+    for b in range(B):
+        n_pos_c, n_neg_c = int(counts[b][0]), int(counts[b][1])
+        if n_pos_c > n_exp_pos:
+            perm_pos[b, :n_exp_pos] = torch.randperm(n_pos_c)[:n_exp_pos].to(torch.int32)
+            n_pos, use_p = n_exp_pos, 1
+        else:
+            n_pos, use_p = n_pos_c, 0
+        n_exp_neg = num - n_pos
+        if neg_pos_ub >= 0:
+            n_exp_neg = min(n_exp_neg, int(neg_pos_ub * max(1, n_pos)))
+        if n_neg_c > n_exp_neg:
+            perm_neg[b, :n_exp_neg] = torch.randperm(n_neg_c)[:n_exp_neg].to(torch.int32)
+            n_neg, use_n = n_exp_neg, 1
+        else:
+            n_neg, use_n = n_neg_c, 0
+        plan[b] = torch.tensor([n_pos, n_neg, base, use_p, use_n], dtype=torch.int32)
+        rows.append(n_pos + n_neg)
+        base += n_pos + n_neg
+    return plan, perm_pos, perm_neg, rows
+
+
 def rcnn_assign_sample(proposals, num_props, gt_bboxes, gt_labels, num_classes,
                        pos_iou_thr, neg_iou_thr, min_pos_iou=0., num=512, pos_fraction=0.25,
                        neg_pos_ub=-1, means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.),
@@ -467,30 +505,9 @@ def rcnn_assign_sample(proposals, num_props, gt_bboxes, gt_labels, num_classes,
                                 num_gt.data_ptr(), gt_inds.data_ptr(), counts.data_ptr(),
                                 _stream()), 'brcnn_rcnn_assign')
     cnt = counts.cpu().tolist()          # the one host sync of the training front-end
-    n_exp_pos = int(num * pos_fraction)
-    cap = max(1, num)
-    plan = torch.zeros((B, 5), dtype=torch.int32)
-    perm_pos = torch.zeros((B, cap), dtype=torch.int32)
-    perm_neg = torch.zeros((B, cap), dtype=torch.int32)
-    rows, base = [], 0
-    for b in range(B):
-        n_pos_c, n_neg_c = cnt[b]
-        if n_pos_c > n_exp_pos:
-            perm_pos[b, :n_exp_pos] = torch.randperm(n_pos_c)[:n_exp_pos].to(torch.int32)
-            n_pos, use_p = n_exp_pos, 1
-        else:
-            n_pos, use_p = n_pos_c, 0
-        n_exp_neg = num - n_pos
-        if neg_pos_ub >= 0:
-            n_exp_neg = min(n_exp_neg, int(neg_pos_ub * max(1, n_pos)))
-        if n_neg_c > n_exp_neg:
-            perm_neg[b, :n_exp_neg] = torch.randperm(n_neg_c)[:n_exp_neg].to(torch.int32)
-            n_neg, use_n = n_exp_neg, 1
-        else:
-            n_neg, use_n = n_neg_c, 0
-        plan[b] = torch.tensor([n_pos, n_neg, base, use_p, use_n], dtype=torch.int32)
-        rows.append(n_pos + n_neg)
-        base += n_pos + n_neg
+    plan, perm_pos, perm_neg, rows = sample_plan(cnt, num, pos_fraction, neg_pos_ub)
+    cap = perm_pos.size(1)
+    base = sum(rows)
     N = base
     to = lambda t: t.to(dev, non_blocking=True)
     plan_d, pp_d, pn_d = to(plan), to(perm_pos), to(perm_neg)

@@ -121,3 +121,38 @@ def test_ops_reject_cpu_tensors():
         ops.delta2bbox(torch.zeros(3, 4), torch.zeros(3, 4))
     with pytest.raises(RuntimeError):
         ops.roi_extract([torch.zeros(1, 4, 8, 8)], torch.zeros(2, 5), [0.125])
+
+
+def test_sample_plan_matches_random_sampler_counts_and_rng_stream():
+    """ops.sample_plan (the host half of the fused training front-end) draws exactly the
+    permutations RandomSampler.sample draws, in the same order, from the same CPU RNG
+    state, and selects the same index sets."""
+    rng = np.random.RandomState(0)
+    cases = []
+    for n_pos, n_neg in ((3, 2000), (300, 1500), (0, 40), (200, 100), (128, 384), (129, 0)):
+        gi = torch.cat([torch.ones(n_pos, dtype=torch.long), torch.zeros(n_neg, dtype=torch.long),
+                        -torch.ones(7, dtype=torch.long)])
+        gi = gi[torch.from_numpy(rng.permutation(len(gi)))]
+        cases.append(gi)
+    for ub in (-1, 3):
+        s = sampling.RandomSampler(num=512, pos_fraction=0.25, neg_pos_ub=ub,
+                                   add_gt_as_proposals=False)
+        torch.manual_seed(5)
+        ref = []
+        for gi in cases:
+            ar = sampling.AssignResult(0, gi.clone(), gi.new_zeros(len(gi), dtype=torch.float))
+            res = s.sample(ar, torch.zeros(len(gi), 4), torch.zeros(0, 4))
+            ref.append((res.pos_inds, res.neg_inds))
+        torch.manual_seed(5)
+        counts = [(int((gi > 0).sum()), int((gi == 0).sum())) for gi in cases]
+        plan, pp, pn, rows = ops.sample_plan(counts, 512, 0.25, ub)
+        base = 0
+        for b, gi in enumerate(cases):
+            n_pos, n_neg, first, use_p, use_n = plan[b].tolist()
+            assert first == base and rows[b] == n_pos + n_neg
+            base += rows[b]
+            pos_list = torch.nonzero(gi > 0).squeeze(1)
+            neg_list = torch.nonzero(gi == 0).squeeze(1)
+            pos = pos_list[pp[b, :n_pos].long()].sort().values if use_p else pos_list
+            neg = neg_list[pn[b, :n_neg].long()].sort().values if use_n else neg_list
+            assert torch.equal(pos, ref[b][0]) and torch.equal(neg, ref[b][1]), (ub, b)
