@@ -61,6 +61,40 @@ class HotPathGraph:
         return self._fn()
 
 
+class DualStreamRunner:
+    """Two (or more) captured steps in flight, one stream each.
+
+    One step is a short bandwidth/latency-bound phase (proposals, layout hand-off,
+    RoIAlign, post-processing: our kernels) around a long compute-bound phase (the 2-fc
+    head on cuBLAS SGEMM).  Consecutive batches are independent, so replaying them
+    alternately on two streams lets the memory-bound phase of batch i+1 run beside the
+    GEMMs of batch i.  Each stream owns its own graph (own workspaces and outputs); the
+    input tensors may be shared (they are only read)."""
+
+    def __init__(self, graphs):
+        assert len(graphs) >= 2
+        self.graphs = graphs
+        self.streams = [torch.cuda.Stream() for _ in graphs]
+        self._i = 0
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            s.wait_stream(cur)
+
+    def step(self):
+        k = self._i % len(self.graphs)
+        self._i += 1
+        with torch.cuda.stream(self.streams[k]):
+            self.graphs[k].replay()
+        return self.graphs[k].outputs
+
+    def drain(self):
+        """Make the current stream wait for both branches (call before recording the
+        closing event / reading outputs)."""
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            cur.wait_stream(s)
+
+
 class HostPipeline:
     """Double-buffered end-to-end pipeline for host-resident inputs.
 

@@ -328,3 +328,30 @@ def test_fused_assign_sample_targets_equals_python_path(cuda, case):
         out.append(roi.forward_train(feats, _metas(B), plist, gts, labels))
     for k in ('loss_cls', 'loss_bbox', 'acc'):
         assert torch.allclose(out[0][k], out[1][k], rtol=1e-6, atol=1e-7), k
+
+
+def test_dual_stream_runner_matches_single_graph(cuda):
+    """graph.py::DualStreamRunner: two graphs replayed alternately on two streams give the
+    same detections as one graph, for any interleaving."""
+    from boosting_rcnn_b200.graph import DualStreamRunner, HotPathGraph
+    torch.manual_seed(0)
+    rpn, roi, model = configs.build_hot_path('utdac')
+    rpn, roi = rpn.to(cuda).eval(), roi.to(cuda).eval()
+    B, sizes = 2, synth.featmap_sizes(256, 320)
+    cls, box, iou = synth.rpn_outputs(B, sizes, rpn.num_anchors, seed=5)
+    t = lambda arrs: [torch.from_numpy(a).to(cuda) for a in arrs]
+    ins = (t(synth.fpn_feats(B, 256, sizes, seed=6)), t(cls), t(box), t(iou))
+    g1 = HotPathGraph(rpn, roi, _metas(B), *ins, rcnn_test_cfg=model['test_cfg']['rcnn'])
+    g2 = HotPathGraph(rpn, roi, _metas(B), *ins, rcnn_test_cfg=model['test_cfg']['rcnn'])
+    ref = [o.clone() for o in g1.replay()]
+    torch.cuda.synchronize()
+    dual = DualStreamRunner([g1, g2])
+    outs = []
+    for _ in range(7):
+        o = dual.step()
+        outs.append(o)
+    dual.drain()
+    torch.cuda.synchronize()
+    for g in (g1, g2):
+        for a, b in zip(g.outputs, ref):
+            assert torch.equal(a, b)
