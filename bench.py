@@ -628,6 +628,18 @@ def main():
     # headline: throughput with two batches in flight (one captured graph per stream);
     # --no-graph: the eager single-stream number
     ms = ms_dual if ms_dual is not None else ms_single
+    verified = None
+    if ms_dual is not None:
+        # the two in-flight graphs must reproduce the single-stream detections bit for bit
+        ref_out = [o.clone() for o in g_nchw.replay()]
+        torch.cuda.synchronize()
+        for _ in range(4):
+            dual.step()
+        dual.drain()
+        torch.cuda.synchronize()
+        verified = all(torch.equal(a, b) for g in (g_nchw, g_nchw2)
+                       for a, b in zip(g.outputs, ref_out))
+        assert verified, 'two-stream replay changed the detections'
     e2e = E2E()
     k_e2e = max(K // 2, 4)
     ms_e2e = timed(e2e.step, k_e2e, 3, drain=e2e.drain)
@@ -745,6 +757,7 @@ def main():
                            'layout); NCHW->NHWC conversion kernels are inside the timed step'),
             'value_single_stream_channels_last_feats': B * world * K / (ms_cl * 1e-3),
             'value_single_stream': B * world * K / (ms_single * 1e-3),
+            'two_stream_outputs_bit_identical': verified,
             'ms_per_step_single_stream': ms_single / K,
             'value_single_stream_tf32_head_informational': (B * world * K / (ms_tf32 * 1e-3)) if ms_tf32 else None,
             'e2e': {'value': B * world * k_e2e / (ms_e2e * 1e-3), 'unit': 'images/s',
