@@ -177,6 +177,27 @@ def main():
     gold['rpn_proposals'] = props.numpy()
     gold['rpn_img_shape'] = np.array([90, 125], dtype=np.float32)
 
+    # ---- the same at training size: 61 380 anchors, nms_pre 4000 -> 11 780 candidates, so
+    # the (restated) mmcv batched_nms takes its split_thr >= 10000 path (per-level nms +
+    # re-sort).  Inputs are re-generated from the seed by the test
+    # (synth.rpn_outputs), only the 2000 x 5 result is stored.
+    big_sizes = [(64, 80), (32, 40), (16, 20), (8, 10), (4, 5)]
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT)))
+    import synth
+    bcls, bbox, biou = synth.rpn_outputs(1, big_sizes, 9, seed=4242)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        big_anchors = gen.grid_anchors(big_sizes, device='cpu')
+    cfg_big = AttrDict(nms_pre=4000, max_per_img=2000, nms=dict(type='nms', iou_threshold=0.7),
+                       min_bbox_size=0)
+    props_big = ns['_get_bboxes_single'](
+        self, [torch.from_numpy(c[0]) for c in bcls], [torch.from_numpy(c[0]) for c in bbox],
+        [torch.from_numpy(c[0]) for c in biou], big_anchors, (500, 633, 3), 1.0, cfg_big)
+    assert props_big.shape == (2000, 5)
+    np.savez_compressed(os.path.join(OUT, 'reference_golden_rpn_train.npz'),
+                        proposals=props_big.numpy(), img_shape=np.array([500, 633], np.float32),
+                        seed=np.array(4242), sizes=np.array(big_sizes))
+
     # ---- map_roi_levels (single_level_roi_extractor.py:36-55) ----
     ns = base_namespace()
     lift('mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py',

@@ -355,3 +355,19 @@ def test_dual_stream_runner_matches_single_graph(cuda):
     for g in (g1, g2):
         for a, b in zip(g.outputs, ref):
             assert torch.equal(a, b)
+
+
+def test_golden_rpn_train_size_split_path_cuda(cuda):
+    """The CUDA path against the train-size golden produced by executing the reference's
+    _get_bboxes_single (11 780 candidates, mmcv split path): same 2000 proposals up to swaps
+    of rows whose scores agree to ~1e-7 (torch.sigmoid vs pinned exp, unstable torch.sort)."""
+    from test_oracle_golden import _match_rows_allowing_near_tie_swaps, _rpn_train_golden_inputs
+    g, sizes, cls, box, iou = _rpn_train_golden_inputs()
+    gen = AnchorGenerator(strides=[8, 16, 32, 64, 128], ratios=[0.5, 1.0, 2.0],
+                          octave_base_scale=4, scales_per_octave=3)
+    p = ops.make_rpn_params(1, sizes, synth.STRIDES, 9, 4000, 2000, 0.7, 0.0)
+    t = lambda arrs: [torch.from_numpy(a).to(cuda) for a in arrs]
+    hw = torch.tensor([list(g['img_shape'])], dtype=torch.float32, device=cuda)
+    props, num = ops.rpn_get_bboxes(p, t(cls), t(box), t(iou), gen.base_anchor_table().to(cuda), hw)
+    assert int(num[0]) == 2000
+    assert _match_rows_allowing_near_tie_swaps(props[0].cpu().numpy(), g['proposals']) <= 20
