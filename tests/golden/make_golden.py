@@ -218,6 +218,16 @@ def main():
     # ---- multiclass_nms (bbox_nms.py:8-95) ----
     ns = base_namespace()
     lift('mmdet/core/post_processing/bbox_nms.py', ['multiclass_nms'], ns)
+    # COCO scale: 256 RoIs x 80 classes, score_thr 0.001 -> ~20 000 candidates, so the
+    # restated mmcv batched_nms runs its split path; inputs are re-generated from the seed
+    # by the test (tests/synth.py::multiclass_inputs), only the 100 detections are stored
+    import synth as _synth
+    mbb, mss = _synth.multiclass_inputs(256, 80, seed=777)
+    dd, ll = ns['multiclass_nms'](torch.from_numpy(mbb), torch.from_numpy(mss), 0.001,
+                                  dict(type='nms', iou_threshold=0.5), 100)
+    assert int((mss[:, :-1] > 0.001).sum()) >= 10000
+    np.savez_compressed(os.path.join(OUT, 'reference_golden_multiclass_coco.npz'),
+                        dets=dd.numpy(), labels=ll.numpy(), seed=np.array(777))
     R, C = 60, 4
     ctr = rng.uniform(20, 280, (R, 1, 2)) + rng.normal(0, 6, (R, C, 2))
     whc = rng.uniform(20, 120, (R, C, 2))

@@ -60,3 +60,16 @@ def random_boxes(n, img_h, img_w, seed=0, clustered=False):
     r = random_rois(1, n, img_h, img_w, seed=seed, min_size=8, max_size=400,
                     clustered=clustered)
     return r[:, 1:].copy()
+
+
+def multiclass_inputs(R, C, seed=0, img=(800, 1333)):
+    """(R, 4C) per-class boxes clustered around R seeds and (R, C+1) scores with
+    distinct values (no ties): input of multiclass_nms at COCO scale."""
+    rng = np.random.RandomState(seed)
+    ctr = rng.uniform(40, 760, (R, 1, 2)) * [img[1] / 800.0, 1.0] + rng.normal(0, 8, (R, C, 2))
+    wh = rng.uniform(20, 200, (R, C, 2))
+    b = np.concatenate([ctr - wh / 2, ctr + wh / 2], -1)
+    b[..., 0::2] = b[..., 0::2].clip(0, img[1])
+    b[..., 1::2] = b[..., 1::2].clip(0, img[0])
+    s = rng.permutation(R * (C + 1)).reshape(R, C + 1).astype(np.float32) / (R * (C + 1))
+    return b.reshape(R, C * 4).astype(np.float32), s.astype(np.float32)

@@ -371,3 +371,14 @@ def test_golden_rpn_train_size_split_path_cuda(cuda):
     props, num = ops.rpn_get_bboxes(p, t(cls), t(box), t(iou), gen.base_anchor_table().to(cuda), hw)
     assert int(num[0]) == 2000
     assert _match_rows_allowing_near_tie_swaps(props[0].cpu().numpy(), g['proposals']) <= 20
+
+
+def test_golden_multiclass_nms_coco_scale_cuda(cuda):
+    """The batched_nms operator on the COCO-scale golden of the executed reference
+    multiclass_nms (80 classes, > 10 000 candidates)."""
+    from test_oracle_golden import _multiclass_coco_candidates
+    g, boxes, scores, labels = _multiclass_coco_candidates()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    dets, keep = ops.batched_nms(t(boxes), t(scores), t(labels), dict(type='nms', iou_threshold=0.5))
+    np.testing.assert_array_equal(labels[keep.cpu().numpy()][:100], g['labels'])
+    np.testing.assert_array_equal(dets[:100].cpu().numpy().view(np.uint32), g['dets'].view(np.uint32))

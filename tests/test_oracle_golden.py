@@ -253,3 +253,24 @@ def test_rpn_train_size_split_path_vs_executed_reference():
         gen.base_anchor_table().numpy(), synth.STRIDES, tuple(g['img_shape']), 4000, 2000, 0.7, 0.0)
     swapped = _match_rows_allowing_near_tie_swaps(props, g['proposals'])
     assert swapped <= 20, swapped
+
+
+def _multiclass_coco_candidates():
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden',
+                             'reference_golden_multiclass_coco.npz'))
+    mb, ms = synth.multiclass_inputs(256, 80, seed=int(g['seed']))
+    R, C = ms.shape[0], ms.shape[1] - 1
+    valid = ms[:, :C] > 0.001                      # bbox_nms.py:55, row-major (roi, class)
+    rr, cc = np.nonzero(valid)
+    boxes = mb.reshape(R, C, 4)[rr, cc]
+    return g, boxes, ms[rr, cc], cc
+
+
+def test_multiclass_nms_coco_scale_split_path_vs_executed_reference():
+    """256 RoIs x 80 classes above score_thr (> 10 000 candidates -> mmcv batched_nms split
+    path) executed by the reference's multiclass_nms: identical 100 detections + labels."""
+    g, boxes, scores, labels = _multiclass_coco_candidates()
+    assert len(scores) >= 10000
+    dets, keep = oracle.batched_nms(boxes, scores, labels, 0.5)
+    np.testing.assert_array_equal(labels[keep][:100], g['labels'])
+    np.testing.assert_array_equal(dets[:100].view(np.uint32), g['dets'].view(np.uint32))
