@@ -156,3 +156,47 @@ def test_sample_plan_matches_random_sampler_counts_and_rng_stream():
             pos = pos_list[pp[b, :n_pos].long()].sort().values if use_p else pos_list
             neg = neg_list[pn[b, :n_neg].long()].sort().values if use_n else neg_list
             assert torch.equal(pos, ref[b][0]) and torch.equal(neg, ref[b][1]), (ub, b)
+
+
+def test_register_into_mmdet_against_a_stub_registry(monkeypatch):
+    """registry.register_into_mmdet / mmdet_plugin (INTEGRATION.md level 1) against a stub of
+    mmdet.models.builder exposing mmcv's Registry.register_module(name=, force=, module=)."""
+    import importlib
+    import sys
+    import types
+
+    class StubRegistry:
+        def __init__(self):
+            self.module_dict = {}
+
+        def register_module(self, name=None, force=False, module=None):
+            if name in self.module_dict and not force:
+                raise KeyError(name)
+            self.module_dict[name] = module
+            return module
+
+    heads, extractors = StubRegistry(), StubRegistry()
+    heads.module_dict['ATSSRPNHead'] = object          # the reference's own class is replaced
+    builder = types.ModuleType('mmdet.models.builder')
+    builder.HEADS, builder.ROI_EXTRACTORS = heads, extractors
+    models = types.ModuleType('mmdet.models')
+    models.builder = builder
+    mmdet = types.ModuleType('mmdet')
+    mmdet.models = models
+    for n, m in (('mmdet', mmdet), ('mmdet.models', models), ('mmdet.models.builder', builder)):
+        monkeypatch.setitem(sys.modules, n, m)
+    from boosting_rcnn_b200 import bbox_head, registry, roi_extractor, roi_head, rpn_head
+    names = registry.register_into_mmdet(force=True)
+    assert set(names) == set(registry.HOT_PATH_CLASSES)
+    assert heads.module_dict['ATSSRPNHead'] is rpn_head.ATSSRPNHead
+    assert heads.module_dict['ProbRoIHead'] is roi_head.ProbRoIHead
+    assert heads.module_dict['ProbConvFCBBoxHead'] is bbox_head.ProbConvFCBBoxHead
+    assert extractors.module_dict['SingleRoIExtractor'] is roi_extractor.SingleRoIExtractor
+    # subset selection through the plugin module's environment variable
+    heads.module_dict.clear()
+    monkeypatch.setenv('BRCNN_PLUGIN_CLASSES', 'ProbRoIHead,SingleRoIExtractor')
+    sys.modules.pop('boosting_rcnn_b200.mmdet_plugin', None)
+    plugin = importlib.import_module('boosting_rcnn_b200.mmdet_plugin')
+    assert plugin.REGISTERED == ('ProbRoIHead', 'SingleRoIExtractor')
+    assert set(heads.module_dict) == {'ProbRoIHead'}
+    sys.modules.pop('boosting_rcnn_b200.mmdet_plugin', None)
