@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument('--cpu-images', type=int, default=0,
                     help='images in the CPU-baseline sample (0: one per host thread, <= 16)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train-record', action='store_true',
+                    help='skip the configs[2] training-step sub-record of the default line')
+    ap.add_argument('--strong-total', type=int, default=16,
+                    help='images of the strong-scaling sub-record (sharded over the GPUs)')
     ap.add_argument('--no-graph', action='store_true', help='launch kernels one by one')
     ap.add_argument('--rpn-max-per-img', type=int, default=0,
                     help='override test_cfg.rpn.max_per_img (BASELINE configs[3]: VOC at 1000)')
@@ -204,6 +208,35 @@ def roi_footprint_bytes(rois, sizes, channels, finest=56.0):
     return tot
 
 
+def roi_union_bytes(rois, sizes, channels, finest=56.0):
+    """Distinct feature bytes the RoIs read: per (image, level) the UNION of the footprint
+    pixels (rows/columns any bilinear tap of the RoI can touch, the kernels' own
+    conservative box) as a bitmap, x C x 4 B.  This is what has to cross HBM at least
+    once; `roi_footprint_bytes` (SURVEY.md §8d's sum of footprints) counts a pixel once
+    per RoI that covers it and is only an upper bound on it."""
+    r = rois[rois[:, 0] >= 0]
+    if len(r) == 0:
+        return 0
+    nb = int(r[:, 0].max()) + 1
+    w, h = r[:, 3] - r[:, 1], r[:, 4] - r[:, 2]
+    scale = np.sqrt(w * h)
+    lvl = np.clip(np.floor(np.log2(scale / finest + 1e-6)), 0, len(sizes) - 1).astype(int)
+    tot = 0
+    for l, (H, W) in enumerate(sizes):
+        s = np.float32(1.0 / STRIDES[l])
+        bm = np.zeros((nb, H, W), dtype=bool)
+        for q in r[lvl == l]:
+            x0, y0 = q[1] * s - 0.5, q[2] * s - 0.5
+            x1, y1 = q[3] * s - 0.5, q[4] * s - 0.5
+            if x1 < -1 or y1 < -1 or x0 > W or y0 > H:
+                continue
+            xa, xb = max(0, int(np.floor(max(x0, 0)))), min(W - 1, int(np.floor(min(max(x1, 0), W))) + 1)
+            ya, yb = max(0, int(np.floor(max(y0, 0)))), min(H - 1, int(np.floor(min(max(y1, 0), H))) + 1)
+            bm[int(q[0]), ya:yb + 1, xa:xb + 1] = True
+        tot += int(bm.sum()) * channels * 4
+    return tot
+
+
 # ----------------------------------------------------------------------------
 # secondary workloads (not the headline line; same JSON contract)
 # ----------------------------------------------------------------------------
@@ -219,6 +252,29 @@ def _dev_time(fn, reps, dev, flush_mb=256):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+
+def _graph_time(fn, reps, dev, flush_mb=256):
+    """mean device ms of fn() captured alone in a CUDA graph (no host launch gaps in the
+    number), L2 flushed before every repetition"""
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    flush = torch.empty(flush_mb << 20, dtype=torch.uint8, device=dev)
+    g.replay()
+    evs = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
         b.record()
         evs.append((a, b))
     torch.cuda.synchronize()
@@ -262,23 +318,23 @@ def _timed_steps(fn, K, W, world, dist, dev):
     return ms
 
 
-def bench_train(args, rank, world, local_rank):
-    """configs[2]: R-CNN training step on B200-generated proposals: train-cfg
-    proposal generation (nms_pre 4000 / 2000 per image), assign + sample (host
-    logic of the reference), RoIAlign forward, 2-fc head,
-    boost loss, backward (head GEMMs on cuBLAS, RoIAlign backward gather),
-    NCCL all-reduce of the head gradients + one fused scalar all-reduce."""
+def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20, W=3,
+                 with_stages=True):
+    """configs[2]: R-CNN training step on B200-generated proposals: train-cfg proposal
+    generation (nms_pre 4000 / 2000 per image), fused assign + sample + targets + prior
+    (2 launches + the reference's CPU randperm), RoIAlign forward ((R,7,7,C) hand-off), 2-fc
+    head, boost loss, backward (head GEMMs on cuBLAS, TMA-staged RoIAlign backward gather),
+    then the reference's collectives: NCCL all-reduce of the head gradients (one flat bucket,
+    mmdet/apis/train.py:75-83) + ONE fused scalar all-reduce for the logged losses
+    (detectors/base.py:201-207).  Returns the record (rank 0) or None."""
     from boosting_rcnn_b200 import _lib, configs, ops
     from boosting_rcnn_b200 import dist as bdist
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device('cuda', local_rank)
-    torch.cuda.set_device(dev)
-    dist = _dist_setup(world, dev)
     lib = _lib.load()
-    geom = configs.IMAGE_GEOMETRY[args.cfg]
-    B = args.batch
+    geom = configs.IMAGE_GEOMETRY[cfg_name]
     torch.manual_seed(0)
-    rpn_head, roi_head, model = configs.build_hot_path(args.cfg, train=True)
+    rpn_head, roi_head, model = configs.build_hot_path(cfg_name, train=True)
     rpn_head, roi_head = rpn_head.to(dev).eval(), roi_head.to(dev).train()
     A, C = rpn_head.num_anchors, roi_head.bbox_roi_extractor.out_channels
     NC = roi_head.bbox_head.num_classes
@@ -300,9 +356,11 @@ def bench_train(args, rank, world, local_rank):
         labels.append(torch.from_numpy(rng.randint(0, NC, n)).to(dev))
     prop_cfg = model['train_cfg']['rpn_proposal']
     params = [p for p in roi_head.parameters() if p.requires_grad]
+    n_grad = sum(p.numel() for p in params)
     scal = {}
+    comm_events = []
 
-    def step():
+    def step(comm=True):
         for p in params:
             p.grad = None
         for f in feats:
@@ -311,7 +369,9 @@ def bench_train(args, rank, world, local_rank):
             plist = rpn_head.get_bboxes_padded(cls, box, iou, metas, cfg=prop_cfg)
         losses = roi_head.forward_train(feats, metas, plist, gts, labels)
         (losses['loss_cls'] + losses['loss_bbox']).backward()
-        if world > 1:
+        if world > 1 and comm:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             # one flat bucket (the head has ~14M parameters): all-reduce, average, scatter back
             flat = torch.cat([p.grad.reshape(-1) for p in params])
             dist.all_reduce(flat)
@@ -321,65 +381,102 @@ def bench_train(args, rank, world, local_rank):
                 n = p.numel()
                 p.grad.copy_(flat[off:off + n].view_as(p.grad))
                 off += n
-        scal.update(bdist.fused_scalar_allreduce({k: v.detach() for k, v in losses.items()}))
+            scal.update(bdist.fused_scalar_allreduce({k: v.detach() for k, v in losses.items()}))
+            e1.record()
+            comm_events.append((e0, e1))
+        else:
+            scal.update({k: v.detach() for k, v in losses.items()})
 
-    K, W = args.steps, max(args.warmup, 3)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = lib.brcnn_launch_count()
     ms = _timed_steps(step, K, W, world, dist, dev)
     launches = (lib.brcnn_launch_count() - l0) * K // (K + W)
-    clocks = sampler.stop() if sampler else None
-    out = None
-    if rank == 0:
+    ms_comm = 0.0
+    if comm_events:
+        torch.cuda.synchronize()
+        ms_comm = float(np.mean([a.elapsed_time(b) for a, b in comm_events[-K:]]))
+        if dist:
+            t = torch.tensor([ms_comm], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_comm = float(t.item())
+    ms_nocomm = _timed_steps(lambda: step(False), K, 1, world, dist, dev) if world > 1 else ms
+    if rank != 0:
+        return None
+    rec = {
+        'workload': f'boosting_rcnn {cfg_name} R-CNN training step, {B} synthetic 1333x800 '
+                    f'images per GPU, 512 sampled RoIs/img (BASELINE configs[2])',
+        'value': B * world * K / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world,
+        'images_per_gpu': B, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
+        'ms_allreduce': ms_comm, 'ms_per_step_no_comm': ms_nocomm / K,
+        'allreduce_bytes': n_grad * 4,
+        'collectives': ('none (1 GPU)' if world == 1 else
+                        'NCCL all-reduce of the head gradients (one flat fp32 bucket) + one fused '
+                        'scalar all-reduce of the logged losses'),
+        'gpu_launches_per_step': int(launches // max(K, 1)),
+        'launch_mode': 'eager (one host sync per step: the reference\'s CPU randperm)',
+        'losses': {k: float(v) for k, v in scal.items()},
+    }
+    if with_stages:
         peak, peak_src = _peak()
-        # stage device times on fixed sampled RoIs
         with torch.no_grad():
             plist = rpn_head.get_bboxes(cls, box, iou, metas, cfg=prop_cfg)
         rois = torch.cat([torch.cat([p.new_full((min(512, p.size(0)), 1), float(b)),
                                      p[:512, :4]], 1) for b, p in enumerate(plist)])
         R = rois.size(0)
         scales = [1.0 / s_ for s_ in STRIDES]
-        nhwc = [f.detach().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True)
-                for f in feats]
-        rf = ops.roi_extract(nhwc, rois, scales, 7)
-        go = torch.randn_like(rf)
+        nhwc = [f.detach().contiguous(memory_format=torch.channels_last) for f in feats]
+        sizes_hw = [tuple(f.shape[-2:]) for f in nhwc]
+        rp = ops.make_roi_params(B, C, sizes_hw, scales, 7)
+        go = torch.randn(R, C, 7, 7, device=dev).contiguous(memory_format=torch.channels_last)
         cs = torch.randn(R, NC + 1, device=dev)
         bp = torch.randn(R, 4 * NC, device=dev)
         lab = torch.randint(0, NC + 1, (R,), device=dev)
         lw = torch.ones(R, device=dev)
         pr = torch.rand(R, device=dev)
         bt, bw = torch.randn(R, 4, device=dev), (lab < NC).float()[:, None].expand(R, 4).contiguous()
-        st = {
-            'rpn_get_bboxes_train_cfg': _dev_time(
-                lambda: rpn_head.get_bboxes_padded(cls, box, iou, metas, cfg=prop_cfg), 10, dev),
-            'roi_align_fwd': _dev_time(lambda: ops.roi_extract(nhwc, rois, scales, 7), 10, dev),
-            'roi_align_bwd': _dev_time(
-                lambda: torch.autograd.grad(ops.roi_extract(nhwc, rois, scales, 7), nhwc, go), 10, dev),
-            'boost_loss_fwd_bwd': _dev_time(
-                lambda: ops.boost_loss(cs, bp, lab, lw, pr, bt, bw, NC, False, 0.5, 0.0, 2.0, 2.0,
-                                       False), 10, dev),
-        }
-        st['roi_align_bwd'] -= st['roi_align_fwd']
+        with torch.no_grad():
+            st = {
+                'rpn_get_bboxes_train_cfg': _graph_time(
+                    lambda: rpn_head.get_bboxes_padded(cls, box, iou, metas, cfg=prop_cfg), 10, dev),
+                'roi_align_fwd': _graph_time(
+                    lambda: ops.roi_extract(nhwc, rois, scales, 7, channels_last_out=True), 10, dev),
+                'roi_align_bwd': _graph_time(lambda: ops.roi_extract_backward(rp, go, rois), 10, dev),
+                'boost_loss_fwd_bwd': _graph_time(
+                    lambda: ops.boost_loss(cs, bp, lab, lw, pr, bt, bw, NC, False, 0.5, 0.0, 2.0,
+                                           2.0, False), 10, dev),
+            }
         feat_bytes = sum(f.numel() * 4 for f in feats)
         bwd_bytes = R * C * 49 * 4 + feat_bytes
         ach = bwd_bytes / (st['roi_align_bwd'] * 1e-3) / 1e9
-        roof = dict(kernel='roi_bwd_gather2_kernel (+ prep, grad_out transpose)', bound='hbm',
-                    achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,
-                    peak_source=peak_src, algorithmic_bytes_per_launch=bwd_bytes,
-                    ms_per_launch=st['roi_align_bwd'])
+        rec['stages_ms'] = st
+        rec['roofline'] = dict(kernel='roi_bwd_gather3_kernel (+ roi_bwd_prep_kernel)', bound='hbm',
+                               achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,
+                               peak_source=peak_src, algorithmic_bytes_per_launch=bwd_bytes,
+                               ms_per_launch=st['roi_align_bwd'],
+                               note='bytes = grad_out read once + every grad map written once')
+    return rec
+
+
+def bench_train(args, rank, world, local_rank):
+    """`--mode train`: the configs[2] record as the top-level JSON line."""
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    dist = _dist_setup(world, dev)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    rec = train_record(args, rank, world, local_rank, dist, cfg_name=args.cfg, B=args.batch,
+                       K=args.steps, W=max(args.warmup, 3))
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
         out = {
-            'metric': 'RoI-path training images/s @1333x800', 'value': B * world * K / (ms * 1e-3),
-            'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic',
-            'config': dict(workload=f'boosting_rcnn {args.cfg} R-CNN training step, {B} synthetic '
-                                    f'1333x800 images per GPU, 512 sampled RoIs/img',
-                           images_per_gpu=B, rpn_proposal=prop_cfg, rcnn=model['train_cfg']['rcnn'],
-                           parallelism=f'image-sharded x{world}; NCCL all-reduce of head grads + '
-                                       f'one fused scalar all-reduce',
-                           note='eager; assign+sample+targets = 2 kernels + the reference CPU randperm (one sync)'),
-            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'stages_ms': st,
-            'losses': {k: float(v) for k, v in scal.items()},
+            'metric': 'RoI-path training images/s @1333x800', 'value': rec['value'],
+            'unit': 'images/s', 'n_gpus': world, 'steps': rec['steps'], 'warmup': rec['warmup'],
+            'ms_per_step': rec['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': dict(workload=rec['workload'], images_per_gpu=rec['images_per_gpu'],
+                           parallelism=f'image-sharded x{world}; ' + rec['collectives']),
+            'gpu_launches': rec['gpu_launches_per_step'] * rec['steps'], 'clocks': clocks,
+            'roofline': rec.get('roofline'), 'stages_ms': rec.get('stages_ms'),
+            'ms_allreduce': rec['ms_allreduce'], 'ms_per_step_no_comm': rec['ms_per_step_no_comm'],
+            'losses': rec['losses'],
         }
         print(json.dumps(out))
     if dist:
@@ -628,6 +725,30 @@ def main():
     # headline: throughput with two batches in flight (one captured graph per stream);
     # --no-graph: the eager single-stream number
     ms = ms_dual if ms_dual is not None else ms_single
+    # the same K-step block four more times: median of 5 (variance of a 45 ms timed region)
+    head_fn, head_drain = (dual.step, dual.drain) if ms_dual is not None else (step, None)
+    blocks = sorted([ms] + [timed(head_fn, K, 0, drain=head_drain) for _ in range(4)])
+    ms_median = blocks[2]
+
+    # ---- strong scaling (BASELINE configs[1] as written: ONE batch of 16 images sharded over
+    # the GPUs, SURVEY §8e 16/8/4/2 per GPU): rank r owns images shard_range(16, r, world)
+    strong = None
+    if not args.no_graph:
+        from boosting_rcnn_b200.dist import shard_range
+        tot = args.strong_total
+        lo, hi = shard_range(tot, rank, world)
+        lo, hi = min(lo, B), min(hi, B)
+        nb = hi - lo
+        g_strong = None
+        if nb > 0:
+            sl = lambda ts: [t[lo:hi].contiguous() for t in ts]
+            g_strong = HotPathGraph(rpn_head, roi_head, metas[lo:hi], sl(d_feats), sl(d_cls),
+                                    sl(d_box), sl(d_iou), rcnn_test_cfg=test_rcnn, rescale=True)
+        ms_strong = timed(g_strong.replay if g_strong is not None else (lambda: None), K, W)
+        strong = dict(images_total=tot, images_per_gpu=nb, value=tot * K / (ms_strong * 1e-3),
+                      unit='images/s', ms_per_step=ms_strong / K, scaling='strong',
+                      note='one CUDA graph per step on one stream, inputs resident; no data-path '
+                           'collective (detections stay on their rank)')
     verified = None
     if ms_dual is not None:
         # the two in-flight graphs must reproduce the single-stream detections bit for bit
@@ -654,14 +775,15 @@ def main():
             scales = [1.0 / s for s in STRIDES]
             nhwc = ops.pyramid_to_nhwc(d_feats)
             feats_cl = [t.permute(0, 3, 1, 2) for t in nhwc]
-            rf = ops.roi_extract(feats_cl, rois, scales, 7)
+            rf = ops.roi_extract(feats_cl, rois, scales, 7, channels_last_out=True)
             cs, bp = roi_head.bbox_head(rf)
             hw, sf = roi_head._img_consts(metas, dev)
             rp = roi_head.bbox_head.rcnn_params(B, props.boxes.size(1), ConfigDict(test_rcnn), True, True)
             stages = {
                 'rpn_get_bboxes': lambda: rpn_head.get_bboxes_padded(d_cls, d_box, d_iou, metas),
                 'nchw_to_nhwc_x5': lambda: ops.pyramid_to_nhwc(d_feats),
-                'roi_align_fwd': lambda: ops.roi_extract(feats_cl, rois, scales, 7),
+                'roi_align_fwd': lambda: ops.roi_extract(feats_cl, rois, scales, 7,
+                                                         channels_last_out=True),
                 'fc_head_cublas': lambda: roi_head.bbox_head(rf),
                 'rcnn_get_bboxes': lambda: ops.rcnn_get_bboxes(rp, rois, prior, props.num, cs, bp,
                                                                hw, sf),
@@ -692,39 +814,81 @@ def main():
                 torch.cuda.synchronize()
                 stage_ms[name] = float(np.mean([a.elapsed_time(b) for a, b in evs]))
             del flush
-        peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
-        else:
-            peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+        peak, peak_src = _peak()
         rois_h = rois.cpu().numpy()
         n_live = int((rois_h[:, 0] >= 0).sum())
         feat_bytes = sum(f.numel() * 4 for f in d_feats)
         out_bytes = rois_h.shape[0] * C * 49 * 4
         fp = roi_footprint_bytes(rois_h, sizes, C)
+        un = roi_union_bytes(rois_h, sizes, C)
         # ncu dram__bytes_read+write per launch of the same command (profiles/)
         traffic = {}
         tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(f'{args.cfg}_b{B}', {})
-        # algorithmic bytes per launch (DESIGN.md §4 / SURVEY.md §8d)
+        # algorithmic bytes per launch: output bytes + the UNION of the footprint pixels per
+        # (image, level) (what must cross HBM at least once).  SURVEY §8d's formula
+        # (sum of footprints capped at the map bytes) is reported beside it.
         kern = {
-            'roi_align_fwd_tma_kernel': dict(bytes=out_bytes + min(fp, feat_bytes),
-                                         ms=stage_ms['roi_align_fwd'], live_rois=n_live,
-                                         rois=int(rois_h.shape[0])),
+            'roi_align_fwd3_kernel': dict(bytes=out_bytes + un, ms=stage_ms['roi_align_fwd'],
+                                          live_rois=n_live, rois=int(rois_h.shape[0]),
+                                          union_feature_bytes=un,
+                                          bytes_survey_formula=out_bytes + min(fp, feat_bytes)),
             'transpose_multi_kernel': dict(bytes=2 * feat_bytes, ms=stage_ms['nchw_to_nhwc_x5']),
         }
         for k, v in kern.items():
             v['achieved'] = v['bytes'] / (v['ms'] * 1e-3) / 1e9
             v['frac'] = v['achieved'] / peak
             v['traffic'] = traffic.get(k)
+            if 'bytes_survey_formula' in v:
+                v['frac_survey_formula'] = v['bytes_survey_formula'] / (v['ms'] * 1e-3) / 1e9 / peak
         # dominant kernel = largest share of OUR kernel time in the step
         dom = max(kern, key=lambda k: kern[k]['ms'])
         d = kern[dom]
         roof = dict(kernel=dom, bound='hbm', achieved=d['achieved'], peak=peak, unit='GB/s',
                     frac=d['frac'], traffic=d['traffic'], peak_source=peak_src,
                     algorithmic_bytes_per_launch=d['bytes'], ms_per_launch=d['ms'],
+                    frac_survey_formula=d.get('frac_survey_formula'),
+                    bytes_definition='output bytes + union of footprint pixels per (image, level)',
                     kernels=kern)
+
+    # ---- own-kernel stage times at the strong-scaling per-GPU batch (rank 0's shard) ----
+    if rank == 0 and strong is not None and strong['images_per_gpu'] not in (0, B):
+        nb = strong['images_per_gpu']
+        with torch.no_grad():
+            sl = lambda ts: [t[:nb].contiguous() for t in ts]
+            s_feats, s_cls, s_box, s_iou = sl(d_feats), sl(d_cls), sl(d_box), sl(d_iou)
+            s_metas = metas[:nb]
+            sprops = rpn_head.get_bboxes_padded(s_cls, s_box, s_iou, s_metas)
+            srois, sprior = ops.bbox2roi_padded(sprops.boxes, sprops.num)
+            s_cl = [t.permute(0, 3, 1, 2) for t in ops.pyramid_to_nhwc(s_feats)]
+            srf = ops.roi_extract(s_cl, srois, scales, 7, channels_last_out=True)
+            scs, sbp = roi_head.bbox_head(srf)
+            shw, ssf = roi_head._img_consts(s_metas, dev)
+            srp = roi_head.bbox_head.rcnn_params(nb, sprops.boxes.size(1), ConfigDict(test_rcnn),
+                                                 True, True)
+            strong['stages_ms'] = {
+                'rpn_get_bboxes': _graph_time(
+                    lambda: rpn_head.get_bboxes_padded(s_cls, s_box, s_iou, s_metas), 10, dev),
+                'nchw_to_nhwc_x5': _graph_time(lambda: ops.pyramid_to_nhwc(s_feats), 10, dev),
+                'roi_align_fwd': _graph_time(
+                    lambda: ops.roi_extract(s_cl, srois, scales, 7, channels_last_out=True), 10, dev),
+                'fc_head_cublas': _graph_time(lambda: roi_head.bbox_head(srf), 10, dev),
+                'rcnn_get_bboxes': _graph_time(
+                    lambda: ops.rcnn_get_bboxes(srp, srois, sprior, sprops.num, scs, sbp, shw, ssf),
+                    10, dev),
+            }
+            st = strong['stages_ms']
+            strong['own_kernels_ms'] = sum(v for k, v in st.items() if k != 'fc_head_cublas')
+            strong['limiter'] = max(st, key=st.get)
+
+    # ---- configs[2] training step at this N (gradient all-reduce over NVLink when N > 1) ----
+    train = None
+    if not args.no_train_record:
+        import torch.distributed as tdist
+        train = train_record(args, rank, world, local_rank, tdist if world > 1 else None,
+                             cfg_name='coco', B=2, K=min(max(K, 10), 20), W=3,
+                             with_stages=(rank == 0))
 
     # ------------------------------------------------------------ CPU baseline
     cpu = None
@@ -759,6 +923,8 @@ def main():
             'value_single_stream': B * world * K / (ms_single * 1e-3),
             'two_stream_outputs_bit_identical': verified,
             'ms_per_step_single_stream': ms_single / K,
+            'value_median_of_5_blocks': B * world * K / (ms_median * 1e-3),
+            'strong_scaling': strong, 'train': train,
             'value_single_stream_tf32_head_informational': (B * world * K / (ms_tf32 * 1e-3)) if ms_tf32 else None,
             'e2e': {'value': B * world * k_e2e / (ms_e2e * 1e-3), 'unit': 'images/s',
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,

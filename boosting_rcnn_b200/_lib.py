@@ -46,7 +46,7 @@ class RoiParams(Structure):
         ('spatial_scale', c_float * MAX_LEVELS),
         ('pooled_h', c_int32), ('pooled_w', c_int32),
         ('sampling_ratio', c_int32), ('aligned', c_int32),
-        ('finest_scale', c_float),
+        ('finest_scale', c_float), ('out_layout', c_int32),
     ]
 
 

@@ -78,6 +78,18 @@ class ProbConvFCBBoxHead(nn.Module):
         self.fc_cls = nn.Linear(self.cls_last_dim, num_classes + 1)
         self.fc_reg = nn.Linear(self.reg_last_dim, 4 if reg_class_agnostic else 4 * num_classes)
         self.init_weights()
+        # RoI-feature hand-off: when the first layer after the flatten is
+        # shared_fcs.0, its weight lives with columns in (ph, pw, c) order so that the
+        # channels-last RoI features ((R,7,7,C) storage) feed it as a free view and the
+        # gradient comes back bin-major for the RoIAlign backward.  state_dict() / load
+        # convert to / from the reference's (c, ph, pw) order (convfc_bbox_head.py:164), so
+        # checkpoints are interchangeable.
+        self.fc1_hwc = (num_shared_fcs > 0 and not with_avg_pool and self.roi_feat_area > 1)
+        if self.fc1_hwc:
+            with torch.no_grad():
+                self.shared_fcs[0].weight.copy_(self._fc1_to_hwc(self.shared_fcs[0].weight))
+            self._register_state_dict_hook(ProbConvFCBBoxHead._state_dict_hook)
+            self._register_load_state_dict_pre_hook(self._load_state_dict_pre_hook)
 
     def _branch(self, n_convs, n_fcs, in_channels, is_shared=False):
         last = in_channels
@@ -98,6 +110,36 @@ class ProbConvFCBBoxHead(nn.Module):
             last = self.fc_out_channels
         return convs, fcs, last
 
+    # ---- fc1 column order: reference (c, ph, pw) <-> stored (ph, pw, c) ----
+    def _fc1_channels(self):
+        return self.shared_fcs[0].in_features // self.roi_feat_area
+
+    def _fc1_to_hwc(self, w):
+        o = w.size(0)
+        return w.reshape(o, self._fc1_channels(), self.roi_feat_area).permute(0, 2, 1).reshape(o, -1)
+
+    def _fc1_to_ref(self, w):
+        o = w.size(0)
+        return w.reshape(o, self.roi_feat_area, self._fc1_channels()).permute(0, 2, 1).reshape(o, -1)
+
+    @staticmethod
+    def _state_dict_hook(module, state_dict, prefix, local_metadata):
+        key = prefix + 'shared_fcs.0.weight'
+        if key in state_dict:
+            state_dict[key] = module._fc1_to_ref(state_dict[key]).contiguous()
+
+    def _load_state_dict_pre_hook(self, state_dict, prefix, *args):
+        key = prefix + 'shared_fcs.0.weight'
+        if key in state_dict and state_dict[key].dim() == 2 and \
+                state_dict[key].size(1) == self.shared_fcs[0].in_features:
+            state_dict[key] = self._fc1_to_hwc(state_dict[key]).contiguous()
+
+    def _flatten(self, x):
+        """``x.flatten(1)`` of the reference (:164) against the stored column order."""
+        if self.fc1_hwc and x.dim() == 4:
+            return x.permute(0, 2, 3, 1).reshape(x.size(0), -1)   # a view for channels_last x
+        return x.flatten(1)
+
     def init_weights(self):
         # bbox_head.py:89-101 + convfc_bbox_head.py:97-107
         for group in (self.shared_fcs, self.cls_fcs, self.reg_fcs):
@@ -115,7 +157,7 @@ class ProbConvFCBBoxHead(nn.Module):
         if self.num_shared_fcs > 0:
             if self.with_avg_pool:
                 x = self.avg_pool(x)
-            x = x.flatten(1)
+            x = self._flatten(x)
             for fc in self.shared_fcs:
                 x = self.relu(fc(x))
         x_cls, x_reg = x, x

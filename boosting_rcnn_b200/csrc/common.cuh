@@ -27,6 +27,9 @@
 
 namespace brcnn {
 
+// cached cudaFuncSetAttribute(MaxDynamicSharedMemorySize) — defined in libbrcnn.cu
+cudaError_t ensure_dyn_smem(const void* fn, size_t bytes, bool max_carveout = false);
+
 // ---------------------------------------------------------------------------
 // pinned_expf: Cephes-style single precision exp, written with explicit
 // fmaf so that gcc (-ffp-contract=off) and nvcc (-fmad=false) produce the same

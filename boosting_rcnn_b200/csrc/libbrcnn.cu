@@ -5,6 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "../../include/brcnn.h"
 #include "boost_loss.cuh"
@@ -15,6 +18,8 @@
 #include "roi_align.cuh"
 #include "roi_align_bwd.cuh"
 #include "roi_align_bwd2.cuh"
+#include "roi_align_bwd3.cuh"
+#include "roi_align_fwd3.cuh"
 #include "roi_align_tma.cuh"
 #include "rpn.cuh"
 #include "rpn_nms.cuh"
@@ -24,6 +29,44 @@ static std::atomic<int64_t> g_launches{0};
 int64_t g_launch_count_add(int n) { return g_launches.fetch_add(n) + n; }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// cudaFuncSetAttribute is issued once per (kernel, device): the largest dynamic
+// shared-memory size requested so far is remembered, later calls with a size that
+// already fits are free.  (Thread-safe; the only process-wide state of the library
+// besides the launch counter.)
+static std::mutex g_attr_mu;
+static std::map<std::pair<const void*, int>, int> g_attr_smem;
+static std::map<int, int> g_sm_count;
+cudaError_t ensure_dyn_smem(const void* fn, size_t bytes, bool max_carveout) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(g_attr_mu);
+  const auto key = std::make_pair(fn, dev);
+  const auto it = g_attr_smem.find(key);
+  if (it != g_attr_smem.end() && it->second >= (int)bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  if (max_carveout) {
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+  }
+  g_attr_smem[key] = (int)bytes;
+  return cudaSuccess;
+}
+static int sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::lock_guard<std::mutex> lk(g_attr_mu);
+  const auto it = g_sm_count.find(dev);
+  if (it != g_sm_count.end()) return it->second;
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    n = 148;
+  g_sm_count[dev] = n;
+  return n;
+}
 static inline bool misaligned16(const void* p) { return ((uintptr_t)p & 15) != 0; }
 static inline int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
@@ -386,8 +429,7 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
     BRCNN_CUDA_CHECK_LAST();
   }
   if (smem > 48 * 1024) {
-    e = cudaFuncSetAttribute(rpn_topk_decode_kernel,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dyn_smem((const void*)rpn_topk_decode_kernel, smem);
     if (e != cudaSuccess) return (int)e;
   }
   {
@@ -436,8 +478,7 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
       long long* dbg = dbg_buf;
       if (cs > 1) {
         if (lay.total > 32 * 1024) {
-          e = cudaFuncSetAttribute(rpn_nms_image_kernel<RNI_CLUSTER>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+          e = ensure_dyn_smem((const void*)rpn_nms_image_kernel<RNI_CLUSTER>, lay.total);
           if (e != cudaSuccess) return (int)e;
         }
         e = cudaLaunchKernelEx(&cfg, rpn_nms_image_kernel<RNI_CLUSTER>,
@@ -448,8 +489,7 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
                                (const int32_t*)nullptr, 0.0f, (int64_t*)nullptr);
       } else {
         if (lay.total > 32 * 1024) {
-          e = cudaFuncSetAttribute(rpn_nms_image_kernel<1>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+          e = ensure_dyn_smem((const void*)rpn_nms_image_kernel<1>, lay.total);
           if (e != cudaSuccess) return (int)e;
         }
         e = cudaLaunchKernelEx(&cfg, rpn_nms_image_kernel<1>,
@@ -583,8 +623,7 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
       g_launch_count_add(1);
       BRCNN_CUDA_CHECK_LAST();
       if (lay.total > 32 * 1024) {
-        e = cudaFuncSetAttribute(rpn_nms_image_kernel<RNI_CLUSTER>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+        e = ensure_dyn_smem((const void*)rpn_nms_image_kernel<RNI_CLUSTER>, lay.total);
         if (e != cudaSuccess) return (int)e;
       }
       cudaLaunchConfig_t cfg;
@@ -641,8 +680,7 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
       BRCNN_CUDA_CHECK_LAST();
       const size_t smem = (size_t)keep_pad * 20;
       if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(nms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem);
+        e = ensure_dyn_smem((const void*)nms_fused_kernel, smem);
         if (e != cudaSuccess) return (int)e;
       }
       u64* kept_key = (u64*)(ws + w.mask);   // K u64, the bitmask area is unused on this path
@@ -653,8 +691,7 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
       BRCNN_CUDA_CHECK_LAST();
       const size_t sm = (size_t)np2 * 8;
       if (sm > 32 * 1024) {
-        e = cudaFuncSetAttribute(nms_merge_sort_kernel<OpMergeEpilogue>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        e = ensure_dyn_smem((const void*)nms_merge_sort_kernel<OpMergeEpilogue>, sm);
         if (e != cudaSuccess) return (int)e;
       }
       OpMergeEpilogue ep{keep};
@@ -719,7 +756,7 @@ int brcnn_bbox2roi_padded(const float* proposals, const int32_t* num_proposals,
 static int roi_args_from(const brcnn_roi_params* p, RoiArgs* a) {
   if (!p || p->batch <= 0 || p->channels <= 0 || (p->channels & 3) ||
       p->num_levels <= 0 || p->num_levels > BRCNN_MAX_LEVELS || p->pooled_h <= 0 ||
-      p->pooled_w <= 0)
+      p->pooled_w <= 0 || (p->out_layout != 0 && p->out_layout != 1))
     return BRCNN_ERR_ARG;
   memset(a, 0, sizeof(*a));
   a->B = p->batch; a->C = p->channels; a->L = p->num_levels;
@@ -754,6 +791,39 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
     if (a.H[l] > a.max_h) a.max_h = a.H[l];
     if (a.W[l] > a.max_w) a.max_w = a.W[l];
   }
+  // ---- v3: persistent cross-RoI pipelined kernel, (R,ph,pw,C) output (roi_align_fwd3.cuh) ----
+  if (p->out_layout == 1) {
+    if (a.PH > RT_P || a.PW > RT_P || misaligned16(out)) return BRCNN_ERR_UNSUPPORTED;
+    const int chunk = a.C < 4 * RT_SLAB_Q ? a.C : 4 * RT_SLAB_Q;
+    Roi3Smem lay;
+    lay.tab_floats = (R3_DESC + a.max_h * 8 + 8 * a.max_w + 31) & ~31;
+    const size_t tables = (size_t)2 * lay.tab_floats * 4;
+    const size_t budget = 110 * 1024;           // two CTAs per SM
+    // a slot holds up to 16 footprint pixels of the channel chunk (wider rows: x-chunk passes)
+    static const int slot_px = [] {
+      const char* e = getenv("BRCNN_R3_SLOT_PX");   // tuning knob (developer)
+      const int v = e ? atoi(e) : 0;
+      return v >= 4 && v <= 64 ? v : 16;
+    }();
+    lay.slot_bytes = (slot_px * chunk * 4 + 127) & ~127;
+    if (tables + (size_t)3 * 128 >= budget) return BRCNN_ERR_UNSUPPORTED;
+    while ((size_t)3 * lay.slot_bytes + tables > budget && lay.slot_bytes > 128)
+      lay.slot_bytes = ((lay.slot_bytes / 2) + 127) & ~127;
+    if (lay.slot_bytes < chunk * 4 || (size_t)3 * lay.slot_bytes + tables > budget)
+      return BRCNN_ERR_UNSUPPORTED;
+    lay.ns = (int)((budget - tables) / lay.slot_bytes);
+    if (lay.ns > R3_MAX_STAGES) lay.ns = R3_MAX_STAGES;
+    lay.total = (int)((size_t)lay.ns * lay.slot_bytes + tables);
+    a.chunk_c = chunk;
+    cudaError_t e = ensure_dyn_smem((const void*)roi_align_fwd3_kernel, lay.total, true);
+    if (e != cudaSuccess) return (int)e;
+    const int slots = 2 * sm_count();
+    dim3 grid(R < slots ? R : slots, (a.C + chunk - 1) / chunk);
+    roi_align_fwd3_kernel<<<grid, RT_THREADS, lay.total, stream>>>(a, rois, R, out, roi_levels, lay);
+    g_launch_count_add(1);
+    BRCNN_CUDA_CHECK_LAST();
+    return BRCNN_OK;
+  }
   // ---- v2: TMA row-streaming kernel (roi_align_tma.cuh) ----
   {
     static const bool force_v1 = [] {
@@ -771,13 +841,7 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
     if (!force_v1 && a.PH <= RT_P && a.PW <= RT_P && ring >= need && !misaligned16(out)) {
       a.chunk_c = chunk;
       const size_t smem = ring + tables;
-      cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_tma_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(roi_align_fwd_tma_kernel,
-                               cudaFuncAttributePreferredSharedMemoryCarveout,
-                               cudaSharedmemCarveoutMaxShared);
+      cudaError_t e = ensure_dyn_smem((const void*)roi_align_fwd_tma_kernel, smem, true);
       if (e != cudaSuccess) return (int)e;
       dim3 grid(R, (a.C + chunk - 1) / chunk);
       roi_align_fwd_tma_kernel<<<grid, RT_THREADS, smem, stream>>>(a, rois, R, out, roi_levels,
@@ -801,18 +865,12 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
   dim3 grid(R, nchunks);
   cudaError_t e;
   if (a.PW <= 7) {
-    e = cudaFuncSetAttribute(roi_align_fwd_kernel<7>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
     // 3 CTAs x ~58 KB per SM: ask for the large shared-memory carveout
-    e = cudaFuncSetAttribute(roi_align_fwd_kernel<7>,
-                             cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
+    e = ensure_dyn_smem((const void*)roi_align_fwd_kernel<7>, smem, true);
     if (e != cudaSuccess) return (int)e;
     roi_align_fwd_kernel<7><<<grid, ROI_THREADS, smem, stream>>>(a, rois, R, out, roi_levels);
   } else {
-    e = cudaFuncSetAttribute(roi_align_fwd_kernel<ROI_MAXP>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dyn_smem((const void*)roi_align_fwd_kernel<ROI_MAXP>, smem);
     if (e != cudaSuccess) return (int)e;
     roi_align_fwd_kernel<ROI_MAXP><<<grid, ROI_THREADS, smem, stream>>>(a, rois, R, out,
                                                                          roi_levels);
@@ -822,24 +880,43 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
   return BRCNN_OK;
 }
 
-static bool roi_bwd_use_v2(const RoiArgs& a) {
-  static const bool force_v1 = [] {
+// 0 = v1 (pooled sizes > 7), 2 = v2 gather (BRCNN_ROI_BWD=v2), 3 = v3 TMA-staged gather
+static int roi_bwd_version(const RoiArgs& a, int R) {
+  static const int forced = [] {
     const char* e = getenv("BRCNN_ROI_BWD");
-    return e && e[0] == 'v' && e[1] == '1';
+    if (e && e[0] == 'v' && e[1] == '1') return 1;
+    if (e && e[0] == 'v' && e[1] == '2') return 2;
+    return 0;
   }();
-  return !force_v1 && a.PH <= B2_P && a.PW <= B2_P && (long long)a.B * a.L < 65535;
+  const bool small = a.PH <= B2_P && a.PW <= B2_P && (long long)a.B * a.L < 65535;
+  if (forced == 1 || !small) return 1;
+  // the (image, level) buckets of v3 hold R entries each
+  const bool buckets_ok = (size_t)a.B * a.L * (size_t)(R > 0 ? R : 1) * 20 <= ((size_t)256 << 20);
+  if (forced == 2 || !buckets_ok) return 2;
+  return 3;
 }
 
 size_t brcnn_roi_extract_backward_workspace_bytes(const brcnn_roi_params* p,
                                                   int32_t R) {
   RoiArgs a;
   if (roi_args_from(p, &a) || R < 0) return 0;
-  return roi_bwd_use_v2(a) ? roi_bwd2_ws(a, R).total : roi_bwd_ws(a, R).total;
+  const int v = roi_bwd_version(a, R);
+  if (v == 3) return roi_bwd3_ws(a, R, p->out_layout == 0).total;
+  return v == 2 ? roi_bwd2_ws(a, R).total : roi_bwd_ws(a, R).total;
 }
 
-static int roi_bwd2_launch(RoiArgs a, const float* grad_out, const float* rois, int R,
-                           float* const* grad_feats, void* workspace, size_t workspace_bytes,
-                           cudaStream_t stream) {
+// grad_out (R,C,nbins) -> gt (R,nbins,C)
+static int roi_bwd_transpose_grad(const float* grad_out, float* gt, int R, int C, int nbins,
+                                  cudaStream_t stream) {
+  const float* tin[1] = {grad_out};
+  float* tout[1] = {gt};
+  const int trows[1] = {C}, tcols[1] = {nbins};
+  return transpose_launch_multi(tin, tout, 1, R, trows, tcols, stream);
+}
+
+static int roi_bwd2_launch(RoiArgs a, const float* grad_out, int out_layout, const float* rois,
+                           int R, float* const* grad_feats, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream) {
   const RoiBwd2Ws w = roi_bwd2_ws(a, R);
   if (!workspace || workspace_bytes < w.total) return BRCNN_ERR_WORKSPACE;
   if (misaligned16(workspace)) return BRCNN_ERR_ARG;
@@ -866,21 +943,114 @@ static int roi_bwd2_launch(RoiArgs a, const float* grad_out, const float* rois, 
   RoiBwdRec* recs = (RoiBwdRec*)(ws + w.recs);
   unsigned short* keys = (unsigned short*)(ws + w.keys);
   float* tab = (float*)(ws + w.tab);
-  float* gt = (float*)(ws + w.gt);
+  const float* gt = grad_out;
   const int nbins = a.PH * a.PW;
   if (R > 0) {
-    roi_bwd_prep_kernel<<<R, 128, 0, stream>>>(ba.a, rois, R, ba.TR, recs, keys, tab);
+    RoiBwdBuckets nob;
+    memset(&nob, 0, sizeof(nob));
+    roi_bwd_prep_kernel<<<R, 128, 0, stream>>>(ba.a, rois, R, ba.TR, recs, keys, tab, nob);
     g_launch_count_add(1);
     BRCNN_CUDA_CHECK_LAST();
-    const float* tin[1] = {grad_out};
-    float* tout[1] = {gt};
-    const int trows[1] = {a.C}, tcols[1] = {nbins};
-    const int rc = transpose_launch_multi(tin, tout, 1, R, trows, tcols, stream);
-    if (rc) return rc;
+    if (out_layout == 0) {
+      if (misaligned16(grad_out)) return BRCNN_ERR_ARG;
+      const int rc = roi_bwd_transpose_grad(grad_out, (float*)(ws + w.gt), R, a.C, nbins, stream);
+      if (rc) return rc;
+      gt = (const float*)(ws + w.gt);
+    }
   }
   dim3 grid((unsigned)base, (a.C + B2_CCH - 1) / B2_CCH);
   if (grid.y > 65535) return BRCNN_ERR_UNSUPPORTED;
   roi_bwd_gather2_kernel<<<grid, B2_THREADS, 0, stream>>>(ba, recs, keys, R, tab, gt);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+static int roi_bwd3_launch(RoiArgs a, const float* grad_out, int out_layout, const float* rois,
+                           int R, float* const* grad_feats, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream) {
+  const RoiBwd3Ws w = roi_bwd3_ws(a, R, out_layout == 0);
+  if (!workspace || workspace_bytes < w.total) return BRCNN_ERR_WORKSPACE;
+  if (misaligned16(workspace) || (R > 0 && misaligned16(grad_out))) return BRCNN_ERR_ARG;
+  RoiBwd3Args ba;
+  memset(&ba, 0, sizeof(ba));
+  for (int l = 0; l < a.L; ++l) {
+    if (a.H[l] > a.max_h) a.max_h = a.H[l];
+    if (a.W[l] > a.max_w) a.max_w = a.W[l];
+  }
+  ba.a = a;
+  ba.TR = a.max_h + a.max_w;
+  ba.bucket_cap = R > 0 ? R : 1;
+  long long base = 0;
+  for (int l = a.L - 1; l >= 0; --l) {      // coarse levels first
+    if (!grad_feats[l] || misaligned16(grad_feats[l])) return BRCNN_ERR_ARG;
+    ba.grad[l] = grad_feats[l];
+    ba.tiles_x[l] = (a.W[l] + B3_TS - 1) / B3_TS;
+    ba.tiles_y[l] = (a.H[l] + B3_TS - 1) / B3_TS;
+    ba.tile_first[l] = (int)base;
+    base += (long long)ba.tiles_x[l] * ba.tiles_y[l] * a.B;
+    if (base > 0x7fffffffLL) return BRCNN_ERR_UNSUPPORTED;
+  }
+  char* ws = (char*)workspace;
+  RoiBwdRec* recs = (RoiBwdRec*)(ws + w.recs);
+  unsigned short* keys = (unsigned short*)(ws + w.keys);
+  float* tab = (float*)(ws + w.tab);
+  int32_t* bucket_cnt = (int32_t*)(ws + w.bucket_cnt);
+  int32_t* tile_cnt = (int32_t*)(ws + w.tile_cnt);
+  int32_t* bucket = (int32_t*)(ws + w.bucket);
+  RoiBwdRec* bucket_rec = (RoiBwdRec*)(ws + w.bucket_rec);
+  const float* gt = grad_out;
+  const int nbins = a.PH * a.PW;
+  cudaError_t e = cudaMemsetAsync(bucket_cnt, 0, w.zero_bytes, stream);
+  if (e != cudaSuccess) return (int)e;
+  if (R > 0) {
+    RoiBwdBuckets bk;
+    memset(&bk, 0, sizeof(bk));
+    bk.bucket = bucket; bk.bucket_rec = bucket_rec; bk.bucket_cnt = bucket_cnt;
+    bk.tile_cnt = tile_cnt; bk.tile_side = B3_TS;
+    for (int l = 0; l < a.L; ++l) {
+      bk.tiles_x[l] = ba.tiles_x[l]; bk.tiles_y[l] = ba.tiles_y[l];
+      bk.tile_first[l] = ba.tile_first[l];
+    }
+    roi_bwd_prep_kernel<<<R, 128, 0, stream>>>(ba.a, rois, R, ba.TR, recs, keys, tab, bk);
+    g_launch_count_add(1);
+    BRCNN_CUDA_CHECK_LAST();
+    if (out_layout == 0) {
+      const int rc = roi_bwd_transpose_grad(grad_out, (float*)(ws + w.gt), R, a.C, nbins, stream);
+      if (rc) return rc;
+      gt = (const float*)(ws + w.gt);
+    }
+  }
+  dim3 grid((unsigned)base, (a.C + B3_CS - 1) / B3_CS);
+  if (grid.y > 65535) return BRCNN_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)B3_NS * B3_STAGE;
+  e = ensure_dyn_smem((const void*)roi_bwd_gather3_kernel, smem, true);
+  if (e != cudaSuccess) return (int)e;
+#ifdef BRCNN_DEBUG_TIMING
+  // developer build only (-DBRCNN_DEBUG_TIMING): per-phase cycle sums of the gather CTAs
+  static unsigned long long* dbg = [] {
+    unsigned long long* pbuf = nullptr;
+    cudaMalloc(&pbuf, 16 * 8);
+    return pbuf;
+  }();
+  cudaMemsetAsync(dbg, 0, 16 * 8, stream);
+  roi_bwd_gather3_kernel<<<grid, B3_THREADS, smem, stream>>>(ba, bucket_rec, bucket, bucket_cnt,
+                                                            tile_cnt, R, tab, gt, dbg);
+  {
+    unsigned long long h[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int c = 0; c < 2; ++c)
+      if (h[c * 8])
+        fprintf(stderr, "[gather3 %s] ctas=%llu mean cycles: list=%llu first=%llu walk=%llu "
+                "store=%llu  rois/cta=%.2f\n", c ? "busy " : "empty", h[c * 8],
+                h[c * 8 + 1] / h[c * 8], h[c * 8 + 2] / h[c * 8], h[c * 8 + 3] / h[c * 8],
+                h[c * 8 + 4] / h[c * 8], (double)h[c * 8 + 5] / h[c * 8]);
+  }
+#else
+  roi_bwd_gather3_kernel<<<grid, B3_THREADS, smem, stream>>>(ba, bucket_rec, bucket, bucket_cnt,
+                                                            tile_cnt, R, tab, gt);
+#endif
   g_launch_count_add(1);
   BRCNN_CUDA_CHECK_LAST();
   return BRCNN_OK;
@@ -896,9 +1066,14 @@ int brcnn_roi_extract_backward(const brcnn_roi_params* p, const float* grad_out,
   if (rc) return rc;
   if (R < 0 || !grad_feats_nhwc_host) return BRCNN_ERR_ARG;
   if (R > 0 && (!grad_out || !rois)) return BRCNN_ERR_ARG;
-  if (roi_bwd_use_v2(a))
-    return roi_bwd2_launch(a, grad_out, rois, R, grad_feats_nhwc_host, workspace,
+  const int v = roi_bwd_version(a, R);
+  if (v == 3)
+    return roi_bwd3_launch(a, grad_out, p->out_layout, rois, R, grad_feats_nhwc_host, workspace,
                            workspace_bytes, stream);
+  if (v == 2)
+    return roi_bwd2_launch(a, grad_out, p->out_layout, rois, R, grad_feats_nhwc_host, workspace,
+                           workspace_bytes, stream);
+  if (p->out_layout != 0) return BRCNN_ERR_UNSUPPORTED;
   return roi_bwd_launch(a, grad_out, rois, R, grad_feats_nhwc_host, workspace,
                         workspace_bytes, stream);
 }
@@ -1029,8 +1204,7 @@ int brcnn_rcnn_sample_targets(const brcnn_sample_params* p, const float* proposa
   const size_t smem = (size_t)sel_cap * 8 + (size_t)(a.Gmax + a.M) * 4;
   if (smem > 200 * 1024) return BRCNN_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(rcnn_sample_target_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dyn_smem((const void*)rcnn_sample_target_kernel, smem);
     if (e != cudaSuccess) return (int)e;
   }
   rcnn_sample_target_kernel<<<p->batch, ST_THREADS, smem, stream>>>(

@@ -464,9 +464,7 @@ inline int launch_nms_merge(const int32_t* kept_pos, const u64* kept_key,
     const size_t sm = (size_t)np2 * sizeof(u64);
     if (sm <= 200 * 1024) {
       if (sm > 32 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(nms_merge_sort_kernel<Epilogue>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sm);
+        cudaError_t e = ensure_dyn_smem((const void*)nms_merge_sort_kernel<Epilogue>, sm);
         if (e != cudaSuccess) return (int)e;
       }
       nms_merge_sort_kernel<Epilogue><<<B, 1024, sm, stream>>>(
@@ -480,9 +478,7 @@ inline int launch_nms_merge(const int32_t* kept_pos, const u64* kept_key,
   int use_smem = 1;
   if (smem > 200 * 1024) { use_smem = 0; smem = 0; }
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(nms_merge_kernel<Epilogue>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    cudaError_t e = ensure_dyn_smem((const void*)nms_merge_kernel<Epilogue>, smem);
     if (e != cudaSuccess) return (int)e;
   }
   nms_merge_kernel<Epilogue><<<B, 256, smem, stream>>>(
@@ -515,9 +511,7 @@ inline int launch_nms_segments(const float4* boxes, const uint8_t* valid,
   if (nms_use_fused(keep_pad)) {
     const size_t smem = (size_t)keep_pad * 20;
     if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(nms_fused_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem);
+      cudaError_t e = ensure_dyn_smem((const void*)nms_fused_kernel, smem);
       if (e != cudaSuccess) return (int)e;
     }
     nms_fused_kernel<<<S, NMS_FUSED_THREADS, smem, stream>>>(

@@ -39,6 +39,16 @@ struct RoiBwdRec {      // 16 B, read by every tile CTA
   int ylo, yhi, xlo, xhi;   // inclusive footprint; empty if ylo > yhi
 };
 
+// optional outputs of roi_bwd_prep_kernel for the v3 gather (roi_align_bwd3.cuh)
+struct RoiBwdBuckets {
+  int32_t* bucket;       // [B*L][R] RoI ids per (image, level), arrival order
+  RoiBwdRec* bucket_rec; // [B*L][R] their footprint boxes (same order)
+  int32_t* bucket_cnt;   // [B*L]
+  int32_t* tile_cnt;     // [tiles] number of RoIs whose footprint box touches the tile
+  int tile_side;
+  int tiles_x[BRCNN_MAX_LEVELS], tiles_y[BRCNN_MAX_LEVELS], tile_first[BRCNN_MAX_LEVELS];
+};
+
 struct RoiBwd2Args {
   RoiArgs a;
   float* grad[BRCNN_MAX_LEVELS];  // NHWC (B,H,W,C)
@@ -51,7 +61,7 @@ struct RoiBwd2Args {
 __global__ void __launch_bounds__(128)
 roi_bwd_prep_kernel(const __grid_constant__ RoiArgs a, const float* __restrict__ rois, int R,
                     int TR, RoiBwdRec* __restrict__ recs, unsigned short* __restrict__ keys,
-                    float* __restrict__ tab) {
+                    float* __restrict__ tab, const RoiBwdBuckets bk) {
   const int r = blockIdx.x;
   const int tid = threadIdx.x;
   const float* roi = rois + (size_t)r * 5;
@@ -70,8 +80,28 @@ roi_bwd_prep_kernel(const __grid_constant__ RoiArgs a, const float* __restrict__
       else { rec.ylo = rec.xlo = 1; rec.yhi = rec.xhi = 0; }
     }
   }
-  if (tid == 0) { recs[r] = rec; keys[r] = key; }
+  if (tid == 0) {
+    recs[r] = rec; keys[r] = key;
+    // v3 gather: append to the (image, level) bucket; arrival order is arbitrary, the
+    // gather kernel sorts each tile's list by RoI index
+    if (ok && bk.bucket != nullptr) {
+      const size_t slot = (size_t)key * R + atomicAdd(bk.bucket_cnt + key, 1);
+      bk.bucket[slot] = r;
+      bk.bucket_rec[slot] = rec;
+    }
+  }
   if (!ok) return;
+  if (bk.tile_cnt != nullptr) {
+    const int ts = bk.tile_side;
+    const int tx0 = rec.xlo / ts, ty0 = rec.ylo / ts;
+    const int ntx = rec.xhi / ts - tx0 + 1, nty = rec.yhi / ts - ty0 + 1;
+    int32_t* tc = bk.tile_cnt + bk.tile_first[g.lvl] +
+                  (size_t)g.b * bk.tiles_x[g.lvl] * bk.tiles_y[g.lvl];
+    for (int i = tid; i < ntx * nty; i += 128) {
+      const int dy = i / ntx, dx = i - dy * ntx;
+      atomicAdd(tc + (ty0 + dy) * bk.tiles_x[g.lvl] + tx0 + dx, 1);
+    }
+  }
   const int fh = rec.yhi - rec.ylo + 1, fw = rec.xhi - rec.xlo + 1;
   float* t = tab + (size_t)r * TR * 8;
   for (int row = tid; row < fh + fw; row += 128) {

@@ -1,0 +1,331 @@
+// K3 (v3): persistent, cross-RoI pipelined RoIAlign forward with the (R, PH, PW, C)
+// feature hand-off.
+//
+// Reference behaviour: single_level_roi_extractor.py:36-115 + mmcv RoIAlign (aligned=True,
+// pool_mode='avg', sampling_ratio=0), SURVEY.md App. A5/A6.  Same separable formulation as
+// roi_align_tma.cuh,
+//     out[ph][pw][c] = sum_y Wy[ph][y] * ( sum_x Wx[pw][x] * F[y][x][c] ),
+// evaluated x-first one footprint row at a time; what changes is the schedule and the
+// instruction count (the v2 kernel was issue-bound: 61 M warp instructions per 4096 RoIs):
+//   * one CTA per SM slot (2 per SM) loops over RoIs r = blockIdx.x, += gridDim.x.  The ring of
+//     fixed-size row slots and its mbarriers live across RoIs: the producer warp streams RoI
+//     i+1's footprint rows (1-D `cp.async.bulk`) while the consumer warps are still folding /
+//     storing RoI i — no per-RoI barrier init, table build or output staging bubble;
+//   * the producer warp does ALL per-RoI scalar work once (geometry, level map, footprint box,
+//     separable weight tables, per-row / per-column non-zero bands) and publishes it through a
+//     double-buffered descriptor + table area (tab_full / tab_empty mbarriers); consumers read
+//     a 48-byte descriptor instead of redoing the geometry in every thread;
+//   * arithmetic is packed: fma.rn.f32x2 (FFMA2) halves the FMA issue slots of both passes, and
+//     the y-fold jumps straight to the row's band [pa, pb] of pooled rows (switch on pa) instead
+//     of seven predicated 8-FMA groups;
+//   * the output is written (R, PH, PW, C): a consumer lane holds a channel quad for one pooled
+//     column, so each pooled row leaves as a fully coalesced 512 B streaming store per warp —
+//     no shared-memory staging, no bank conflicts.  ConvFCBBoxHead's first FC consumes that
+//     order directly (its weight columns are permuted once, convfc_bbox_head.py:164).
+#pragma once
+#include "common.cuh"
+#include "roi_align.cuh"
+#include "roi_align_tma.cuh"
+
+namespace brcnn {
+
+constexpr int R3_MAX_STAGES = 8;
+constexpr int R3_DESC = 32;   // descriptor ints at the head of a table buffer
+
+struct Roi3Smem {
+  int slot_bytes, ns, tab_floats, total;
+};
+
+__device__ __forceinline__ void r3_ffma2(float2& d, const float2 a, const float2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)),
+        "l"(reinterpret_cast<const unsigned long long&>(b)));
+}
+
+// acc[PH] += w[PH] * h (static pooled-row index)
+template <int PH>
+__device__ __forceinline__ void r3_fold1(float2 (&a0)[RT_P][2], float2 (&a1)[RT_P][2],
+                                         const float (&wv)[8], const float2 (&h0)[2],
+                                         const float2 (&h1)[2]) {
+  if constexpr (PH < RT_P) {
+    const float2 w2 = make_float2(wv[PH], wv[PH]);
+    r3_ffma2(a0[PH][0], w2, h0[0]);
+    r3_ffma2(a0[PH][1], w2, h0[1]);
+    r3_ffma2(a1[PH][0], w2, h1[0]);
+    r3_ffma2(a1[PH][1], w2, h1[1]);
+  }
+}
+// the row's band starts at pooled row P and is at most 3 long: fold rows P .. min(P+2, pb)
+template <int P>
+__device__ __forceinline__ void r3_fold3(float2 (&a0)[RT_P][2], float2 (&a1)[RT_P][2],
+                                         const float (&wv)[8], int pb, const float2 (&h0)[2],
+                                         const float2 (&h1)[2]) {
+  r3_fold1<P>(a0, a1, wv, h0, h1);
+  if (P + 1 <= pb) r3_fold1<P + 1>(a0, a1, wv, h0, h1);
+  if (P + 2 <= pb) r3_fold1<P + 2>(a0, a1, wv, h0, h1);
+}
+
+// dynamic smem: ring ns*slot_bytes | tab[2], each: desc[32 ints] | wy[max_h][8] | wx[8][max_w]
+//   desc: 0 dead, 1 ylo(unused by consumers), 2 fh, 3 fw, 4 npass, 5 cw, 8..15 xs[pw], 16..23 xe[pw]
+//   wy row: 7 weights (1/count folded in) + packed non-zero band pa | pb << 8
+__global__ void __launch_bounds__(RT_THREADS, 2)
+roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict__ rois, int R,
+                      float* __restrict__ out, int32_t* __restrict__ roi_levels,
+                      const Roi3Smem lay) {
+  extern __shared__ __align__(128) unsigned char r3_smem[];
+  float* ring = reinterpret_cast<float*>(r3_smem);
+  float* tabs = reinterpret_cast<float*>(r3_smem + (size_t)lay.ns * lay.slot_bytes);
+  __shared__ __align__(8) uint64_t full_bar[R3_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[R3_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tab_full[2];
+  __shared__ __align__(8) uint64_t tab_empty[2];
+
+  const int c0 = blockIdx.y * a.chunk_c;
+  const int cc = min(a.chunk_c, a.C - c0);
+  const int ncq = cc >> 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NS = lay.ns;
+  const int slot_floats = lay.slot_bytes >> 2;
+  const int px_bytes = cc * 4;
+  const int cw_max = max(1, lay.slot_bytes / px_bytes);
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], RT_CONS_WARPS);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tab_full[s], 1);
+      mbar_init(&tab_empty[s], RT_CONS_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const uint32_t tfull0 = smem_u32(tab_full), tempty0 = smem_u32(tab_empty);
+
+  int s = 0, round = 0;   // ring position (both roles advance identically)
+  int k = 0;              // RoIs processed so far by this CTA (table buffer = k & 1)
+
+  if (warp == RT_CONS_WARPS) {
+    // ============================= producer warp =============================
+    // Schedule per RoI k: (1) issue its first NS footprint rows (their slots were last used
+    // by earlier RoIs, so this never waits on RoI k's own rows), (2) build and publish the
+    // tables of RoI k+1 while those rows fly / are consumed, (3) issue the remaining rows.
+    struct Geo {
+      RoiGeom g;
+      int ylo, xlo, fh, fw, npass, cw, lvl;
+      bool dead;
+    };
+    auto geo_of = [&](const float (&rv)[5]) {
+      Geo q;
+      const bool padding = rv[0] < 0.f;
+      int ylo = 1, yhi = 0, xlo = 1, xhi = 0;
+      q.g.b = -1; q.g.lvl = 0;
+      if (!padding) {
+        q.g = roi_geometry(a, rv);
+        roi_axis_range(q.g.start_h, q.g.bin_h, a.PH, q.g.gh, q.g.H, ylo, yhi);
+        roi_axis_range(q.g.start_w, q.g.bin_w, a.PW, q.g.gw, q.g.W, xlo, xhi);
+      }
+      q.ylo = ylo; q.xlo = xlo;
+      q.fh = yhi - ylo + 1; q.fw = xhi - xlo + 1;
+      q.dead = padding || q.fh <= 0 || q.fw <= 0 || q.g.b < 0 || q.g.b >= a.B;
+      q.lvl = padding ? -1 : q.g.lvl;
+      q.npass = 1; q.cw = q.fw;
+      if (!q.dead && q.fw > cw_max) {
+        q.npass = (q.fw + cw_max - 1) / cw_max;
+        q.cw = (q.fw + q.npass - 1) / q.npass;
+      }
+      return q;
+    };
+    // descriptor + separable weight tables of RoI number kk (of this CTA) -> buffer kk & 1
+    auto publish = [&](const Geo& q, int kk) {
+      float* tb = tabs + (size_t)(kk & 1) * lay.tab_floats;
+      int* desc = reinterpret_cast<int*>(tb);
+      float* wy = tb + R3_DESC;                        // [fh][8]
+      float* wx = wy + (size_t)a.max_h * 8;            // [pw][max_w]
+      if (kk >= 2) mbar_wait_addr(tempty0 + 8u * (kk & 1), (uint32_t)(((kk >> 1) & 1) ^ 1));
+      if (lane == 0) {
+        desc[0] = q.dead ? 1 : 0; desc[1] = q.ylo; desc[2] = q.fh; desc[3] = q.fw;
+        desc[4] = q.npass; desc[5] = q.cw;
+      }
+      if (lane < 8) { desc[8 + lane] = q.fw; desc[16 + lane] = -1; }
+      __syncwarp();
+      if (!q.dead) {
+        // Wy: lane = (row, pooled row); the band of a row comes from a ballot over its 8 lanes
+        for (int i0 = 0; i0 < 8 * q.fh; i0 += 32) {
+          const int i = i0 + lane, dy = i >> 3, ph = i & 7;
+          float v = 0.f;
+          if (dy < q.fh && ph < a.PH)
+            v = roi_axis_weight(q.g.start_h, q.g.bin_h, q.g.gh, q.g.H, ph, q.ylo + dy) *
+                q.g.inv_count;
+          const unsigned nz = (__ballot_sync(0xffffffffu, v != 0.f) >> (lane & 24)) & 0x7fu;
+          if (ph == 7) v = __int_as_float(nz ? ((__ffs(nz) - 1) | ((31 - __clz(nz)) << 8)) : 1);
+          if (dy < q.fh) wy[i] = v;
+        }
+        // Wx: lane = (column, pooled column); bands through shared-memory min / max
+        for (int i0 = 0; i0 < 8 * q.fw; i0 += 32) {
+          const int i = i0 + lane, dx = i >> 3, pw = i & 7;
+          if (dx < q.fw && pw < a.PW) {
+            const float v = roi_axis_weight(q.g.start_w, q.g.bin_w, q.g.gw, q.g.W, pw, q.xlo + dx);
+            wx[pw * a.max_w + dx] = v;
+            if (v != 0.f) { atomicMin(&desc[8 + pw], dx); atomicMax(&desc[16 + pw], dx); }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tab_full[kk & 1]);
+    };
+    auto issue_rows = [&](const Geo& q, int j0, int j1) {   // rows [j0, j1) of pass-major order
+      const float* fbase = a.feat[q.g.lvl] + ((size_t)q.g.b * q.g.H * q.g.W) * a.C + c0;
+      const bool contiguous = (cc == a.C);
+      for (int j = j0; j < j1; ++j) {
+        const int pass = j / q.fh, dy = j - pass * q.fh;
+        const int x0 = pass * q.cw;
+        const int cwe = min(q.cw, q.fw - x0);
+        if (round > 0) mbar_wait_addr(empty0 + 8u * s, (uint32_t)((round - 1) & 1));
+        const float* src = fbase + ((size_t)(q.ylo + dy) * q.g.W + q.xlo + x0) * a.C;
+        float* slot = ring + (size_t)s * slot_floats;
+        if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(cwe * px_bytes));
+        if (contiguous) {
+          if (lane == 0) tma_load_1d(slot, src, (uint32_t)(cwe * px_bytes), &full_bar[s]);
+        } else {
+          __syncwarp();
+          for (int px = lane; px < cwe; px += 32)
+            tma_load_1d(slot + (size_t)px * cc, src + (size_t)px * a.C, (uint32_t)px_bytes,
+                        &full_bar[s]);
+        }
+        if (++s == NS) { s = 0; ++round; }
+      }
+    };
+    auto load_roi = [&](int r, float (&rv)[5]) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) rv[i] = (r < R) ? __ldg(rois + (size_t)r * 5 + i) : -1.f;
+    };
+    float rv[5];
+    load_roi(blockIdx.x, rv);
+    Geo cur = geo_of(rv);
+    load_roi(blockIdx.x + gridDim.x, rv);
+    if ((int)blockIdx.x < R) publish(cur, 0);
+    for (int r = blockIdx.x; r < R; r += gridDim.x, ++k) {
+      if (roi_levels != nullptr && blockIdx.y == 0 && lane == 0) roi_levels[r] = cur.lvl;
+      const int rows = cur.dead ? 0 : cur.npass * cur.fh;
+      const int pre = min(rows, NS);
+      issue_rows(cur, 0, pre);
+      const int rn = r + gridDim.x;
+      Geo nxt = cur;
+      if (rn < R) {
+        nxt = geo_of(rv);
+        load_roi(rn + gridDim.x, rv);
+        publish(nxt, k + 1);
+      }
+      issue_rows(cur, pre, rows);
+      cur = nxt;
+    }
+  } else {
+    // ============================= consumer warps ============================
+    const int pw = warp;
+    const bool act0 = (pw < a.PW) && (lane < ncq);
+    const bool act1 = (pw < a.PW) && (lane + 32 < ncq);
+    const int q1 = act1 ? lane + 32 : lane;   // inactive second quad re-reads the first
+    const size_t bin_stride = (size_t)a.C;
+    for (int r = blockIdx.x; r < R; r += gridDim.x, ++k) {
+      const float* tb = tabs + (size_t)(k & 1) * lay.tab_floats;
+      const int* desc = reinterpret_cast<const int*>(tb);
+      const float* wy = tb + R3_DESC;
+      const float* wxp = wy + (size_t)a.max_h * 8 + (size_t)(act0 ? pw : 0) * a.max_w;
+      float* dst = out + (size_t)r * a.PH * a.PW * a.C + c0 + (size_t)pw * bin_stride;
+      mbar_wait_addr(tfull0 + 8u * (k & 1), (uint32_t)((k >> 1) & 1));
+      const int4 d0 = *reinterpret_cast<const int4*>(desc);        // dead, ylo, fh, fw
+      const int npass = desc[4], cw = desc[5];
+      const int fh = d0.z, fw = d0.w;
+      float2 acc0[RT_P][2], acc1[RT_P][2];
+#pragma unroll
+      for (int i = 0; i < RT_P; ++i) {
+        acc0[i][0] = acc0[i][1] = make_float2(0.f, 0.f);
+        acc1[i][0] = acc1[i][1] = make_float2(0.f, 0.f);
+      }
+      if (d0.x == 0) {
+        const int bxs = act0 ? desc[8 + pw] : 1, bxe = act0 ? desc[16 + pw] : 0;
+        for (int pass = 0; pass < npass; ++pass) {
+          const int x0 = pass * cw;
+          const int cwe = min(cw, fw - x0);
+          const int xs = max(bxs, x0), xe = min(bxe, x0 + cwe - 1);
+          const bool work = act0 && (xs <= xe);
+          for (int dy = 0; dy < fh; ++dy) {
+            mbar_wait_addr(full0 + 8u * s, (uint32_t)(round & 1));
+            float2 h0[2], h1[2];
+            h0[0] = h0[1] = h1[0] = h1[1] = make_float2(0.f, 0.f);
+            if (work) {
+              const float4* px = reinterpret_cast<const float4*>(ring + (size_t)s * slot_floats) +
+                                 (xs - x0) * ncq;
+              for (int x = xs; x <= xe; ++x) {
+                const float4 v0 = px[lane];
+                const float4 v1 = px[q1];
+                const float w = wxp[x];
+                px += ncq;
+                const float2 w2 = make_float2(w, w);
+                r3_ffma2(h0[0], w2, make_float2(v0.x, v0.y));
+                r3_ffma2(h0[1], w2, make_float2(v0.z, v0.w));
+                r3_ffma2(h1[0], w2, make_float2(v1.x, v1.y));
+                r3_ffma2(h1[1], w2, make_float2(v1.z, v1.w));
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_addr(empty0 + 8u * s);
+            if (work) {
+              const float4 wa = *reinterpret_cast<const float4*>(wy + dy * 8);
+              const float4 wb = *reinterpret_cast<const float4*>(wy + dy * 8 + 4);
+              const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, 0.f};
+              const int pk = __float_as_int(wb.w);
+              const int pa = pk & 0xff, pb = pk >> 8;       // warp-uniform band of this row
+              if (pa <= pb) {
+                if (pb - pa <= 2) {
+                  switch (pa) {
+                    case 0: r3_fold3<0>(acc0, acc1, wv, pb, h0, h1); break;
+                    case 1: r3_fold3<1>(acc0, acc1, wv, pb, h0, h1); break;
+                    case 2: r3_fold3<2>(acc0, acc1, wv, pb, h0, h1); break;
+                    case 3: r3_fold3<3>(acc0, acc1, wv, pb, h0, h1); break;
+                    case 4: r3_fold3<4>(acc0, acc1, wv, pb, h0, h1); break;
+                    case 5: r3_fold3<5>(acc0, acc1, wv, pb, h0, h1); break;
+                    default: r3_fold3<6>(acc0, acc1, wv, pb, h0, h1); break;
+                  }
+                } else {
+#pragma unroll
+                  for (int ph = 0; ph < RT_P; ++ph) {
+                    const float w = wv[ph];
+                    if (w == 0.f) continue;   // zero outside the band (skip: 0 * inf stays out)
+                    const float2 w2 = make_float2(w, w);
+                    r3_ffma2(acc0[ph][0], w2, h0[0]);
+                    r3_ffma2(acc0[ph][1], w2, h0[1]);
+                    r3_ffma2(acc1[ph][0], w2, h1[0]);
+                    r3_ffma2(acc1[ph][1], w2, h1[1]);
+                  }
+                }
+              }
+            }
+            if (++s == NS) { s = 0; ++round; }
+          }
+        }
+      }
+      // tables no longer needed: the producer may overwrite this buffer two RoIs ahead
+      __syncwarp();
+      if (lane == 0) mbar_arrive_addr(tempty0 + 8u * (k & 1));
+      if (pw < a.PW) {
+#pragma unroll
+        for (int ph = 0; ph < RT_P; ++ph) {
+          if (ph < a.PH) {
+            float4* o = reinterpret_cast<float4*>(dst + (size_t)(ph * a.PW) * bin_stride);
+            if (act0) __stcs(o + lane, make_float4(acc0[ph][0].x, acc0[ph][0].y, acc0[ph][1].x,
+                                                   acc0[ph][1].y));
+            if (act1) __stcs(o + lane + 32, make_float4(acc1[ph][0].x, acc1[ph][0].y,
+                                                        acc1[ph][1].x, acc1[ph][1].y));
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace brcnn

@@ -209,7 +209,7 @@ def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
 # RoI extraction (level map + multi-level RoIAlign), autograd enabled
 # --------------------------------------------------------------------------
 def make_roi_params(batch, channels, featmap_sizes, spatial_scales, output_size,
-                    sampling_ratio=0, aligned=True, finest_scale=56):
+                    sampling_ratio=0, aligned=True, finest_scale=56, out_layout=0):
     p = RoiParams()
     p.batch, p.channels, p.num_levels = int(batch), int(channels), len(featmap_sizes)
     for l, ((h, w), s) in enumerate(zip(featmap_sizes, spatial_scales)):
@@ -218,6 +218,7 @@ def make_roi_params(batch, channels, featmap_sizes, spatial_scales, output_size,
     p.pooled_h, p.pooled_w = int(oh), int(ow)
     p.sampling_ratio, p.aligned = int(sampling_ratio), int(bool(aligned))
     p.finest_scale = float(finest_scale)
+    p.out_layout = int(out_layout)
     return p
 
 
@@ -334,22 +335,33 @@ def map_roi_levels(rois, num_levels, finest_scale=56):
 
 
 class _RoiExtractFunction(Function):
-    """feats are (B,C,H,W)-shaped tensors (any memory format)."""
+    """feats are (B,C,H,W)-shaped tensors (any memory format).
+
+    ``channels_last_out``: the (R,C,oh,ow) result is stored (R,oh,ow,C) — a
+    ``torch.channels_last`` tensor.  That is the RoI-feature hand-off to the first FC
+    (``ProbConvFCBBoxHead`` reads it as a free (R, oh*ow*C) view against permuted weight
+    columns); the forward kernel then stores straight from registers and the backward
+    kernel reads ``grad_out`` bin-major with no transpose."""
 
     @staticmethod
     def forward(ctx, rois, spatial_scales, output_size, sampling_ratio, aligned,
-                finest_scale, *feats):
+                finest_scale, channels_last_out, *feats):
         lib = _lib.load()
         rois = _f32c(rois, 'rois')
         assert rois.dim() == 2 and rois.size(1) == 5, 'RoI must be (idx, x1, y1, x2, y2)!'
         B, C = feats[0].shape[:2]
         sizes = [tuple(f.shape[-2:]) for f in feats]
         p = make_roi_params(B, C, sizes, spatial_scales, output_size,
-                            sampling_ratio, aligned, finest_scale)
+                            sampling_ratio, aligned, finest_scale,
+                            out_layout=1 if channels_last_out else 0)
         nhwc = pyramid_to_nhwc(feats)
         R = rois.size(0)
-        out = torch.empty((R, C, p.pooled_h, p.pooled_w), dtype=torch.float32,
-                          device=rois.device)
+        if channels_last_out:
+            out = torch.empty((R, p.pooled_h, p.pooled_w, C), dtype=torch.float32,
+                              device=rois.device).permute(0, 3, 1, 2)
+        else:
+            out = torch.empty((R, C, p.pooled_h, p.pooled_w), dtype=torch.float32,
+                              device=rois.device)
         lvls = torch.empty((R,), dtype=torch.int32, device=rois.device)
         check(lib.brcnn_roi_extract_forward(
             p, ptr_array([t.data_ptr() for t in nhwc]), rois.data_ptr(), R,
@@ -362,35 +374,58 @@ class _RoiExtractFunction(Function):
 
     @staticmethod
     def backward(ctx, grad_out, _grad_lvls):
-        lib = _lib.load()
         (rois,) = ctx.saved_tensors
-        p = ctx.params
-        grad_out = _f32c(grad_out, 'grad_out')
-        dev = grad_out.device
-        R = rois.size(0)
-        grads = [torch.empty((p.batch, p.feat_h[l], p.feat_w[l], p.channels),
-                             dtype=torch.float32, device=dev)
-                 for l in range(p.num_levels)]
-        ws = _ws(lib.brcnn_roi_extract_backward_workspace_bytes(p, R), dev)
-        check(lib.brcnn_roi_extract_backward(
-            p, grad_out.data_ptr(), rois.data_ptr(), R,
-            ptr_array([g.data_ptr() for g in grads]), ws.data_ptr(), ws.numel(),
-            _stream()), 'brcnn_roi_extract_backward')
+        grads = roi_extract_backward(ctx.params, grad_out, rois)
         # channels_last inputs get a channels_last gradient for free;
         # NCHW-contiguous inputs get an NCHW-contiguous one (one launch).
         need = [i for i, cl in enumerate(ctx.channels_last) if not cl]
         conv = dict(zip(need, pyramid_to_nchw([grads[i] for i in need])))
         outs = [conv[i] if i in conv else g.permute(0, 3, 1, 2) for i, g in enumerate(grads)]
-        return (None, None, None, None, None, None, *outs)
+        return (None, None, None, None, None, None, None, *outs)
+
+
+def roi_extract_backward(params, grad_out, rois):
+    """Gradient of ``roi_extract`` w.r.t. every pyramid level, NHWC (B,H,W,C) each.
+    ``grad_out`` is the logical (R,C,oh,ow) tensor; bin-major storage ((R,oh,ow,C), what the
+    permuted-FC hand-off produces) is consumed as it is, anything else goes through the
+    (R,C,oh*ow) layout and one transpose inside the library."""
+    lib = _lib.load()
+    p = RoiParams.from_buffer_copy(params)
+    if not grad_out.is_cuda:
+        raise RuntimeError('grad_out must be a CUDA tensor: no CPU path')
+    if grad_out.dtype != torch.float32:
+        grad_out = grad_out.float()
+    gp = grad_out.permute(0, 2, 3, 1)
+    if (gp.is_contiguous() and grad_out.data_ptr() % 16 == 0 and p.pooled_h <= 7
+            and p.pooled_w <= 7):
+        p.out_layout = 1
+    else:
+        p.out_layout = 0
+        grad_out = _f32c(grad_out, 'grad_out')
+    dev = grad_out.device
+    R = rois.size(0)
+    grads = [torch.empty((p.batch, p.feat_h[l], p.feat_w[l], p.channels),
+                         dtype=torch.float32, device=dev)
+             for l in range(p.num_levels)]
+    ws = _ws(lib.brcnn_roi_extract_backward_workspace_bytes(p, R), dev)
+    check(lib.brcnn_roi_extract_backward(
+        p, grad_out.data_ptr(), rois.data_ptr(), R,
+        ptr_array([g.data_ptr() for g in grads]), ws.data_ptr(), ws.numel(),
+        _stream()), 'brcnn_roi_extract_backward')
+    return grads
 
 
 def roi_extract(feats, rois, spatial_scales, output_size=7, sampling_ratio=0,
-                aligned=True, finest_scale=56, return_levels=False):
+                aligned=True, finest_scale=56, return_levels=False, channels_last_out=False):
     """Fused SingleRoIExtractor.forward: level mapping + RoIAlign on every
-    level in one launch.  Returns (R,C,oh,ow) [and int32 levels]."""
+    level in one launch.  Returns (R,C,oh,ow) [and int32 levels]; with
+    ``channels_last_out`` the same logical tensor stored (R,oh,ow,C)."""
+    oh, ow = _pair(output_size)
+    if channels_last_out and (oh > 7 or ow > 7):
+        channels_last_out = False       # the persistent kernel covers pooled sizes <= 7
     out, lvls = _RoiExtractFunction.apply(rois, tuple(spatial_scales), output_size,
                                           sampling_ratio, aligned, finest_scale,
-                                          *feats)
+                                          bool(channels_last_out), *feats)
     return (out, lvls) if return_levels else out
 
 

@@ -19,8 +19,12 @@ from .registry import ROI_EXTRACTORS
 class SingleRoIExtractor(nn.Module):
 
     def __init__(self, roi_layer, out_channels, featmap_strides, finest_scale=56,
-                 init_cfg=None):
+                 init_cfg=None, channels_last_out=True):
         super().__init__()
+        # (R,C,oh,ow) result stored (R,oh,ow,C) (torch.channels_last): the RoI-feature
+        # hand-off ProbConvFCBBoxHead reads as a free view; any other consumer sees the
+        # reference's logical tensor (``flatten(1)`` then costs one copy)
+        self.channels_last_out = channels_last_out
         self.roi_layers = self.build_roi_layers(roi_layer, featmap_strides)
         self.out_channels = out_channels
         self.featmap_strides = featmap_strides
@@ -60,4 +64,4 @@ class SingleRoIExtractor(nn.Module):
         feats = feats[:self.num_inputs]
         return ops.roi_extract(feats, rois, [l.spatial_scale for l in self.roi_layers][:len(feats)],
                                layer.output_size, layer.sampling_ratio, layer.aligned,
-                               self.finest_scale)
+                               self.finest_scale, channels_last_out=self.channels_last_out)

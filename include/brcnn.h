@@ -149,6 +149,12 @@ typedef struct brcnn_roi_params {
   int32_t sampling_ratio;                /* 0 = adaptive ceil(roi/pooled)    */
   int32_t aligned;                       /* mmcv default 1                   */
   float finest_scale;                    /* 56                               */
+  int32_t out_layout;                    /* memory order of `out` / `grad_out`:
+                                            0 = (R,C,ph,pw) as mmcv RoIAlign returns it,
+                                            1 = (R,ph,pw,C): the channels-last RoI feature
+                                            hand-off to the first FC (permuted weight columns,
+                                            convfc_bbox_head.py:164); forward epilogue and
+                                            backward then need no transpose               */
 } brcnn_roi_params;
 
 /* bbox2roi (mmdet/core/bbox/transforms.py:59-78) on the padded proposal
@@ -166,7 +172,8 @@ int brcnn_map_roi_levels(const float* rois, int32_t num_rois,
 
 /* rois: (R,5) [batch_idx, x1,y1,x2,y2]; rows with batch_idx < 0 are padding
  * and produce zeros.  out: (R, C, pooled_h, pooled_w) NCHW-contiguous, the
- * layout ConvFCBBoxHead flattens (convfc_bbox_head.py:164).
+ * layout ConvFCBBoxHead flattens (convfc_bbox_head.py:164), or
+ * (R, pooled_h, pooled_w, C) when p->out_layout == 1.
  * roi_levels: optional int32[R] (level used for each RoI).                 */
 int brcnn_roi_extract_forward(const brcnn_roi_params* p,
                               const float* const* feats_nhwc_host,
@@ -177,7 +184,7 @@ size_t brcnn_roi_extract_backward_workspace_bytes(const brcnn_roi_params* p,
                                                   int32_t num_rois);
 /* grad_feats_nhwc: host array[L] of (B,H_l,W_l,C) buffers; every element is
  * written exactly once (levels without RoIs get zeros), no float atomics,
- * bit-reproducible run to run.                                             */
+ * bit-reproducible run to run.  grad_out is in the layout p->out_layout names. */
 int brcnn_roi_extract_backward(const brcnn_roi_params* p,
                                const float* grad_out, const float* rois,
                                int32_t num_rois,

@@ -269,3 +269,152 @@ def boost_loss(cls_score, labels, prior, bbox_pred, bbox_targets, bbox_weights,
                             _p(out), _p(gc), _p(gb))
     return dict(loss_cls=out[0], loss_bbox=out[1], acc=out[2], scalars=out,
                 grad_cls=gc, grad_bbox=gb)
+
+
+# ---------------------------------------------------------------------------
+# R-CNN training front-end: assign + sample + targets + prior (numpy restatement;
+# SURVEY.md §8 a11 / f1).  The random permutations are injected (`randperm(n)`), because the
+# reference draws them with torch.randperm on the CPU generator (random_sampler.py:58).
+# ---------------------------------------------------------------------------
+def bbox_overlaps(b1, b2, eps=1e-6):
+    """mmdet/core/bbox/iou_calculators/iou2d_calculator.py:75-260, mode='iou',
+    is_aligned=False: (len(b1), len(b2)) fp32 IoU matrix, op for op."""
+    b1, b2 = _f(b1).reshape(-1, 4), _f(b2).reshape(-1, 4)
+    area1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    area2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    lt = np.maximum(b1[:, None, :2], b2[None, :, :2])
+    rb = np.minimum(b1[:, None, 2:], b2[None, :, 2:])
+    wh = np.maximum(rb - lt, np.float32(0))
+    overlap = wh[..., 0] * wh[..., 1]
+    union = area1[:, None] + area2[None, :] - overlap
+    union = np.maximum(union, np.float32(eps))
+    return (overlap / union).astype(np.float32)
+
+
+def bbox_overlaps_aligned(b1, b2, eps=1e-6):
+    """iou2d_calculator.py:214-226,250-253: is_aligned=True."""
+    b1, b2 = _f(b1).reshape(-1, 4), _f(b2).reshape(-1, 4)
+    area1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    area2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    lt = np.maximum(b1[:, :2], b2[:, :2])
+    rb = np.minimum(b1[:, 2:], b2[:, 2:])
+    wh = np.maximum(rb - lt, np.float32(0))
+    overlap = wh[:, 0] * wh[:, 1]
+    union = np.maximum(area1 + area2 - overlap, np.float32(eps))
+    return (overlap / union).astype(np.float32)
+
+
+def max_iou_assign(bboxes, gt_bboxes, pos_iou_thr, neg_iou_thr, min_pos_iou=0.0,
+                   match_low_quality=True, gt_max_assign_all=True):
+    """MaxIoUAssigner.assign / assign_wrt_overlaps
+    (mmdet/core/bbox/assigners/max_iou_assigner.py:61-212), no ignore regions.
+    Returns (gt_inds (n,) int64: 0 bg, -1 ignore, k+1 assigned GT; max_overlaps (n,))."""
+    bboxes, gt_bboxes = _f(bboxes)[:, :4], _f(gt_bboxes).reshape(-1, 4)
+    n, k = bboxes.shape[0], gt_bboxes.shape[0]
+    gt_inds = np.full((n,), -1, dtype=np.int64)
+    if k == 0 or n == 0:                                   # :148-160
+        if k == 0:
+            gt_inds[:] = 0
+        return gt_inds, np.zeros((n,), np.float32)
+    ov = bbox_overlaps(gt_bboxes, bboxes)                  # (k, n)
+    max_ov, argmax_ov = ov.max(0), ov.argmax(0)            # first maximum
+    gt_max = ov.max(1)
+    if isinstance(neg_iou_thr, (tuple, list)):             # :173-181
+        gt_inds[(max_ov >= np.float32(neg_iou_thr[0])) & (max_ov < np.float32(neg_iou_thr[1]))] = 0
+    else:
+        gt_inds[(max_ov >= 0) & (max_ov < np.float32(neg_iou_thr))] = 0
+    pos = max_ov >= np.float32(pos_iou_thr)                # :184-185
+    gt_inds[pos] = argmax_ov[pos] + 1
+    if match_low_quality:                                  # :187-202, GT order matters
+        for i in range(k):
+            if gt_max[i] >= np.float32(min_pos_iou):
+                if gt_max_assign_all:
+                    gt_inds[ov[i] == gt_max[i]] = i + 1
+                else:
+                    gt_inds[ov[i].argmax()] = i + 1
+    return gt_inds, max_ov
+
+
+def bbox2delta(proposals, gt, means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.)):
+    """mmdet/core/bbox/coder/delta_xywh_bbox_coder.py:98-141, fp32."""
+    p, g = _f(proposals).reshape(-1, 4), _f(gt).reshape(-1, 4)
+    h = np.float32(0.5)
+    px, py = (p[:, 0] + p[:, 2]) * h, (p[:, 1] + p[:, 3]) * h
+    pw, ph = p[:, 2] - p[:, 0], p[:, 3] - p[:, 1]
+    gx, gy = (g[:, 0] + g[:, 2]) * h, (g[:, 1] + g[:, 3]) * h
+    gw, gh = g[:, 2] - g[:, 0], g[:, 3] - g[:, 1]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        d = np.stack([(gx - px) / pw, (gy - py) / ph, np.log(gw / pw), np.log(gh / ph)], -1)
+    d = (d - np.asarray(means, np.float32)[None]) / np.asarray(stds, np.float32)[None]
+    return d.astype(np.float32)
+
+
+def random_sample(gt_inds, num, pos_fraction, neg_pos_ub, randperm):
+    """RandomSampler._sample_pos/_sample_neg + BaseSampler.sample index bookkeeping
+    (samplers/random_sampler.py:32-82, base_sampler.py:78-101): gallery[randperm(n)[:k]]
+    when a list is longer than its quota, then .unique() (= ascending sort)."""
+    def pick(mask, k):
+        inds = np.nonzero(mask)[0]
+        if inds.size <= k:
+            return inds
+        perm = np.asarray(randperm(inds.size))[:k]
+        return np.unique(inds[perm])
+    pos = pick(gt_inds > 0, int(num * pos_fraction))
+    n_neg = num - pos.size
+    if neg_pos_ub >= 0:
+        n_neg = min(n_neg, int(neg_pos_ub * max(1, pos.size)))
+    neg = pick(gt_inds == 0, n_neg)
+    return pos, neg
+
+
+def rcnn_train_prep(proposals, gt_bboxes, gt_labels, num_classes, pos_iou_thr, neg_iou_thr,
+                    min_pos_iou, num, pos_fraction, neg_pos_ub, means, stds, randperm,
+                    pos_weight=-1, match_low_quality=False):
+    """Body of ProbRoIHead.forward_train up to the head forward
+    (mmdet/models/roi_heads/prob_roi_head.py:33-64) + bbox2roi (transforms.py:59-78) +
+    BBoxHead.get_targets (bbox_head.py:122-253) for a batch given as per-image lists.
+    Returns dict(rois, labels, label_weights, bbox_targets, bbox_weights, prior, rows,
+    gt_inds=[per image, after add_gt_])."""
+    out = dict(rois=[], labels=[], label_weights=[], bbox_targets=[], bbox_weights=[], prior=[],
+               rows=[], gt_inds=[], pos_inds=[], neg_inds=[])
+    for b, (pr, gb, gl) in enumerate(zip(proposals, gt_bboxes, gt_labels)):
+        pr, gb = _f(pr), _f(gb).reshape(-1, 4)
+        G = gb.shape[0]
+        gi, _ = max_iou_assign(pr[:, :4], gb, pos_iou_thr, neg_iou_thr, min_pos_iou,
+                               match_low_quality)
+        boxes = pr[:, :4]
+        if G > 0:                                          # add_gt_as_proposals (:78-88)
+            boxes = np.concatenate([gb, boxes], 0)
+            gi = np.concatenate([np.arange(1, G + 1, dtype=np.int64), gi])  # add_gt_
+        pos, neg = random_sample(gi, num, pos_fraction, neg_pos_ub, randperm)
+        pos_boxes, neg_boxes = boxes[pos], boxes[neg]
+        n_pos, n_neg = pos.size, neg.size
+        # prior extraction, prob_roi_head.py:51-64
+        pos_prior = pr[pos[G:] - G, -1]
+        neg_prior = np.float32(1) - pr[neg - G, -1]
+        prior = np.concatenate([np.zeros((G,), np.float32), pos_prior, neg_prior]).astype(np.float32)
+        # get_targets, bbox_head.py:122-186
+        labels = np.full((n_pos + n_neg,), num_classes, dtype=np.int64)
+        lw = np.zeros((n_pos + n_neg,), np.float32)
+        bt = np.zeros((n_pos + n_neg, 4), np.float32)
+        bw = np.zeros((n_pos + n_neg, 4), np.float32)
+        if n_pos > 0:
+            assigned = gi[pos] - 1
+            labels[:n_pos] = np.asarray(gl, np.int64)[assigned]
+            lw[:n_pos] = 1.0 if pos_weight <= 0 else pos_weight
+            bt[:n_pos] = bbox2delta(pos_boxes, gb[assigned], means, stds)
+            bw[:n_pos] = 1
+        if n_neg > 0:
+            lw[-n_neg:] = 1.0
+        sb = np.concatenate([pos_boxes, neg_boxes], 0)
+        out['rois'].append(np.concatenate([np.full((sb.shape[0], 1), b, np.float32), sb], 1))
+        for k, v in (('labels', labels), ('label_weights', lw), ('bbox_targets', bt),
+                     ('bbox_weights', bw), ('prior', prior)):
+            out[k].append(v)
+        out['rows'].append(n_pos + n_neg)
+        out['gt_inds'].append(gi)
+        out['pos_inds'].append(pos)
+        out['neg_inds'].append(neg)
+    for k in ('rois', 'labels', 'label_weights', 'bbox_targets', 'bbox_weights', 'prior'):
+        out[k] = np.concatenate(out[k], 0)
+    return out

@@ -73,3 +73,35 @@ def multiclass_inputs(R, C, seed=0, img=(800, 1333)):
     b[..., 1::2] = b[..., 1::2].clip(0, img[0])
     s = rng.permutation(R * (C + 1)).reshape(R, C + 1).astype(np.float32) / (R * (C + 1))
     return b.reshape(R, C * 4).astype(np.float32), s.astype(np.float32)
+
+
+RCNN_TRAIN_CASES = ('plenty', 'few_negatives', 'no_gt_image', 'many_positives')
+
+
+def rcnn_train_case(case, batch=3, num_classes=80):
+    """Inputs of the R-CNN training front-end (assign + sample + targets + prior) for one
+    named case: per image GT boxes (G,4), GT labels (G,) int64 and proposals (n,5)
+    [x1,y1,x2,y2,score] with scores descending (the RPN's output order).
+      plenty         : many negatives, a few positives (both lists go through randperm or not)
+      few_negatives  : fewer negatives than the quota (no permutation of the negatives)
+      no_gt_image    : image 1 has no GT (everything background)
+      many_positives : > 128 positive candidates -> randperm on the positives; some GTs are
+                       dropped, which misaligns the reference's `pos_inds[num_gts:]` prior
+                       slice (prob_roi_head.py:52) — reproduced, not fixed."""
+    assert case in RCNN_TRAIN_CASES
+    rng = np.random.RandomState(11)
+    gts, labels, plist = [], [], []
+    for b in range(batch):
+        G = 6 if case != 'no_gt_image' or b != 1 else 0
+        g = random_boxes(max(G, 1), 250, 317, seed=40 + b)[:G].reshape(-1, 4)
+        gts.append(g.astype(np.float32))
+        labels.append(rng.randint(0, num_classes, G).astype(np.int64))
+        n_jit = {'plenty': 10, 'few_negatives': 60, 'no_gt_image': 10, 'many_positives': 60}[case]
+        n_rnd = {'plenty': 900, 'few_negatives': 40, 'no_gt_image': 500, 'many_positives': 700}[case]
+        parts = [g + rng.normal(0, 1.5, g.shape) for _ in range(n_jit)] if G else []
+        parts.append(random_boxes(n_rnd, 250, 317, seed=60 + b))
+        bx = np.concatenate(parts).astype(np.float32)
+        bx = bx[rng.permutation(len(bx))]
+        sc = np.sort(rng.rand(len(bx)).astype(np.float32))[::-1].copy()
+        plist.append(np.concatenate([bx, sc[:, None]], 1).astype(np.float32))
+    return gts, labels, plist

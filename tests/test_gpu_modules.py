@@ -264,61 +264,46 @@ def test_cuda_graph_replay_equals_eager_and_pipeline(cuda):
         assert torch.equal(a, b.cpu())
 
 
-@pytest.mark.parametrize('case', ['plenty', 'few_negatives', 'no_gt_image', 'many_positives'])
-def test_fused_assign_sample_targets_equals_python_path(cuda, case):
-    """ops.rcnn_assign_sample (2 launches + host randperm) vs the reference-shaped
-    Python path (MaxIoUAssigner / RandomSampler / get_targets / prior extraction of
-    sampling.py, bbox_head.py, roi_head.py) under the same CPU RNG seed: identical
-    rows, labels and priors; bbox targets within 1e-6 (logf)."""
+@pytest.mark.parametrize('case', synth.RCNN_TRAIN_CASES)
+def test_fused_assign_sample_targets_equals_executed_reference(cuda, case):
+    """brcnn_rcnn_assign + brcnn_rcnn_sample_targets (2 launches + the reference's CPU
+    randperm) against (1) the golden produced by EXECUTING the reference's MaxIoUAssigner /
+    RandomSampler / BBoxHead.get_targets / ProbRoIHead.forward_train
+    (tests/golden/make_golden_train.py) and (2) the numpy oracle, under the same CPU RNG
+    seed: rois, labels, weights and priors bit-exact, bbox targets <= 1e-6 (logf).
+    `many_positives` reproduces the reference's misaligned pos_inds[num_gts:] prior slice."""
+    import os
+    from test_oracle_golden import TRAIN_GOLD, _train_prep_oracle
+    gold = np.load(TRAIN_GOLD)
     torch.manual_seed(3)
     _, roi, m = configs.build_hot_path('coco', train=True)
     roi = roi.to(cuda).train()
-    rng = np.random.RandomState(11)
-    B = 3
-    gts, labels, plist = [], [], []
-    for b in range(B):
-        G = 6 if case != 'no_gt_image' or b != 1 else 0
-        g = synth.random_boxes(max(G, 1), 250, 317, seed=40 + b)[:G]
-        gts.append(torch.from_numpy(g.reshape(-1, 4)).to(cuda))
-        labels.append(torch.from_numpy(rng.randint(0, 80, G)).to(cuda))
-        n_jit = {'plenty': 10, 'few_negatives': 60, 'no_gt_image': 10, 'many_positives': 60}[case]
-        n_rnd = {'plenty': 900, 'few_negatives': 40, 'no_gt_image': 500, 'many_positives': 700}[case]
-        parts = [g + rng.normal(0, 1.5, g.shape) for _ in range(n_jit)] if G else []
-        parts.append(synth.random_boxes(n_rnd, 250, 317, seed=60 + b))
-        bx = np.concatenate(parts).astype(np.float32)
-        bx = bx[rng.permutation(len(bx))]
-        sc = np.sort(rng.rand(len(bx)).astype(np.float32))[::-1].copy()
-        plist.append(torch.from_numpy(np.concatenate([bx, sc[:, None]], 1)).to(cuda))
-    # ---- Python path, exactly the body of ProbRoIHead.forward_train ----
-    torch.manual_seed(123)
-    results, priors = [], []
-    for i in range(B):
-        ar = roi.bbox_assigner.assign(plist[i], gts[i], None, labels[i])
-        res = roi.bbox_sampler.sample(ar, plist[i], gts[i], labels[i])
-        results.append(res)
-        G = ar.num_gts
-        pos_prior = plist[i][res.pos_inds[G:] - G, -1]
-        neg_prior = 1 - plist[i][res.neg_inds - G, -1]
-        priors.append(torch.cat([pos_prior.new_zeros(G), pos_prior, neg_prior]))
-    ref_rois = bbox2roi([r.bboxes for r in results])
-    ref_lab, ref_lw, ref_bt, ref_bw = roi.bbox_head.get_targets(results, gts, labels, roi.train_cfg)
-    ref_prior = torch.cat(priors)
-    # ---- fused path, same CPU RNG state ----
-    torch.manual_seed(123)
+    gts_h, labels_h, plist_h = synth.rcnn_train_case(case)
+    B = len(plist_h)
+    gts = [torch.from_numpy(g).to(cuda) for g in gts_h]
+    labels = [torch.from_numpy(l).to(cuda) for l in labels_h]
+    plist = [torch.from_numpy(p).to(cuda) for p in plist_h]
     a, s, h = roi.bbox_assigner, roi.bbox_sampler, roi.bbox_head
+    assert (a.pos_iou_thr, a.neg_iou_thr, a.min_pos_iou, s.num, s.pos_fraction) == \
+        (0.6, 0.6, 0.6, 512, 0.25)
+    torch.manual_seed(123)
     pp = pad_proposals(plist)
     rois, lab, lw, bt, bw, prior, rows = ops.rcnn_assign_sample(
         pp.boxes, pp.num, gts, labels, h.num_classes, a.pos_iou_thr, a.neg_iou_thr, a.min_pos_iou,
         s.num, s.pos_fraction, s.neg_pos_ub, h.bbox_coder.means, h.bbox_coder.stds,
         roi.train_cfg.pos_weight)
-    assert rows == [r.bboxes.size(0) for r in results]
-    assert torch.equal(rois, ref_rois)
-    assert torch.equal(lab, ref_lab) and torch.equal(lw, ref_lw) and torch.equal(bw, ref_bw)
-    assert torch.equal(prior, ref_prior)
-    assert torch.allclose(bt, ref_bt, rtol=1e-6, atol=1e-6)
+    o = _train_prep_oracle(case)
+    for ref, what in ((lambda k: gold[f'{case}/{k}'], 'executed reference'),
+                      (lambda k: o[k], 'oracle')):
+        assert rows == [int(v) for v in ref('rows')], what
+        for k, t in (('rois', rois), ('label_weights', lw), ('bbox_weights', bw), ('prior', prior)):
+            np.testing.assert_array_equal(t.cpu().numpy().view(np.uint32),
+                                          np.asarray(ref(k)).view(np.uint32), f'{k} vs {what}')
+        np.testing.assert_array_equal(lab.cpu().numpy(), ref('labels'))
+        np.testing.assert_allclose(bt.cpu().numpy(), ref('bbox_targets'), rtol=1e-6, atol=1e-6)
     if case == 'many_positives':
-        assert any(r.pos_inds.numel() == 128 for r in results)   # randperm on the positives too
-    # and through the module: same losses either way
+        assert all(int(n) == 128 for n in gold[f'{case}/num_pos'])   # randperm on the positives
+    # and through the module: the Python fallback path and the fused path give the same losses
     sizes = synth.featmap_sizes(256, 320)
     feats = [torch.from_numpy(f).to(cuda) for f in synth.fpn_feats(B, 256, sizes, seed=4)]
     out = []

@@ -21,7 +21,7 @@ def _close(a, b, what):
 
 
 def _case(dev, batch, pad_hw, C, n_per_img, seed, clustered=False, channels_last=False,
-          extra_rois=None):
+          extra_rois=None, channels_last_out=False):
     sizes = synth.featmap_sizes(*pad_hw)
     scales = [1.0 / s for s in synth.STRIDES]
     feats = synth.fpn_feats(batch, C, sizes, seed=seed)
@@ -34,7 +34,9 @@ def _case(dev, batch, pad_hw, C, n_per_img, seed, clustered=False, channels_last
         tf = [f.contiguous(memory_format=torch.channels_last) for f in tf]
     tf = [f.requires_grad_(True) for f in tf]
     out, lv = ops.roi_extract(tf, torch.from_numpy(rois).to(dev), scales, 7, 0, True, 56,
-                              return_levels=True)
+                              return_levels=True, channels_last_out=channels_last_out)
+    if channels_last_out:   # (R,7,7,C) storage behind the reference's logical shape
+        assert out.shape[1] == C and out.permute(0, 2, 3, 1).is_contiguous()
     ref, rlv = oracle.roi_extract_forward(feats, rois, scales)
     np.testing.assert_array_equal(lv.cpu().numpy().astype(np.int64), rlv)
     _close(out.detach().cpu().numpy(), ref, 'roi features')
@@ -239,3 +241,105 @@ def test_roi_backward_channel_slabs_and_long_lists(cuda, C, n):
     ref = oracle.roi_extract_backward(g[live], rois[live], [f.shape for f in feats], scales)
     for l, (t, r) in enumerate(zip(tf, ref)):
         _close(t.grad.cpu().numpy(), r, f'grad level {l}')
+
+
+# ---------------------------------------------------------------------------
+# (R,7,7,C) feature hand-off: persistent forward kernel (roi_align_fwd3.cuh) and the
+# TMA-staged backward gather reading bin-major gradients (roi_align_bwd3.cuh)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('pad_hw,C,n,clustered', [
+    ((256, 320), 64, 50, False), ((800, 1344), 256, 256, True), ((256, 320), 4, 30, False),
+    ((256, 320), 320, 30, False), ((256, 320), 516, 30, True), ((800, 1344), 256, 2000, False)])
+def test_roi_forward_hwc_layout_matches_nchw_layout(cuda, pad_hw, C, n, clustered):
+    """The persistent kernel does the same per-row arithmetic as the per-RoI TMA kernel; only
+    the x-chunking of wide footprints differs (fixed 16-pixel slots), so the two layouts agree
+    to the last few ulp (and both match the oracle)."""
+    ex = np.array([[-1, 0, 0, 0, 0], [0, 5, 5, 5, 5], [1, 0, 0, pad_hw[1], pad_hw[0]],
+                   [0, 2, 2, pad_hw[1] - 2, 6], [1, pad_hw[1] - 20, pad_hw[0] - 6, pad_hw[1] + 10,
+                                                  pad_hw[0] + 14], [7, 1, 1, 50, 50]],
+                  dtype=np.float32)
+    sizes = synth.featmap_sizes(*pad_hw)
+    scales = [1.0 / s for s in synth.STRIDES]
+    feats = [torch.from_numpy(f).to(cuda) for f in synth.fpn_feats(2, C, sizes, seed=50 + C)]
+    rois = np.concatenate([synth.random_rois(2, n, pad_hw[0], pad_hw[1], seed=51 + C,
+                                             clustered=clustered), ex], 0).astype(np.float32)
+    tr = torch.from_numpy(rois).to(cuda)
+    a, la = ops.roi_extract(feats, tr, scales, 7, return_levels=True)
+    b, lb = ops.roi_extract(feats, tr, scales, 7, return_levels=True, channels_last_out=True)
+    assert b.permute(0, 2, 3, 1).is_contiguous() and a.is_contiguous()
+    assert torch.equal(la, lb)
+    an, bn = a.cpu().numpy(), b.cpu().numpy()
+    assert float(np.abs(an - bn).max()) <= 2e-6 * max(float(np.abs(an).max()), 1e-6)
+    live = (rois[:, 0] >= 0) & (rois[:, 0] < 2)
+    ref, _ = oracle.roi_extract_forward([f.cpu().numpy() for f in feats], rois[live], scales)
+    _close(b.cpu().numpy()[live], ref, 'hwc roi features')
+    assert float(b[~torch.from_numpy(live).to(cuda)].abs().max()) == 0.0
+
+
+def test_roi_forward_hwc_other_pooled_sizes(cuda):
+    feat = synth.fpn_feats(2, 32, [(50, 84)], seed=4)[0]
+    rois = synth.random_rois(2, 25, 800, 1344, seed=12)
+    tf, tr = torch.from_numpy(feat).to(cuda), torch.from_numpy(rois).to(cuda)
+    for osz in [(5, 3), (1, 1), (7, 2)]:
+        out = ops.roi_extract([tf], tr, [1 / 16], osz, channels_last_out=True)
+        _close(out.cpu().numpy(), oracle.roi_align_forward(feat, rois, osz, 1 / 16), f'out {osz}')
+
+
+@pytest.mark.parametrize('grad_hwc', [False, True])
+@pytest.mark.parametrize('pad_hw,C,n', [((256, 320), 64, 120), ((256, 320), 132, 60),
+                                        ((256, 320), 4, 40), ((800, 1344), 256, 512),
+                                        ((256, 320), 320, 1500)])
+def test_roi_backward_both_gradient_layouts(cuda, pad_hw, C, n, grad_hwc):
+    """grad_out arriving (R,C,7,7)-contiguous (transposed inside the library) or bin-major
+    (R,7,7,C) (the permuted-FC hand-off; consumed as is): same gradients, <= 1e-5 vs oracle.
+    The 1500-RoI case puts > 512 RoIs on one (image, level) bucket (windowed list rounds)."""
+    ex = np.array([[-1, 0, 0, 0, 0], [0, 5, 5, 5, 5], [0, 0, 0, pad_hw[1], pad_hw[0]],
+                   [0, 2, 2, pad_hw[1] - 2, 6]], dtype=np.float32)
+    B = 1 if n > 1000 else 2
+    tf, feats, rois, scales, out = _case(cuda, B, pad_hw, C, n, seed=60 + C, clustered=True,
+                                         extra_rois=ex, channels_last_out=grad_hwc)
+    g = np.random.RandomState(61).normal(0, 1, out.shape).astype(np.float32)
+    gt = torch.from_numpy(g).to(cuda)
+    if grad_hwc:
+        gt = gt.contiguous(memory_format=torch.channels_last)
+    out.backward(gt)
+    live = rois[:, 0] >= 0
+    ref = oracle.roi_extract_backward(g[live], rois[live], [f.shape for f in feats], scales)
+    for l, (t, r) in enumerate(zip(tf, ref)):
+        assert t.grad is not None and t.grad.shape == r.shape
+        _close(t.grad.cpu().numpy(), r, f'grad level {l}')
+
+
+def test_roi_backward_hwc_deterministic(cuda):
+    res = []
+    for _ in range(3):
+        tf, feats, rois, scales, out = _case(cuda, 2, (256, 320), 128, 700, seed=70,
+                                             clustered=True, channels_last_out=True)
+        g = np.random.RandomState(71).normal(0, 1, out.shape).astype(np.float32)
+        out.backward(torch.from_numpy(g).to(cuda).contiguous(memory_format=torch.channels_last))
+        res.append([t.grad.cpu().numpy() for t in tf])
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_head_consumes_hwc_features_as_a_view(cuda):
+    """ProbConvFCBBoxHead: channels-last RoI features feed fc1 without a copy, give the
+    same logits as the reference-ordered flatten, and the gradient returns bin-major."""
+    from boosting_rcnn_b200 import configs
+    torch.manual_seed(0)
+    _, roi_head, _ = configs.build_hot_path('utdac')
+    head = roi_head.bbox_head.to(cuda)
+    x = torch.randn(64, 256, 7, 7, device=cuda)
+    xcl = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    assert head._flatten(xcl).data_ptr() == xcl.data_ptr()
+    cs0, bp0 = head(x)
+    cs1, bp1 = head(xcl)
+    assert torch.allclose(cs0, cs1, rtol=1e-5, atol=1e-6) and torch.allclose(bp0, bp1, rtol=1e-5, atol=1e-6)
+    w_ref = head.state_dict()['shared_fcs.0.weight']
+    y_ref = torch.nn.functional.linear(x.flatten(1), w_ref, head.shared_fcs[0].bias)
+    y = torch.nn.functional.linear(head._flatten(xcl), head.shared_fcs[0].weight,
+                                   head.shared_fcs[0].bias)
+    assert torch.allclose(y, y_ref, rtol=1e-4, atol=1e-4)
+    (cs1.sum() + bp1.sum()).backward()
+    assert xcl.grad.permute(0, 2, 3, 1).is_contiguous()

@@ -274,3 +274,84 @@ def test_multiclass_nms_coco_scale_split_path_vs_executed_reference():
     dets, keep = oracle.batched_nms(boxes, scores, labels, 0.5)
     np.testing.assert_array_equal(labels[keep][:100], g['labels'])
     np.testing.assert_array_equal(dets[:100].view(np.uint32), g['dets'].view(np.uint32))
+
+
+# ---------------------------------------------------------------------------
+# R-CNN training front-end: the numpy oracle against goldens produced by
+# executing the reference's MaxIoUAssigner / RandomSampler / get_targets / forward_train
+# (tests/golden/make_golden_train.py)
+# ---------------------------------------------------------------------------
+TRAIN_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                          'reference_golden_train.npz')
+
+
+def _train_prep_oracle(case, seed=123):
+    import torch
+    gts, labels, plist = synth.rcnn_train_case(case)
+    torch.manual_seed(seed)      # the reference draws torch.randperm on the CPU generator
+    return oracle.rcnn_train_prep(
+        plist, gts, labels, 80, 0.6, 0.6, 0.6, 512, 0.25, -1, (0., 0., 0., 0.),
+        (0.1, 0.1, 0.2, 0.2), randperm=lambda n: torch.randperm(n).numpy())
+
+
+@pytest.mark.parametrize('case', synth.RCNN_TRAIN_CASES)
+def test_train_prep_oracle_equals_executed_reference(case):
+    g = np.load(TRAIN_GOLD)
+    o = _train_prep_oracle(case)
+    assert list(o['rows']) == list(g[f'{case}/rows'])
+    for b in range(len(o['rows'])):
+        np.testing.assert_array_equal(o['pos_inds'][b], g[f'{case}/pos_inds_{b}'])
+        np.testing.assert_array_equal(o['neg_inds'][b], g[f'{case}/neg_inds_{b}'])
+    for k in ('rois', 'label_weights', 'bbox_weights', 'prior'):
+        np.testing.assert_array_equal(o[k].view(np.uint32), g[f'{case}/{k}'].view(np.uint32), k)
+    np.testing.assert_array_equal(o['labels'], g[f'{case}/labels'])
+    np.testing.assert_allclose(o['bbox_targets'], g[f'{case}/bbox_targets'], rtol=1e-6, atol=1e-6)
+    if case == 'many_positives':
+        # GTs were dropped by randperm: the reference's pos_inds[num_gts:] slice is misaligned
+        # (prior 0 on non-GT rows) and the oracle reproduces exactly that
+        assert all(n == 128 for n in g[f'{case}/num_pos'])
+        G = 6
+        assert (g[f'{case}/pos_inds_0'][:G] >= G).any()
+
+
+def test_max_iou_assigner_match_low_quality_equals_executed_reference():
+    """RPN-stage assigner setting (pos=neg=0.5, min_pos_iou=0, match_low_quality=True): a GT
+    that overlaps nothing claims every zero-overlap box (gt_max == 0 >= min_pos_iou), later GTs
+    override earlier ones — reproduced from the executed reference."""
+    g = np.load(TRAIN_GOLD)
+    gi, mo = oracle.max_iou_assign(g['mlq/boxes'], g['mlq/gts'], 0.5, 0.5, 0.0, True)
+    np.testing.assert_array_equal(gi, g['mlq/gt_inds'])
+    np.testing.assert_array_equal(mo.view(np.uint32), g['mlq/max_overlaps'].view(np.uint32))
+    assert (gi == 4).sum() > 100     # the isolated GT (index 3) grabbed the zero-overlap boxes
+
+
+@pytest.mark.parametrize('case', synth.RCNN_TRAIN_CASES)
+def test_python_fallback_train_prep_equals_executed_reference(case):
+    """The torch fallback of the training front-end (boosting_rcnn_b200/sampling.py +
+    ProbConvFCBBoxHead.get_targets + the prior lines of ProbRoIHead.forward_train; used when the
+    fused kernels' limits are exceeded) on CPU tensors against the executed-reference golden."""
+    import torch
+    from boosting_rcnn_b200 import configs
+    from boosting_rcnn_b200.roi_head import bbox2roi
+    g = np.load(TRAIN_GOLD)
+    torch.manual_seed(3)
+    _, roi, _ = configs.build_hot_path('coco', train=True)
+    gts, labels, plist = synth.rcnn_train_case(case)
+    gts, labels, plist = ([torch.from_numpy(a) for a in xs] for xs in (gts, labels, plist))
+    torch.manual_seed(123)
+    results, priors = [], []
+    for i in range(len(plist)):
+        ar = roi.bbox_assigner.assign(plist[i], gts[i], None, labels[i])
+        res = roi.bbox_sampler.sample(ar, plist[i], gts[i], labels[i])
+        results.append(res)
+        G = ar.num_gts
+        pos_prior = plist[i][res.pos_inds[G:] - G, -1]
+        neg_prior = 1 - plist[i][res.neg_inds - G, -1]
+        priors.append(torch.cat([pos_prior.new_zeros(G), pos_prior, neg_prior]))
+    lab, lw, bt, bw = roi.bbox_head.get_targets(results, gts, labels, roi.train_cfg)
+    np.testing.assert_array_equal(bbox2roi([r.bboxes for r in results]).numpy(), g[f'{case}/rois'])
+    np.testing.assert_array_equal(lab.numpy(), g[f'{case}/labels'])
+    np.testing.assert_array_equal(lw.numpy(), g[f'{case}/label_weights'])
+    np.testing.assert_array_equal(bw.numpy(), g[f'{case}/bbox_weights'])
+    np.testing.assert_array_equal(torch.cat(priors).numpy(), g[f'{case}/prior'])
+    np.testing.assert_allclose(bt.numpy(), g[f'{case}/bbox_targets'], rtol=1e-6, atol=1e-6)
