@@ -33,6 +33,19 @@ class RpnParams(Structure):
     ]
 
 
+class RpnLossParams(Structure):
+    _fields_ = [
+        ('batch', c_int32), ('num_levels', c_int32), ('num_anchors', c_int32),
+        ('feat_h', c_int32 * MAX_LEVELS), ('feat_w', c_int32 * MAX_LEVELS),
+        ('stride_w', c_int32 * MAX_LEVELS), ('stride_h', c_int32 * MAX_LEVELS),
+        ('max_gts', c_int32),
+        ('pos_iou_thr', c_float), ('neg_iou_thr', c_float), ('min_pos_iou', c_float),
+        ('gamma', c_float), ('focal_gamma', c_float), ('focal_alpha', c_float),
+        ('loss_cls_weight', c_float), ('loss_bbox_weight', c_float),
+        ('loss_iou_weight', c_float), ('loss_aug_weight', c_float), ('max_ratio', c_float),
+    ]
+
+
 class RpnWsLayout(Structure):
     _fields_ = [(n, c_int64) for n in (
         'cand_cap', 'keep_cap', 'cand_boxes', 'cand_key', 'cand_valid',
@@ -100,6 +113,14 @@ SIGNATURES = {
     'brcnn_rpn_get_bboxes': (c_int32, [
         POINTER(RpnParams), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'brcnn_rpn_loss_workspace_bytes': (c_size_t, [POINTER(RpnLossParams)]),
+    'brcnn_rpn_loss_forward': (c_int32, [
+        POINTER(RpnLossParams), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_void_p),
+        POINTER(c_void_p), c_void_p, c_size_t, c_void_p]),
+    'brcnn_rpn_loss_scale': (c_int32, [
+        POINTER(RpnLossParams), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+        c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_void_p]),
     'brcnn_delta2bbox': (c_int32, [c_void_p, c_void_p, c_int32, c_int32,
                                    POINTER(c_float), POINTER(c_float), c_float,
                                    c_float, c_float, c_void_p, c_void_p]),

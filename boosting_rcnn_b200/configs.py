@@ -13,6 +13,7 @@ import copy
 _RPN_TRAIN = dict(
     assigner=dict(type='MaxIoUAssigner', pos_iou_thr=0.5, neg_iou_thr=0.5, min_pos_iou=0,
                   match_low_quality=True, ignore_iof_thr=-1),
+    sampler=dict(type='PseudoSampler'),
     allowed_border=-1, pos_weight=-1, debug=False)
 _RPN_PROPOSAL_TRAIN = dict(nms_pre=4000, max_per_img=2000,
                            nms=dict(type='nms', iou_threshold=0.7), min_bbox_size=0)
@@ -104,7 +105,8 @@ def build_hot_path(name, train=False):
     from .registry import build_head
     m = model_cfg(name)
     rpn_cfg, roi_cfg = dict(m['rpn_head']), dict(m['roi_head'])
-    rpn_cfg.update(train_cfg=None, test_cfg=m['test_cfg']['rpn'])
+    rpn_cfg.update(train_cfg=m['train_cfg']['rpn'] if train else None,
+                   test_cfg=m['test_cfg']['rpn'])
     roi_cfg.update(train_cfg=m['train_cfg']['rcnn'] if train else None,
                    test_cfg=m['test_cfg']['rcnn'])
     return build_head(rpn_cfg), build_head(roi_cfg), m

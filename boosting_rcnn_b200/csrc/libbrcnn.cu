@@ -22,6 +22,7 @@
 #include "roi_align_fwd3.cuh"
 #include "roi_align_tma.cuh"
 #include "rpn.cuh"
+#include "rpn_loss.cuh"
 #include "rpn_nms.cuh"
 
 namespace brcnn {
@@ -537,6 +538,127 @@ int brcnn_delta2bbox(const float* rois, const float* deltas, int32_t n, int32_t 
   if (tot > 0x7fffffff) return BRCNN_ERR_UNSUPPORTED;
   delta2bbox_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
       a, rois, deltas, out);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+// ------------------------------- RPN loss ---------------------------------
+static int rpn_loss_args(const brcnn_rpn_loss_params* p, RpnLossArgs* a) {
+  if (!p || p->batch <= 0 || p->num_levels <= 0 || p->num_levels > BRCNN_MAX_LEVELS ||
+      p->num_anchors <= 0 || p->num_anchors > BRCNN_MAX_ANCHORS || p->max_gts < 0)
+    return BRCNN_ERR_ARG;
+  if (p->max_gts > 1024 || p->batch > 65535) return BRCNN_ERR_UNSUPPORTED;
+  memset(a, 0, sizeof(*a));
+  a->A = p->num_anchors; a->L = p->num_levels; a->B = p->batch;
+  a->Gmax = p->max_gts > 0 ? p->max_gts : 1;
+  long long blocks = 0;
+  for (int l = 0; l < p->num_levels; ++l) {
+    if (p->feat_h[l] <= 0 || p->feat_w[l] <= 0 || p->stride_w[l] <= 0 || p->stride_h[l] <= 0)
+      return BRCNN_ERR_ARG;
+    const long long n = (long long)p->feat_h[l] * p->feat_w[l] * p->num_anchors;
+    if (n > 0x3fffffff) return BRCNN_ERR_UNSUPPORTED;
+    RpnLossLevel& lv = a->lv[l];
+    lv.H = p->feat_h[l]; lv.W = p->feat_w[l];
+    lv.stride_w = p->stride_w[l]; lv.stride_h = p->stride_h[l];
+    lv.n = (int)n; lv.block_base = (int)blocks;
+    blocks += (n + RL_THREADS - 1) / RL_THREADS;
+  }
+  if (blocks > 0x7fffffff) return BRCNN_ERR_UNSUPPORTED;
+  a->blocks_per_img = (int)blocks;
+  a->pos_iou_thr = p->pos_iou_thr; a->neg_iou_thr = p->neg_iou_thr;
+  a->min_pos_iou = p->min_pos_iou; a->gamma = p->gamma;
+  a->focal_gamma = p->focal_gamma; a->focal_alpha = p->focal_alpha;
+  a->w_cls = p->loss_cls_weight; a->w_bbox = p->loss_bbox_weight;
+  a->w_iou = p->loss_iou_weight; a->w_aug = p->loss_aug_weight;
+  a->max_ratio = p->max_ratio;
+  return BRCNN_OK;
+}
+
+size_t brcnn_rpn_loss_workspace_bytes(const brcnn_rpn_loss_params* p) {
+  RpnLossArgs a;
+  if (rpn_loss_args(p, &a)) return 0;
+  return align256((size_t)a.B * a.Gmax * 4) +
+         align256((size_t)a.B * a.blocks_per_img * RL_SUMS * 4);
+}
+
+int brcnn_rpn_loss_forward(const brcnn_rpn_loss_params* p, const float* const* cls_scores_host,
+                           const float* const* bbox_preds_host, const float* const* iou_preds_host,
+                           const float* base_anchors, const float* gt_boxes,
+                           const int32_t* num_gt, const float* pad_hw, float* sums,
+                           float* const* grad_cls_host, float* const* grad_bbox_host,
+                           float* const* grad_iou_host, void* workspace, size_t workspace_bytes,
+                           brcnn_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RpnLossArgs a;
+  int rc = rpn_loss_args(p, &a);
+  if (rc) return rc;
+  if (!cls_scores_host || !bbox_preds_host || !iou_preds_host || !base_anchors || !num_gt ||
+      !pad_hw || !sums || !grad_cls_host || !grad_bbox_host || !grad_iou_host || !workspace)
+    return BRCNN_ERR_ARG;
+  if (p->max_gts > 0 && (!gt_boxes || misaligned16(gt_boxes))) return BRCNN_ERR_ARG;
+  if (misaligned16(base_anchors) || misaligned16(workspace)) return BRCNN_ERR_ARG;
+  if (workspace_bytes < brcnn_rpn_loss_workspace_bytes(p)) return BRCNN_ERR_WORKSPACE;
+  for (int l = 0; l < a.L; ++l) {
+    RpnLossLevel& lv = a.lv[l];
+    lv.cls = cls_scores_host[l]; lv.bbox = bbox_preds_host[l]; lv.iou = iou_preds_host[l];
+    lv.g_cls = grad_cls_host[l]; lv.g_bbox = grad_bbox_host[l]; lv.g_iou = grad_iou_host[l];
+    if (!lv.cls || !lv.bbox || !lv.iou || !lv.g_cls || !lv.g_bbox || !lv.g_iou)
+      return BRCNN_ERR_ARG;
+  }
+  char* ws = (char*)workspace;
+  unsigned int* gt_max = (unsigned int*)ws;
+  float* partials = (float*)(ws + align256((size_t)a.B * a.Gmax * 4));
+  cudaError_t e = cudaMemsetAsync(gt_max, 0, (size_t)a.B * a.Gmax * 4, stream);
+  if (e != cudaSuccess) return (int)e;
+  const size_t smem = (size_t)a.Gmax * 20;
+  dim3 grid(a.blocks_per_img, a.B);
+  if (p->max_gts > 0) {
+    rpn_loss_gtmax_kernel<<<grid, RL_THREADS, smem, stream>>>(a, base_anchors, gt_boxes, num_gt,
+                                                             pad_hw, gt_max);
+    g_launch_count_add(1);
+    BRCNN_CUDA_CHECK_LAST();
+  }
+  rpn_loss_main_kernel<<<grid, RL_THREADS, smem, stream>>>(a, base_anchors, gt_boxes, num_gt,
+                                                          pad_hw, gt_max, partials);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  rpn_loss_reduce_kernel<<<1, RL_THREADS, 0, stream>>>(a, partials, sums);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
+int brcnn_rpn_loss_scale(const brcnn_rpn_loss_params* p, const float* const* raw_cls_host,
+                         const float* const* raw_bbox_host, const float* const* raw_iou_host,
+                         const float* scale, float* const* out_cls_host,
+                         float* const* out_bbox_host, float* const* out_iou_host,
+                         brcnn_stream_t stream_) {
+  RpnLossArgs a;
+  int rc = rpn_loss_args(p, &a);
+  if (rc) return rc;
+  if (!raw_cls_host || !raw_bbox_host || !raw_iou_host || !scale || !out_cls_host ||
+      !out_bbox_host || !out_iou_host)
+    return BRCNN_ERR_ARG;
+  RpnLossScaleArgs s;
+  memset(&s, 0, sizeof(s));
+  s.L = a.L;
+  long long base = 0;
+  for (int kind = 0; kind < 3; ++kind) {
+    const float* const* raw = kind == 0 ? raw_cls_host : (kind == 1 ? raw_bbox_host : raw_iou_host);
+    float* const* out = kind == 0 ? out_cls_host : (kind == 1 ? out_bbox_host : out_iou_host);
+    for (int l = 0; l < a.L; ++l) {
+      if (!raw[l] || !out[l]) return BRCNN_ERR_ARG;
+      const long long n = (long long)a.lv[l].n * a.B * (kind == 1 ? 4 : 1);
+      if (n > 0x7fffffff) return BRCNN_ERR_UNSUPPORTED;
+      s.raw[kind][l] = raw[l]; s.out[kind][l] = out[l]; s.n[kind][l] = (int)n;
+      s.block_base[kind * a.L + l] = (int)base;
+      base += (n + RL_THREADS * 4 - 1) / (RL_THREADS * 4);
+    }
+  }
+  s.block_base[3 * a.L] = (int)base;
+  if (base > 0x7fffffff) return BRCNN_ERR_UNSUPPORTED;
+  rpn_loss_scale_kernel<<<(unsigned)base, RL_THREADS, 0, (cudaStream_t)stream_>>>(s, scale);
   g_launch_count_add(1);
   BRCNN_CUDA_CHECK_LAST();
   return BRCNN_OK;

@@ -18,6 +18,10 @@
 //   * arithmetic is packed: fma.rn.f32x2 (FFMA2) halves the FMA issue slots of both passes, and
 //     the y-fold jumps straight to the row's band [pa, pb] of pooled rows (switch on pa) instead
 //     of seven predicated 8-FMA groups;
+//   * measured dead ends (B200, configs[1], 4096 RoIs): carving rows from a byte ring instead of
+//     fixed 16-pixel slots (1.8x more rows in flight) ran 0.158 ms vs 0.119 ms — the extra
+//     bookkeeping in the single producer warp costs more than the deeper ring gains; slot sizes
+//     of 8 / 10 / 12 / 20 pixels: 0.127 / 0.126 / 0.122 / 0.119 ms;
 //   * the output is written (R, PH, PW, C): a consumer lane holds a channel quad for one pooled
 //     column, so each pooled row leaves as a fully coalesced 512 B streaming store per warp —
 //     no shared-memory staging, no bank conflicts.  ConvFCBBoxHead's first FC consumes that

@@ -19,8 +19,8 @@ from torch.autograd import Function
 from torch.nn.modules.utils import _pair
 
 from . import _lib
-from ._lib import (AssignParams, LossParams, RcnnParams, RcnnWsLayout, RoiParams, RpnParams,
-                   RpnWsLayout, SampleParams, check, ptr_array)
+from ._lib import (AssignParams, LossParams, RcnnParams, RcnnWsLayout, RoiParams, RpnLossParams,
+                   RpnParams, RpnWsLayout, SampleParams, check, ptr_array)
 
 
 def _stream():
@@ -135,6 +135,102 @@ def delta2bbox(rois, deltas, means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.),
                                        max_ratio_f32(wh_ratio_clip), mh, mw,
                                        out.data_ptr(), _stream()), 'brcnn_delta2bbox')
     return out
+
+
+# --------------------------------------------------------------------------
+# RPN loss path (anchor targets + focal / IoU / MSE / BCE losses + gradients)
+# --------------------------------------------------------------------------
+def make_rpn_loss_params(batch, featmap_sizes, strides, num_anchors, max_gts, pos_iou_thr=0.5,
+                         neg_iou_thr=0.5, min_pos_iou=0.0, gamma=0.5, focal_gamma=2.0,
+                         focal_alpha=0.25, loss_cls_weight=1.0, loss_bbox_weight=1.0,
+                         loss_iou_weight=1.0, loss_aug_weight=1.0, wh_ratio_clip=16 / 1000):
+    p = RpnLossParams()
+    p.batch, p.num_levels, p.num_anchors = int(batch), len(featmap_sizes), int(num_anchors)
+    for l, ((h, w), s) in enumerate(zip(featmap_sizes, strides)):
+        sw, sh = _pair(s)
+        p.feat_h[l], p.feat_w[l] = int(h), int(w)
+        p.stride_w[l], p.stride_h[l] = int(sw), int(sh)
+    p.max_gts = int(max_gts)
+    p.pos_iou_thr, p.neg_iou_thr, p.min_pos_iou = float(pos_iou_thr), float(neg_iou_thr), float(min_pos_iou)
+    p.gamma, p.focal_gamma, p.focal_alpha = float(gamma), float(focal_gamma), float(focal_alpha)
+    p.loss_cls_weight, p.loss_bbox_weight = float(loss_cls_weight), float(loss_bbox_weight)
+    p.loss_iou_weight, p.loss_aug_weight = float(loss_iou_weight), float(loss_aug_weight)
+    p.max_ratio = max_ratio_f32(wh_ratio_clip)
+    return p
+
+
+class _RpnLossFunction(Function):
+    """Returns 3L scalar losses (L x cls, L x bbox, L x iou) + the raw sums tensor.
+
+    One fused all-reduce of the two normalisers replaces the reference's two
+    ``reduce_mean(...).item()`` round trips (atss_rpn_head.py:441-444, 458-460); the
+    division happens on the device, the step stays free of host syncs."""
+
+    @staticmethod
+    def forward(ctx, params, base_anchors, gt_boxes, num_gt, pad_hw, *heads):
+        lib = _lib.load()
+        L = params.num_levels
+        assert len(heads) == 3 * L
+        cls = [_f32c(t, 'cls_scores') for t in heads[:L]]
+        box = [_f32c(t, 'bbox_preds') for t in heads[L:2 * L]]
+        iou = [_f32c(t, 'iou_preds') for t in heads[2 * L:]]
+        dev = cls[0].device
+        B, A = params.batch, params.num_anchors
+        for l in range(L):
+            hw = (params.feat_h[l], params.feat_w[l])
+            assert tuple(cls[l].shape) == (B, A) + hw and tuple(box[l].shape) == (B, 4 * A) + hw
+            assert tuple(iou[l].shape) == (B, A) + hw
+        base_anchors = _f32c(base_anchors, 'base_anchors')
+        gt_boxes, pad_hw = _f32c(gt_boxes, 'gt_boxes'), _f32c(pad_hw, 'pad_hw')
+        num_gt = num_gt.to(torch.int32).contiguous()
+        sums = torch.empty((3 * L + 2,), dtype=torch.float32, device=dev)
+        raw = [torch.empty_like(t) for t in cls + box + iou]
+        ws = _ws(lib.brcnn_rpn_loss_workspace_bytes(params), dev)
+        check(lib.brcnn_rpn_loss_forward(
+            params, ptr_array([t.data_ptr() for t in cls]), ptr_array([t.data_ptr() for t in box]),
+            ptr_array([t.data_ptr() for t in iou]), base_anchors.data_ptr(), gt_boxes.data_ptr(),
+            num_gt.data_ptr(), pad_hw.data_ptr(), sums.data_ptr(),
+            ptr_array([t.data_ptr() for t in raw[:L]]), ptr_array([t.data_ptr() for t in raw[L:2 * L]]),
+            ptr_array([t.data_ptr() for t in raw[2 * L:]]), ws.data_ptr(), ws.numel(), _stream()),
+            'brcnn_rpn_loss_forward')
+        # normalisers: reduce_mean over the ranks, clamp at 1 (one fused all-reduce, on device)
+        norm = sums[3 * L:].clone()
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(norm.div_(dist.get_world_size()), op=dist.ReduceOp.SUM)
+        norm = norm.clamp_(min=1.0)                  # [num_total_samples, bbox_avg_factor]
+        inv = torch.cat([norm[0:1].expand(L), norm[1:2].expand(L), norm[0:1].expand(L)]).reciprocal()
+        losses = sums[:3 * L] * inv
+        ctx.save_for_backward(inv, *raw)
+        ctx.params = params
+        ctx.mark_non_differentiable(sums)
+        return (*losses.unbind(0), sums)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = _lib.load()
+        inv, *raw = ctx.saved_tensors
+        p = ctx.params
+        L = p.num_levels
+        up = torch.stack([g if g is not None else inv.new_zeros(()) for g in grads[:3 * L]])
+        scale = (up.to(inv) * inv).contiguous()
+        out = [torch.empty_like(t) for t in raw]
+        check(lib.brcnn_rpn_loss_scale(
+            p, ptr_array([t.data_ptr() for t in raw[:L]]), ptr_array([t.data_ptr() for t in raw[L:2 * L]]),
+            ptr_array([t.data_ptr() for t in raw[2 * L:]]), scale.data_ptr(),
+            ptr_array([t.data_ptr() for t in out[:L]]), ptr_array([t.data_ptr() for t in out[L:2 * L]]),
+            ptr_array([t.data_ptr() for t in out[2 * L:]]), _stream()), 'brcnn_rpn_loss_scale')
+        return (None, None, None, None, None, *out)
+
+
+def rpn_loss(params, cls_scores, bbox_preds, iou_preds, base_anchors, gt_boxes, num_gt, pad_hw):
+    """Fused ATSSRPNHead.loss (atss=False).  gt_boxes (B,max_gts,4) zero padded + num_gt (B,)
+    int32, pad_hw (B,2) = img_meta['pad_shape'][:2].  Returns (loss_cls [L], loss_bbox [L],
+    loss_iou [L], sums (3L+2,)): lists of 0-dim tensors carrying gradients to the head outputs."""
+    L = params.num_levels
+    out = _RpnLossFunction.apply(params, base_anchors, gt_boxes, num_gt, pad_hw, *cls_scores,
+                                 *bbox_preds, *iou_preds)
+    return list(out[:L]), list(out[L:2 * L]), list(out[2 * L:3 * L]), out[3 * L]
 
 
 # --------------------------------------------------------------------------

@@ -10,8 +10,13 @@ stays on torch/cuDNN as the north star says; parameter names match the
 reference so its checkpoints load (``rpn_convs.N.conv/gn``, ``rpn_cls``,
 ``rpn_reg``, ``rpn_iou``, ``scales.N.scale``).
 
-Not ported: the RPN loss (`loss`, `loss_single`,
-`get_targets`, :299-464,505-686).
+``loss`` (:299-464, with ``get_targets`` :505-603 and the AnchorHead target code it
+dispatches to when ``atss=False``) is B200-native as well: anchor targets (MaxIoUAssigner with
+match_low_quality + PseudoSampler), sigmoid focal loss, IoU-log + MSE regression losses and
+the BCE IoU branch run in three launches (``brcnn_rpn_loss_forward``) with hand-derived
+gradients; the two ``reduce_mean(...).item()`` normalisers become one device-side fused
+all-reduce.  Unsupported variants (atss=True, VarifocalLoss, GHM, reg_decoded_bbox=False)
+raise NotImplementedError at the first ``loss`` call.
 """
 import math
 from collections import namedtuple
@@ -208,17 +213,86 @@ class ATSSRPNHead(nn.Module):
             return self.get_bboxes_padded(cls_scores, bbox_preds, iou_preds, img_metas)
         return self.get_bboxes(cls_scores, bbox_preds, iou_preds, img_metas)
 
-    def loss(self, *args, **kwargs):
-        raise NotImplementedError('the RPN loss is outside the ported hot path '
-                                  '(SURVEY.md §8f rank 2)')
+    # ------------------------------------------------------------------ loss
+    def _loss_supported(self):
+        tc = self.train_cfg
+        a = tc.get('assigner', {}) if tc is not None else {}
+        problems = []
+        if self.atss:
+            problems.append('atss=True (ATSSAssigner)')
+        if not self.reg_decoded_bbox:
+            problems.append('reg_decoded_bbox=False')
+        if self.num_classes != 1:
+            problems.append('num_classes != 1')
+        for name, want in (('loss_cls', 'FocalLoss'), ('loss_bbox', 'IoULoss'),
+                           ('loss_centerness', 'CrossEntropyLoss')):
+            if type(getattr(self, name)).__name__ != want:
+                problems.append(f'{name}={type(getattr(self, name)).__name__}')
+        if self.with_aug_loss and type(self.aug_loss).__name__ != 'MSELoss':
+            problems.append(f'aug_reg_loss={type(self.aug_loss).__name__}')
+        if self.loss_bbox.cfg.get('mode', 'log') != 'log' or self.loss_bbox.cfg.get('linear', False):
+            problems.append('IoULoss mode != log')
+        if tc is None:
+            problems.append('train_cfg is None')
+        else:
+            if a.get('type') != 'MaxIoUAssigner' or not a.get('match_low_quality', True) \
+                    or not a.get('gt_max_assign_all', True) or a.get('ignore_iof_thr', -1) > 0 \
+                    or not isinstance(a.get('neg_iou_thr'), (int, float)):
+                problems.append(f'assigner {dict(a)}')
+            if tc.get('sampler', {}).get('type') != 'PseudoSampler':
+                problems.append(f"sampler {tc.get('sampler')}")
+            if tc.get('allowed_border', -1) >= 0 or tc.get('pos_weight', -1) > 0:
+                problems.append('allowed_border >= 0 / pos_weight > 0')
+        if tuple(self.bbox_coder.means) != (0., 0., 0., 0.) or \
+                tuple(self.bbox_coder.stds) != (1., 1., 1., 1.):
+            problems.append('bbox_coder means/stds other than 0/1')
+        return problems
+
+    def loss(self, cls_scores, bbox_preds, iou_preds, gt_bboxes, img_metas, gt_bboxes_ignore=None):
+        """Reference signature (:405-464).  Returns dict(loss_rpn_cls, loss_rpn_bbox,
+        loss_rpn_iou), each a list with one 0-dim tensor per pyramid level."""
+        problems = self._loss_supported()
+        if gt_bboxes_ignore is not None and any(g is not None and len(g) for g in gt_bboxes_ignore):
+            problems.append('gt_bboxes_ignore')
+        if problems:
+            raise NotImplementedError('the fused RPN loss covers the ATSSRPNHead settings of '
+                                      'configs/boosting_rcnn/*_utdac / *_coco; unsupported: '
+                                      + '; '.join(problems))
+        B = cls_scores[0].size(0)
+        assert len(img_metas) == B and len(gt_bboxes) == B
+        dev = cls_scores[0].device
+        sizes = [tuple(t.shape[-2:]) for t in cls_scores]
+        assert len(sizes) == len(self.anchor_generator.strides)
+        img_shapes = [tuple(m['img_shape'][:2]) for m in img_metas]
+        base, _ = self._constants(dev, img_shapes)
+        Gs = [int(g.size(0)) for g in gt_bboxes]
+        Gmax = max(1, max(Gs))
+        gtb = torch.zeros((B, Gmax, 4), dtype=torch.float32, device=dev)
+        for b in range(B):
+            if Gs[b]:
+                gtb[b, :Gs[b]] = gt_bboxes[b][:, :4].float()
+        num_gt = torch.tensor(Gs, dtype=torch.int32).to(dev, non_blocking=True)
+        pad_hw = torch.tensor([[m['pad_shape'][0], m['pad_shape'][1]] for m in img_metas],
+                              dtype=torch.float32).to(dev, non_blocking=True)
+        a = self.train_cfg.assigner
+        p = ops.make_rpn_loss_params(
+            B, sizes, self.anchor_generator.strides, self.num_anchors, Gmax, a.pos_iou_thr,
+            a.neg_iou_thr, a.get('min_pos_iou', 0.0), self.gamma,
+            self.loss_cls.cfg.get('gamma', 2.0), self.loss_cls.cfg.get('alpha', 0.25),
+            self.loss_cls.loss_weight, self.loss_bbox.loss_weight, self.loss_centerness.loss_weight,
+            self.aug_loss.loss_weight if self.with_aug_loss else 0.0)
+        l_cls, l_bbox, l_iou, _ = ops.rpn_loss(p, cls_scores, bbox_preds, iou_preds, base, gtb,
+                                               num_gt, pad_hw)
+        if not self.with_aug_loss:
+            # without aug_reg_loss the reference does not halve loss_bbox (:346-348)
+            l_bbox = [v * 2 for v in l_bbox]
+        return dict(loss_rpn_cls=l_cls, loss_rpn_bbox=l_bbox, loss_rpn_iou=l_iou)
 
     def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None,
                       proposal_cfg=None, **kwargs):
-        """Proposal half of atss_rpn_head.py:270-294.  The loss half is not
-        ported; an empty loss dict is returned so the R-CNN stage can be
-        trained/benchmarked on B200-generated proposals."""
+        """atss_rpn_head.py:270-294: losses, and proposals when ``proposal_cfg`` is given."""
         outs = self(x)
-        losses = dict()
+        losses = self.loss(*outs, gt_bboxes, img_metas, gt_bboxes_ignore=gt_bboxes_ignore)
         if proposal_cfg is None:
             return losses
         return losses, self.get_bboxes(*outs, img_metas, cfg=proposal_cfg)

@@ -108,6 +108,56 @@ int brcnn_delta2bbox(const float* rois, const float* deltas, int32_t n,
                      float max_w, float* out, brcnn_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * (1b) RPN loss path: anchor targets + losses + gradients
+ * replaces ATSSRPNHead.loss / loss_single / get_targets with atss=False
+ *   (mmdet/models/dense_heads/atss_rpn_head.py:299-464, 505-603),
+ *   AnchorHead.get_anchors / _get_targets_single (anchor_head.py:126-265),
+ *   AnchorGenerator.grid_anchors / valid_flags (anchor_generator.py:338-434),
+ *   MaxIoUAssigner with match_low_quality=True + PseudoSampler (the RPN train_cfg of
+ *   configs/boosting_rcnn), FocalLoss (mmcv sigmoid_focal_loss, losses/focal_loss.py:86),
+ *   IoULoss(mode='log'), MSELoss (aug_reg_loss), CrossEntropyLoss(use_sigmoid=True) on the IoU
+ *   logit, weight_reduce_loss, for reg_decoded_bbox=True, num_classes=1, pos_weight=-1,
+ *   allowed_border=-1, target means 0 / stds 1.
+ * ---------------------------------------------------------------------- */
+typedef struct brcnn_rpn_loss_params {
+  int32_t batch, num_levels, num_anchors;
+  int32_t feat_h[BRCNN_MAX_LEVELS], feat_w[BRCNN_MAX_LEVELS];
+  int32_t stride_w[BRCNN_MAX_LEVELS], stride_h[BRCNN_MAX_LEVELS];
+  int32_t max_gts;                 /* row capacity of gt_boxes per image (<= 1024)    */
+  float pos_iou_thr, neg_iou_thr, min_pos_iou;   /* train_cfg.rpn.assigner              */
+  float gamma;                     /* ATSSRPNHead.gamma: bbox weight = iou_target**gamma */
+  float focal_gamma, focal_alpha;  /* loss_cls                                        */
+  float loss_cls_weight, loss_bbox_weight, loss_iou_weight, loss_aug_weight;
+  float max_ratio;                 /* |ln(wh_ratio_clip)| as fp32                     */
+} brcnn_rpn_loss_params;
+
+size_t brcnn_rpn_loss_workspace_bytes(const brcnn_rpn_loss_params* p);
+
+/* sums: float[3L + 2] = L x sum of weighted focal terms | L x 0.5*(IoU-log + MSE) sums |
+ *   L x BCE sums | num_total_pos | sum of iou_target -- all UN-normalised: the caller divides
+ *   by max(reduce_mean(num_total_pos), 1) resp. max(reduce_mean(sum iou_target), 1)
+ *   (atss_rpn_head.py:441-444, 458-460) on the device, after one fused all-reduce.
+ * grad_*: un-normalised gradients, same shapes as the inputs, every element written.
+ * pad_hw: (B,2) img_meta['pad_shape'][:2] (valid flags); gt_boxes (B,max_gts,4) + num_gt (B). */
+int brcnn_rpn_loss_forward(const brcnn_rpn_loss_params* p,
+                           const float* const* cls_scores_host,  /* host array[L] (B,A,H,W)   */
+                           const float* const* bbox_preds_host,  /* host array[L] (B,4A,H,W)  */
+                           const float* const* iou_preds_host,   /* host array[L] (B,A,H,W)   */
+                           const float* base_anchors,            /* (L,A,4)                   */
+                           const float* gt_boxes, const int32_t* num_gt, const float* pad_hw,
+                           float* sums, float* const* grad_cls_host, float* const* grad_bbox_host,
+                           float* const* grad_iou_host, void* workspace, size_t workspace_bytes,
+                           brcnn_stream_t stream);
+
+/* backward: out = raw * scale[kind * L + level], kind 0 = cls, 1 = bbox, 2 = iou; `scale` is a
+ * DEVICE array of 3L floats (upstream gradient / normaliser).  out may alias raw. */
+int brcnn_rpn_loss_scale(const brcnn_rpn_loss_params* p, const float* const* raw_cls_host,
+                         const float* const* raw_bbox_host, const float* const* raw_iou_host,
+                         const float* scale, float* const* out_cls_host,
+                         float* const* out_bbox_host, float* const* out_iou_host,
+                         brcnn_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * (2) NMS operators — stand-ins for mmcv `_ext.nms` and the Python wrappers
  * mmcv.ops.nms / mmcv.ops.batched_nms (call sites atss_rpn_head.py:756,
  * mmdet/core/post_processing/bbox_nms.py:86).  Order: score descending,

@@ -418,3 +418,182 @@ def rcnn_train_prep(proposals, gt_bboxes, gt_labels, num_classes, pos_iou_thr, n
     for k in ('rois', 'labels', 'label_weights', 'bbox_targets', 'bbox_weights', 'prior'):
         out[k] = np.concatenate(out[k], 0)
     return out
+
+
+# ---------------------------------------------------------------------------
+# RPN loss path: anchor targets + focal / IoU / MSE / BCE losses and
+# their gradients, numpy restatement of ATSSRPNHead.loss with atss=False
+# (mmdet/models/dense_heads/atss_rpn_head.py:299-464,505-603; anchor_head.py:126-265).
+# Assignment runs in fp32 exactly like the reference (IoU thresholds and the
+# `overlaps == gt_max_overlaps` test of match_low_quality are bit-sensitive); the loss
+# arithmetic runs in float64 (the parity bar on values / gradients is 1e-5 relative).
+# ---------------------------------------------------------------------------
+def grid_anchors_level(base, stride, H, W):
+    """AnchorGenerator.single_level_grid_anchors (anchor_generator.py:338-381):
+    anchor[(y*W+x)*A + a] = base[a] + [x*sw, y*sh, x*sw, y*sh], fp32."""
+    sw, sh = (stride, stride) if np.isscalar(stride) else stride
+    xs = (np.arange(W, dtype=np.float32) * np.float32(sw))
+    ys = (np.arange(H, dtype=np.float32) * np.float32(sh))
+    sx, sy = np.meshgrid(xs, ys)
+    shifts = np.stack([sx.ravel(), sy.ravel(), sx.ravel(), sy.ravel()], 1).astype(np.float32)
+    return (shifts[:, None, :] + _f(base)[None, :, :]).reshape(-1, 4).astype(np.float32)
+
+
+def valid_flags_level(H, W, A, stride, pad_hw):
+    """AnchorGenerator.valid_flags / single_level_valid_flags (anchor_generator.py:383-434)."""
+    sw, sh = (stride, stride) if np.isscalar(stride) else stride
+    vh = min(int(np.ceil(pad_hw[0] / sh)), H)
+    vw = min(int(np.ceil(pad_hw[1] / sw)), W)
+    vy = np.arange(H) < vh
+    vx = np.arange(W) < vw
+    return np.repeat((vy[:, None] & vx[None, :]).ravel(), A)
+
+
+def rpn_anchor_targets(gt_bboxes, img_metas, base_anchors, strides, sizes, pos_iou_thr=0.5,
+                       neg_iou_thr=0.5, min_pos_iou=0.0, match_low_quality=True):
+    """get_anchors + get_targets/_get_targets_single with PseudoSampler, reg_decoded_bbox=True,
+    num_classes=1, allowed_border=-1.  Returns per image: anchors (n,4), labels (n,) in
+    {0 fg, 1 bg}, label_weights (n,), assigned gt index (n,) (-1 where not positive)."""
+    A = base_anchors.shape[1]
+    out = []
+    for gts, meta in zip(gt_bboxes, img_metas):
+        anchors = np.concatenate([grid_anchors_level(base_anchors[l], strides[l], H, W)
+                                  for l, (H, W) in enumerate(sizes)], 0)
+        valid = np.concatenate([valid_flags_level(H, W, A, strides[l], meta['pad_shape'][:2])
+                                for l, (H, W) in enumerate(sizes)], 0)
+        n = anchors.shape[0]
+        labels = np.full((n,), 1, dtype=np.int64)          # unmap fill = num_classes (bg)
+        lw = np.zeros((n,), np.float32)
+        assigned = np.full((n,), -1, dtype=np.int64)
+        if valid.any():
+            gi, _ = max_iou_assign(anchors[valid], gts, pos_iou_thr, neg_iou_thr, min_pos_iou,
+                                   match_low_quality)
+            vi = np.nonzero(valid)[0]
+            pos, neg = vi[gi > 0], vi[gi == 0]
+            labels[pos] = 0
+            lw[pos] = 1.0
+            lw[neg] = 1.0
+            assigned[pos] = gi[gi > 0] - 1
+        out.append(dict(anchors=anchors, labels=labels, label_weights=lw, assigned=assigned))
+    return out
+
+
+def rpn_loss(cls, box, iou, gt_bboxes, img_metas, base_anchors, strides, gamma=0.5,
+             focal_gamma=2.0, focal_alpha=0.25, w_cls=1.0, w_bbox=1.0, w_iou=1.0, w_aug=1.0,
+             pos_iou_thr=0.5, neg_iou_thr=0.5, min_pos_iou=0.0, wh_ratio_clip=16 / 1000,
+             world_size=1, other_ranks_num_pos=0.0, other_ranks_iou_sum=0.0):
+    """ATSSRPNHead.loss / loss_single.  cls[l] (B,A,H,W), box[l] (B,4A,H,W), iou[l] (B,A,H,W).
+    Returns dict: loss_rpn_cls / loss_rpn_bbox / loss_rpn_iou (L,) float32, grad_cls / grad_box /
+    grad_iou (lists, gradients of the sum of all 3L losses), num_pos, iou_sum.
+    `other_ranks_*` + `world_size` model reduce_mean (atss_rpn_head.py:441,459)."""
+    L = len(cls)
+    B, A = cls[0].shape[0], cls[0].shape[1]
+    sizes = [tuple(c.shape[-2:]) for c in cls]
+    tg = rpn_anchor_targets(gt_bboxes, img_metas, base_anchors, strides, sizes, pos_iou_thr,
+                            neg_iou_thr, min_pos_iou, True)
+    num_pos = float(sum(int((t['labels'] == 0).sum()) for t in tg))
+    nts = max((num_pos + other_ranks_num_pos) / world_size, 1.0)
+    M = float(np.float32(np.abs(np.log(wh_ratio_clip))))
+    EPS, eps = 1e-12, 1e-6
+    lvl_off = np.cumsum([0] + [h * w * A for h, w in sizes])
+    res = dict(loss_rpn_cls=np.zeros(L), loss_rpn_bbox=np.zeros(L), loss_rpn_iou=np.zeros(L),
+               grad_cls=[], grad_box=[], grad_iou=[])
+    raw_bbox, iou_sum_l = [], []
+    for l, (H, W) in enumerate(sizes):
+        sl = slice(lvl_off[l], lvl_off[l + 1])
+        x = np.stack([cls[l][b].transpose(1, 2, 0).reshape(-1) for b in range(B)]).astype(np.float64)
+        d = np.stack([box[l][b].transpose(1, 2, 0).reshape(-1, 4) for b in range(B)]).astype(np.float64)
+        u = np.stack([iou[l][b].transpose(1, 2, 0).reshape(-1) for b in range(B)]).astype(np.float64)
+        lab = np.stack([t['labels'][sl] for t in tg])
+        lw = np.stack([t['label_weights'][sl] for t in tg]).astype(np.float64)
+        anc = np.stack([t['anchors'][sl] for t in tg]).astype(np.float64)
+        # ---- classification: py_sigmoid_focal_loss (focal_loss.py:13-58) ----
+        t = (lab == 0).astype(np.float64)
+        p = 1.0 / (1.0 + np.exp(-x))
+        bce = np.maximum(x, 0) - x * t + np.log1p(np.exp(-np.abs(x)))
+        pt = (1 - p) * t + p * (1 - t)
+        aw = focal_alpha * t + (1 - focal_alpha) * (1 - t)
+        fw = aw * pt ** focal_gamma
+        res['loss_rpn_cls'][l] = w_cls * (bce * fw * lw).sum() / nts
+        dfw = aw * focal_gamma * pt ** (focal_gamma - 1) * (1 - 2 * t) * p * (1 - p)
+        g_cls = w_cls * lw * (fw * (p - t) + bce * dfw) / nts
+        # ---- positives ----
+        g_box = np.zeros_like(d)
+        g_iou = np.zeros_like(u)
+        pm = lab == 0
+        lb_sum = 0.0
+        isum = 0.0
+        if pm.any():
+            gt = np.stack([np.where(t_['assigned'][sl, None] >= 0,
+                                    _f(g_).reshape(-1, 4)[np.maximum(t_['assigned'][sl], 0)]
+                                    if len(g_) else np.zeros((sl.stop - sl.start, 4), np.float32),
+                                    0.0) for t_, g_ in zip(tg, gt_bboxes)]).astype(np.float64)
+            a_, d_, g_ = anc[pm], d[pm], gt[pm]
+            px, py = (a_[:, 0] + a_[:, 2]) * 0.5, (a_[:, 1] + a_[:, 3]) * 0.5
+            pw, ph = a_[:, 2] - a_[:, 0], a_[:, 3] - a_[:, 1]
+            dwc, dhc = np.clip(d_[:, 2], -M, M), np.clip(d_[:, 3], -M, M)
+            gw, gh = pw * np.exp(dwc), ph * np.exp(dhc)
+            gx, gy = px + pw * d_[:, 0], py + ph * d_[:, 1]
+            x1, y1, x2, y2 = gx - gw * 0.5, gy - gh * 0.5, gx + gw * 0.5, gy + gh * 0.5
+            # aligned IoU (iou2d_calculator.py:214-253) and its derivative
+            ltx, lty = np.maximum(x1, g_[:, 0]), np.maximum(y1, g_[:, 1])
+            rbx, rby = np.minimum(x2, g_[:, 2]), np.minimum(y2, g_[:, 3])
+            iwr, ihr = rbx - ltx, rby - lty
+            iw, ih = np.maximum(iwr, 0), np.maximum(ihr, 0)
+            inter = iw * ih
+            ap = (x2 - x1) * (y2 - y1)
+            ag = (g_[:, 2] - g_[:, 0]) * (g_[:, 3] - g_[:, 1])
+            union = ap + ag - inter
+            uc = np.maximum(union, eps)
+            iou_t = inter / uc                                  # iou_target (detached) == loss IoU
+            wgt = np.maximum(iou_t ** gamma, EPS)
+            # encoded targets (bbox2delta) and the MSE "aug" loss
+            tx, ty = (g_[:, 0] + g_[:, 2]) * 0.5, (g_[:, 1] + g_[:, 3]) * 0.5
+            tw, th = g_[:, 2] - g_[:, 0], g_[:, 3] - g_[:, 1]
+            with np.errstate(divide='ignore', invalid='ignore'):
+                enc = np.stack([(tx - px) / pw, (ty - py) / ph, np.log(tw / pw), np.log(th / ph)], 1)
+            diff = d_ - enc
+            l_aug = w_aug * (wgt[:, None] * diff ** 2).sum()
+            iou_c = np.maximum(iou_t, eps)
+            l_iou = w_bbox * (wgt * -np.log(iou_c)).sum()
+            lb_sum = 0.5 * (l_iou + l_aug)
+            isum = iou_t.sum()
+            # d(-log iou)/d box
+            sel = lambda a, b: np.where(a > b, 1.0, np.where(a == b, 0.5, 0.0))
+            dl_x1, dl_y1 = sel(x1, g_[:, 0]), sel(y1, g_[:, 1])           # d ltx/d x1 ...
+            dr_x2, dr_y2 = sel(g_[:, 2], x2), sel(g_[:, 3], y2)           # d rbx/d x2 ...
+            mw, mh = (iwr >= 0).astype(np.float64), (ihr >= 0).astype(np.float64)
+            di = [-ih * mw * dl_x1, -iw * mh * dl_y1, ih * mw * dr_x2, iw * mh * dr_y2]
+            da = [-(y2 - y1), -(x2 - x1), (y2 - y1), (x2 - x1)]
+            um = sel(union, eps)
+            coef = -(iou_t >= eps).astype(np.float64) / iou_c * wgt * w_bbox * 0.5
+            gb = [coef * (di[k] / uc - inter * um * (da[k] - di[k]) / uc ** 2) for k in range(4)]
+            cw_, ch_ = (np.abs(d_[:, 2]) <= M), (np.abs(d_[:, 3]) <= M)
+            gd = np.stack([(gb[0] + gb[2]) * pw, (gb[1] + gb[3]) * ph,
+                           (gb[2] - gb[0]) * 0.5 * gw * cw_, (gb[3] - gb[1]) * 0.5 * gh * ch_], 1)
+            gd += 0.5 * w_aug * 2 * wgt[:, None] * diff
+            g_box[pm] = gd
+            # centerness/IoU branch: BCE with logits against iou_target
+            xu = u[pm]
+            res['loss_rpn_iou'][l] = w_iou * (np.maximum(xu, 0) - xu * iou_t +
+                                              np.log1p(np.exp(-np.abs(xu)))).sum() / nts
+            g_iou[pm] = w_iou * (1.0 / (1.0 + np.exp(-xu)) - iou_t) / nts
+        raw_bbox.append((lb_sum, g_box))
+        iou_sum_l.append(isum)
+        res['grad_cls'].append(g_cls)
+        res['grad_iou'].append(g_iou)
+    iou_sum = float(sum(iou_sum_l))
+    baf = max((iou_sum + other_ranks_iou_sum) / world_size, 1.0)
+    for l, (H, W) in enumerate(sizes):
+        lb, gbx = raw_bbox[l]
+        res['loss_rpn_bbox'][l] = lb / baf
+        gbx = gbx / baf
+        to_nchw = lambda g, c: np.stack([g[b].reshape(H, W, A * c).transpose(2, 0, 1)
+                                         for b in range(B)]).astype(np.float32)
+        res['grad_box'].append(to_nchw(gbx, 4))
+        res['grad_cls'][l] = to_nchw(res['grad_cls'][l], 1)
+        res['grad_iou'][l] = to_nchw(res['grad_iou'][l], 1)
+    for k in ('loss_rpn_cls', 'loss_rpn_bbox', 'loss_rpn_iou'):
+        res[k] = res[k].astype(np.float32)
+    res['num_pos'], res['iou_sum'], res['targets'] = num_pos, iou_sum, tg
+    return res

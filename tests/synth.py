@@ -105,3 +105,45 @@ def rcnn_train_case(case, batch=3, num_classes=80):
         sc = np.sort(rng.rand(len(bx)).astype(np.float32))[::-1].copy()
         plist.append(np.concatenate([bx, sc[:, None]], 1).astype(np.float32))
     return gts, labels, plist
+
+
+RPN_LOSS_CASES = ('basic', 'isolated_gt', 'no_gt_image', 'partial_valid')
+
+
+def rpn_loss_case(case, batch=2, pad_hw=(128, 160), num_anchors=9):
+    """Inputs of the RPN loss path (ATSSRPNHead.loss, atss_rpn_head.py:405-464) for one named
+    case: RPN head outputs per level (B,A,H,W)/(B,4A,H,W)/(B,A,H,W), GT boxes per image and
+    img_metas (img_shape, pad_shape).
+      basic         : 3-5 GTs per image of mixed sizes
+      isolated_gt   : one extra GT outside every anchor's reach in image 0 — with
+                      min_pos_iou=0 and match_low_quality=True it claims every anchor whose
+                      overlap with it equals its (zero) maximum (max_iou_assigner.py:187-202)
+      no_gt_image   : image 1 has no GT (all anchors negative)
+      partial_valid : image 1's own pad_shape is smaller than the batch pad, so part of each
+                      level is flagged invalid (anchor_generator.py:383-434)"""
+    assert case in RPN_LOSS_CASES
+    seed = 500 + RPN_LOSS_CASES.index(case)
+    rng = np.random.RandomState(seed)
+    sizes = featmap_sizes(*pad_hw)
+    cls, box, iou = rpn_outputs(batch, sizes, num_anchors, seed=seed, cls_std=1.5, box_std=0.3)
+    img_hw = (pad_hw[0] - 6, pad_hw[1] - 3)
+    gts, metas = [], []
+    for b in range(batch):
+        n = int(rng.randint(3, 6))
+        wh = np.exp(rng.uniform(np.log(12), np.log(100), (n, 2)))
+        ctr = rng.uniform(0.15, 0.85, (n, 2)) * [img_hw[1], img_hw[0]]
+        g = np.concatenate([ctr - wh / 2, ctr + wh / 2], 1)
+        g[:, 0::2] = g[:, 0::2].clip(0, img_hw[1])
+        g[:, 1::2] = g[:, 1::2].clip(0, img_hw[0])
+        if case == 'isolated_gt' and b == 0:
+            g = np.concatenate([g[:2], [[900., 900., 910., 910.]], g[2:]], 0)
+        if case == 'no_gt_image' and b == 1:
+            g = np.zeros((0, 4))
+        gts.append(g.astype(np.float32))
+        pad = pad_hw
+        if case == 'partial_valid' and b == 1:
+            pad = (pad_hw[0] - 32, pad_hw[1] - 48)
+        metas.append(dict(img_shape=(min(img_hw[0], pad[0]), min(img_hw[1], pad[1]), 3),
+                          pad_shape=(pad[0], pad[1], 3)))
+    return dict(cls=cls, box=box, iou=iou, gt_bboxes=gts, img_metas=metas, sizes=sizes,
+                num_anchors=num_anchors)

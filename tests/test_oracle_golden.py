@@ -355,3 +355,43 @@ def test_python_fallback_train_prep_equals_executed_reference(case):
     np.testing.assert_array_equal(bw.numpy(), g[f'{case}/bbox_weights'])
     np.testing.assert_array_equal(torch.cat(priors).numpy(), g[f'{case}/prior'])
     np.testing.assert_allclose(bt.numpy(), g[f'{case}/bbox_targets'], rtol=1e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------
+# RPN loss path: oracle vs goldens produced by executing the reference's
+# ATSSRPNHead.loss / loss_single / get_targets + its loss modules
+# (tests/golden/make_golden_rpn_loss.py)
+# ---------------------------------------------------------------------------
+RPN_LOSS_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                             'reference_golden_rpn_loss.npz')
+
+
+def _rpn_loss_oracle(case):
+    c = synth.rpn_loss_case(case)
+    gen = AnchorGenerator(strides=[8, 16, 32, 64, 128], ratios=[0.5, 1.0, 2.0],
+                          octave_base_scale=4, scales_per_octave=3)
+    return c, oracle.rpn_loss(c['cls'], c['box'], c['iou'], c['gt_bboxes'], c['img_metas'],
+                              gen.base_anchor_table().numpy(), synth.STRIDES)
+
+
+def _rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max()) / \
+        max(float(np.abs(b).max()), 1e-12)
+
+
+@pytest.mark.parametrize('case', synth.RPN_LOSS_CASES)
+def test_rpn_loss_oracle_equals_executed_reference(case):
+    g = np.load(RPN_LOSS_GOLD)
+    c, o = _rpn_loss_oracle(case)
+    for k in ('loss_rpn_cls', 'loss_rpn_bbox', 'loss_rpn_iou'):
+        np.testing.assert_allclose(o[k], g[f'{case}/{k}'], rtol=1e-5, atol=1e-7, err_msg=k)
+    for l in range(len(c['cls'])):
+        for name, key in (('grad_cls', 'grad_cls'), ('grad_box', 'grad_box'), ('grad_iou', 'grad_iou')):
+            ref = g[f'{case}/{key}_{l}']
+            if np.abs(ref).max() == 0:
+                assert np.abs(o[name][l]).max() == 0
+            else:
+                assert _rel(o[name][l], ref) <= 1e-5, (name, l, _rel(o[name][l], ref))
+    if case == 'isolated_gt':
+        # the far-away GT (index 2 of image 0) claims every anchor it shares its zero maximum with
+        assert (o['targets'][0]['assigned'] == 2).sum() > 1000
