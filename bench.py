@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument('--cpu-images', type=int, default=0,
                     help='images in the CPU-baseline sample (0: one per host thread, <= 16)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--stress-input', default='boxes', choices=['boxes', 'clustered', 'anchors'],
+                    help='--mode stress: random boxes (SURVEY §8d cfg 5), the clustered variant, '
+                         'or RPN outputs on the COCO pyramid')
     ap.add_argument('--no-train-record', action='store_true',
                     help='skip the configs[2] training-step sub-record of the default line')
     ap.add_argument('--strong-total', type=int, default=16,
@@ -342,7 +345,9 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
                                                       seed=4321 + rank, pin=False)
     metas = img_metas_for(B, geom)
     feats = [t.to(dev).requires_grad_(True) for t in h_feats]
-    cls, box, iou = ([t.to(dev) for t in ts] for ts in (h_cls, h_box, h_iou))
+    # the RPN head outputs are leaves here (the conv tower is torch/cuDNN, outside the path):
+    # the RPN loss sends its gradients to them
+    cls, box, iou = ([t.to(dev).requires_grad_(True) for t in ts] for ts in (h_cls, h_box, h_iou))
     rng = np.random.RandomState(77 + rank)
     gts, labels = [], []
     for b in range(B):
@@ -363,12 +368,19 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
     def step(comm=True):
         for p in params:
             p.grad = None
-        for f in feats:
+        for f in feats + cls + box + iou:
             f.grad = None
+        # RPN loss on the head outputs (anchor targets, focal / IoU / MSE / BCE, gradients): its
+        # two reduce_mean normalisers are one fused device-side all-reduce inside ops.rpn_loss
+        rpn_losses = rpn_head.loss(cls, box, iou, gts, metas)
         with torch.no_grad():   # padded proposals stay on the device (no sync)
             plist = rpn_head.get_bboxes_padded(cls, box, iou, metas, cfg=prop_cfg)
         losses = roi_head.forward_train(feats, metas, plist, gts, labels)
-        (losses['loss_cls'] + losses['loss_bbox']).backward()
+        total = losses['loss_cls'] + losses['loss_bbox']
+        for v in rpn_losses.values():
+            total = total + torch.stack(v).sum()
+        total.backward()
+        losses = dict(losses, **{k: torch.stack(v).sum() for k, v in rpn_losses.items()})
         if world > 1 and comm:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -402,8 +414,9 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
     if rank != 0:
         return None
     rec = {
-        'workload': f'boosting_rcnn {cfg_name} R-CNN training step, {B} synthetic 1333x800 '
-                    f'images per GPU, 512 sampled RoIs/img (BASELINE configs[2])',
+        'workload': f'boosting_rcnn {cfg_name} hot-path training step (RPN loss + proposals + '
+                    f'R-CNN assign/sample + RoIAlign fwd/bwd + boost loss + 2-fc head), {B} '
+                    f'synthetic 1333x800 images per GPU, 512 sampled RoIs/img (BASELINE configs[2])',
         'value': B * world * K / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world,
         'images_per_gpu': B, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
         'ms_allreduce': ms_comm, 'ms_per_step_no_comm': ms_nocomm / K,
@@ -444,6 +457,11 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
                     lambda: ops.boost_loss(cs, bp, lab, lw, pr, bt, bw, NC, False, 0.5, 0.0, 2.0,
                                            2.0, False), 10, dev),
             }
+        dcls, dbox, diou = ([t.detach() for t in ts] for ts in (cls, box, iou))
+        with torch.no_grad():
+            # eager (the GT / pad tensors are built from host lists inside loss())
+            st['rpn_loss_fwd_eager (targets + losses + raw grads)'] = _dev_time(
+                lambda: rpn_head.loss(dcls, dbox, diou, gts, metas), 10, dev)
         feat_bytes = sum(f.numel() * 4 for f in feats)
         bwd_bytes = R * C * 49 * 4 + feat_bytes
         ach = bwd_bytes / (st['roi_align_bwd'] * 1e-3) / 1e9
@@ -484,10 +502,43 @@ def bench_train(args, rank, world, local_rank):
     return 0
 
 
+def stress_boxes(batch, img_hw, seed, clustered=False, per_level=4000, levels=5):
+    """SURVEY §8d cfg 5 ("bypass anchors"): per image `levels` x `per_level` boxes, centres
+    U(image), sides log-U(8*2^l, 64*2^l), unique scores in (0,1); `clustered`: centres are 200
+    seeds + N(0, 4 px) jitter (long suppression chains, clustered RoIs)."""
+    rng = np.random.RandomState(seed)
+    H, W = img_hw
+    out_b, out_s, out_l = [], [], []
+    for _ in range(batch):
+        bs, ls = [], []
+        for l in range(levels):
+            n = per_level
+            if clustered:
+                seeds = rng.rand(200, 2) * [W, H]
+                ctr = seeds[rng.randint(0, 200, n)] + rng.normal(0, 4, (n, 2))
+            else:
+                ctr = rng.rand(n, 2) * [W, H]
+            wh = np.exp(rng.uniform(np.log(8 * 2 ** l), np.log(64 * 2 ** l), (n, 2)))
+            b = np.concatenate([ctr - wh / 2, ctr + wh / 2], 1)
+            b[:, 0::2] = b[:, 0::2].clip(0, W)
+            b[:, 1::2] = b[:, 1::2].clip(0, H)
+            bs.append(b)
+            ls.append(np.full(n, l))
+        n_all = levels * per_level
+        out_b.append(np.concatenate(bs).astype(np.float32))
+        out_l.append(np.concatenate(ls).astype(np.int64))
+        out_s.append(((rng.permutation(n_all) + 0.5) / n_all).astype(np.float32))
+    return out_b, out_s, out_l
+
+
 def bench_stress(args, rank, world, local_rank):
-    """configs[4]: proposal stress test — 5 FPN levels, 4000 pre-NMS proposals per
-    level, 2000 post-NMS RoIs per image, then all RoIs through RoIAlign.  One CUDA
-    graph: brcnn_rpn_get_bboxes (nms_pre 4000 / max 2000) -> bbox2roi -> RoIAlign."""
+    """configs[4]: proposal stress test — 5 FPN levels x 4000 pre-NMS proposals, 2000 post-NMS
+    RoIs per image, all RoIs through RoIAlign.
+      --stress-input boxes | clustered  (SURVEY §8d as written): random boxes bypass the anchor
+          decode; per image batched_nms (ids = level, K = 20 000) -> first 2000 -> RoIAlign;
+      --stress-input anchors: the same sizes through brcnn_rpn_get_bboxes on the COCO pyramid
+          (levels 3/4 only hold 2 457 / 693 anchors, K = 15 150).
+    One CUDA graph per step."""
     from boosting_rcnn_b200 import _lib, configs, ops
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
@@ -502,16 +553,39 @@ def bench_stress(args, rank, world, local_rank):
                                                       seed=99 + rank, pin=False)
     metas = img_metas_for(B, geom)
     feats = [t.to(dev).contiguous(memory_format=torch.channels_last) for t in h_feats]
-    cls, box, iou = ([t.to(dev) for t in ts] for ts in (h_cls, h_box, h_iou))
     cfg = dict(nms_pre=4000, max_per_img=2000, nms=dict(type='nms', iou_threshold=0.7),
                min_bbox_size=0)
     scales = [1.0 / s for s in STRIDES]
+    mode = args.stress_input
+    M = cfg['max_per_img']
+    if mode == 'anchors':
+        cls, box, iou = ([t.to(dev) for t in ts] for ts in (h_cls, h_box, h_iou))
+
+        @torch.no_grad()
+        def proposals():
+            props = rpn_head.get_bboxes_padded(cls, box, iou, metas, cfg=cfg)
+            return props.boxes, props.num
+    else:
+        bx, sc, lv = stress_boxes(B, geom['img_shape'][:2], 4242 + rank, clustered=(mode == 'clustered'))
+        d_bx = [torch.from_numpy(b).to(dev) for b in bx]
+        d_sc = [torch.from_numpy(x).to(dev) for x in sc]
+        d_lv = [torch.from_numpy(x).to(dev) for x in lv]
+
+        @torch.no_grad()
+        def proposals():
+            boxes = torch.zeros((B, M, 5), dtype=torch.float32, device=dev)
+            nums = []
+            for b in range(B):   # mmcv batched_nms per image, ids = pyramid level (no host sync)
+                dets, _, num = ops._nms_raw(d_bx[b], d_sc[b], d_lv[b], 0.7, 0, num_ids=5)
+                boxes[b] = dets[:M]
+                nums.append(num)
+            return boxes, torch.cat(nums).clamp_(max=M)
 
     @torch.no_grad()
     def fn():
-        props = rpn_head.get_bboxes_padded(cls, box, iou, metas, cfg=cfg)
-        rois, _ = ops.bbox2roi_padded(props.boxes, props.num)
-        return props, rois, ops.roi_extract(feats, rois, scales, 7)
+        boxes, num = proposals()
+        rois, _ = ops.bbox2roi_padded(boxes, num)
+        return boxes, num, rois, ops.roi_extract(feats, rois, scales, 7, channels_last_out=True)
 
     for _ in range(2):
         fn()
@@ -519,7 +593,7 @@ def bench_stress(args, rank, world, local_rank):
     g = torch.cuda.CUDAGraph()
     l0 = lib.brcnn_launch_count()
     with torch.cuda.graph(g):
-        props, rois, rf = fn()
+        boxes, num, rois, rf = fn()
     per_step = int(lib.brcnn_launch_count() - l0)
     K, W = args.steps, max(args.warmup, 3)
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -528,26 +602,35 @@ def bench_stress(args, rank, world, local_rank):
     if rank == 0:
         peak, peak_src = _peak()
         with torch.no_grad():
-            t_rpn = _dev_time(lambda: rpn_head.get_bboxes_padded(cls, box, iou, metas, cfg=cfg), 10, dev)
-            t_roi = _dev_time(lambda: ops.roi_extract(feats, rois, scales, 7), 10, dev)
+            t_prop = _graph_time(proposals, 10, dev)
+            t_roi = _graph_time(lambda: ops.roi_extract(feats, rois, scales, 7,
+                                                        channels_last_out=True), 10, dev)
         rois_h = rois.cpu().numpy()
         feat_bytes = sum(f.numel() * 4 for f in feats)
-        nbytes = rois_h.shape[0] * C * 49 * 4 + min(roi_footprint_bytes(rois_h, sizes, C), feat_bytes)
+        out_bytes = rois_h.shape[0] * C * 49 * 4
+        un = roi_union_bytes(rois_h, sizes, C)
+        nbytes = out_bytes + un
         ach = nbytes / (t_roi * 1e-3) / 1e9
+        survey = out_bytes + min(roi_footprint_bytes(rois_h, sizes, C), feat_bytes)
         print(json.dumps({
             'metric': 'proposal stress images/s', 'value': B * world * K / (ms * 1e-3),
             'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': dict(workload=f'proposal stress: 5 levels x 4000 pre-NMS proposals, 2000 '
-                                    f'post-NMS RoIs/img through RoIAlign, {B} images per GPU',
-                           images_per_gpu=B, rpn=cfg, rois=int(rois_h.shape[0]),
-                           live_rois=int((rois_h[:, 0] >= 0).sum())),
+            'config': dict(workload=f'proposal stress ({mode}): 5 levels x 4000 pre-NMS proposals, '
+                                    f'2000 post-NMS RoIs/img through RoIAlign, {B} images per GPU '
+                                    f'(BASELINE configs[4])',
+                           images_per_gpu=B, rpn=cfg, input=mode, rois=int(rois_h.shape[0]),
+                           live_rois=int((rois_h[:, 0] >= 0).sum()),
+                           kept_per_image=[int(v) for v in num.cpu().tolist()]),
             'gpu_launches': per_step * K, 'clocks': clocks,
-            'roofline': dict(kernel='roi_align_fwd_tma_kernel', bound='hbm', achieved=ach, peak=peak,
+            'roofline': dict(kernel='roi_align_fwd3_kernel', bound='hbm', achieved=ach, peak=peak,
                              unit='GB/s', frac=ach / peak, traffic=None, peak_source=peak_src,
-                             algorithmic_bytes_per_launch=nbytes, ms_per_launch=t_roi),
-            'stages_ms': {'rpn_get_bboxes_4000_2000': t_rpn, 'roi_align_fwd': t_roi}}))
+                             algorithmic_bytes_per_launch=nbytes, ms_per_launch=t_roi,
+                             frac_survey_formula=survey / (t_roi * 1e-3) / 1e9 / peak,
+                             bytes_definition='output bytes + union of footprint pixels per '
+                                              '(image, level)'),
+            'stages_ms': {'proposals_nms_20000_to_2000': t_prop, 'roi_align_fwd': t_roi}}))
     if dist:
         dist.destroy_process_group()
     return 0

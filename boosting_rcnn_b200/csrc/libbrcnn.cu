@@ -470,13 +470,18 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       const float* maxc_f = (const float*)img_maxc;
-      // BRCNN_DEBUG_TIMING=1: per-phase cycle counters of CTA 0 (debug only; allocates)
+      // developer builds (-DBRCNN_DEBUG_TIMING) add per-phase cycle counters of CTA 0; the
+      // shipped library never allocates or synchronises here
+#ifdef BRCNN_DEBUG_TIMING
       static long long* dbg_buf = [] {
         long long* pbuf = nullptr;
-        if (getenv("BRCNN_DEBUG_TIMING")) cudaMalloc(&pbuf, 64);
+        cudaMalloc(&pbuf, 64);
         return pbuf;
       }();
       long long* dbg = dbg_buf;
+#else
+      long long* dbg = nullptr;
+#endif
       if (cs > 1) {
         if (lay.total > 32 * 1024) {
           e = ensure_dyn_smem((const void*)rpn_nms_image_kernel<RNI_CLUSTER>, lay.total);
@@ -501,6 +506,7 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
                                (const int32_t*)nullptr, 0.0f, (int64_t*)nullptr);
       }
       if (e != cudaSuccess) return (int)e;
+#ifdef BRCNN_DEBUG_TIMING
       if (dbg != nullptr) {
         long long h[8];
         cudaStreamSynchronize(stream);
@@ -508,6 +514,7 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
         fprintf(stderr, "[rpn_nms_image cs=%d] rounds=%lld cycles: windows=%lld rank=%lld pull+diag=%lld "
                 "combine=%lld resolve=%lld\n", cs, h[5], h[0], h[1], h[2], h[3], h[4]);
       }
+#endif
       g_launch_count_add(1);
       BRCNN_CUDA_CHECK_LAST();
       return BRCNN_OK;
@@ -787,11 +794,13 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
       const char* e = getenv("BRCNN_NMS_OP");
       return e && e[0] == 'o';
     }();
-    const int keep_pad = nms_keep_pad(K, K);
+    // the kept list of a segment lives in shared memory up to 8192 boxes (160 KB); a longer one
+    // (one id holding most of a huge input) spills to global memory inside the kernel
+    int keep_pad = nms_keep_pad(K, K);
+    if (keep_pad > 8192) keep_pad = 8192;
     int np2 = 1;
     while (np2 < K) np2 <<= 1;
-    if (!force_old2 && idxs != nullptr && num_ids > BRCNN_MAX_LEVELS && num_ids <= 1024 &&
-        (size_t)keep_pad * 20 <= 160 * 1024 && (size_t)np2 * 8 <= 160 * 1024) {
+    if (!force_old2 && idxs != nullptr && num_ids > BRCNN_MAX_LEVELS && num_ids <= 1024) {
       int32_t* seg_start = (int32_t*)(ws + w.seg);
       int32_t* seg_count = seg_start + NMS_MAX_IDS;
       cudaError_t e = cudaMemsetAsync(seg_start, 0, 2 * NMS_MAX_IDS * 4, stream);
@@ -812,13 +821,21 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
       g_launch_count_add(1);
       BRCNN_CUDA_CHECK_LAST();
       const size_t sm = (size_t)np2 * 8;
-      if (sm > 32 * 1024) {
-        e = ensure_dyn_smem((const void*)nms_merge_sort_kernel<OpMergeEpilogue>, sm);
-        if (e != cudaSuccess) return (int)e;
+      if (sm <= 160 * 1024) {
+        // all kept keys fit one CTA's shared memory: in-smem bitonic sort
+        if (sm > 32 * 1024) {
+          e = ensure_dyn_smem((const void*)nms_merge_sort_kernel<OpMergeEpilogue>, sm);
+          if (e != cudaSuccess) return (int)e;
+        }
+        OpMergeEpilogue ep{keep};
+        nms_merge_sort_kernel<OpMergeEpilogue><<<1, 1024, sm, stream>>>(
+            kept_key, kept_count_ids(ws, w), num_ids, K, K, np2, num_keep, ep, seg_start);
+      } else {
+        // COCO-scale inputs (K = 20 480, 80 ids): rank counting over the whole GPU
+        dim3 mgrid((unsigned)((K + 255) / 256), (unsigned)num_ids);
+        nms_op_merge_rank_kernel<<<mgrid, 256, 0, stream>>>(kept_key, kept_count_ids(ws, w),
+                                                           seg_start, num_ids, keep, num_keep);
       }
-      OpMergeEpilogue ep{keep};
-      nms_merge_sort_kernel<OpMergeEpilogue><<<1, 1024, sm, stream>>>(
-          kept_key, kept_count_ids(ws, w), num_ids, K, K, np2, num_keep, ep, seg_start);
       g_launch_count_add(1);
       BRCNN_CUDA_CHECK_LAST();
       if (dets != nullptr) {

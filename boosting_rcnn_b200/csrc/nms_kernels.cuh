@@ -135,15 +135,23 @@ nms_fused_kernel(const float4* __restrict__ boxes, const uint8_t* __restrict__ v
         const float4 b = tb[c];
         const float ba = ta[c];
         int q = g;
-        for (; q + 24 < nkept && !hit; q += 32) {
+        const int ns = min(nkept, keep_pad);          // kept boxes resident in shared memory
+        for (; q + 24 < ns && !hit; q += 32) {
           const bool h0 = nms_suppresses(kbox[q], karea[q], b, ba, thr, off);
           const bool h1 = nms_suppresses(kbox[q + 8], karea[q + 8], b, ba, thr, off);
           const bool h2 = nms_suppresses(kbox[q + 16], karea[q + 16], b, ba, thr, off);
           const bool h3 = nms_suppresses(kbox[q + 24], karea[q + 24], b, ba, thr, off);
           hit = h0 | h1 | h2 | h3;
         }
-        for (; q < nkept && !hit; q += 8)
+        for (; q < ns && !hit; q += 8)
           hit = nms_suppresses(kbox[q], karea[q], b, ba, thr, off);
+        // kept list longer than the shared-memory budget (operator path, one huge id):
+        // the tail is re-read from the sorted boxes through kept_pos (rare, slow, correct)
+        for (; q < nkept && !hit; q += 8) {
+          float4 kb = seg[kept_pos[kbase + q]];
+          if (has_off) kb = add_seg_offset(kb, segoff);
+          hit = nms_suppresses(kb, (kb.z - kb.x + off) * (kb.w - kb.y + off), b, ba, thr, off);
+        }
       }
       const unsigned bal = __ballot_sync(0xffffffffu, hit);
       if (lane == 0 && bal) atomicOr(&s_dead[(tid >> 5) & 1], bal);
@@ -202,8 +210,10 @@ nms_fused_kernel(const float4* __restrict__ boxes, const uint8_t* __restrict__ v
           const int q = nkept + __popcll(keep & ((1ull << r) - 1ull));
           if (q < keep_cap && q < max_keep) {
             kept_pos[kbase + q] = t * 64 + r;
-            kbox[q] = tb[r];
-            karea[q] = ta[r];
+            if (q < keep_pad) {
+              kbox[q] = tb[r];
+              karea[q] = ta[r];
+            }
           }
         }
       }
@@ -406,6 +416,33 @@ nms_merge_kernel(const int32_t* __restrict__ kept_pos,
     }
   }
   for (int r = total + threadIdx.x; r < max_out; r += blockDim.x) ep.pad(b, r);
+}
+
+// Operator path with many ids and more kept keys than one CTA can sort in shared memory: the
+// kept lists (each descending, packed at seg_start[g]) are merged by rank counting over the
+// whole GPU: thread (j, g) finds the global rank of kept key j of list g with one binary search
+// per other list and writes keep[rank] = original index (low half of the key is ~index).
+// grid (ceil(max_len / 256), Sg).
+__global__ void __launch_bounds__(256)
+nms_op_merge_rank_kernel(const u64* __restrict__ kept_key, const int32_t* __restrict__ kept_count,
+                         const int32_t* __restrict__ seg_start, int Sg,
+                         int64_t* __restrict__ keep, int32_t* __restrict__ num_keep) {
+  const int g = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g == 0 && j == 0) {
+    int tot = 0;
+    for (int i = 0; i < Sg; ++i) tot += kept_count[i];
+    num_keep[0] = tot;
+  }
+  if (j >= kept_count[g]) return;
+  const u64 key = kept_key[(size_t)seg_start[g] + j];
+  int rank = j;
+  for (int g2 = 0; g2 < Sg; ++g2) {
+    if (g2 == g) continue;
+    const int n2 = kept_count[g2];
+    if (n2 > 0) rank += count_greater_desc(kept_key + (size_t)seg_start[g2], n2, key);
+  }
+  keep[rank] = (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
 }
 
 // Same contract, for epilogues that identify the element from its key alone

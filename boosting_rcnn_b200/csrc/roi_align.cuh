@@ -154,7 +154,9 @@ roi_align_fwd_kernel(const __grid_constant__ RoiArgs a,
   roi_axis_range(g.start_h, g.bin_h, a.PH, g.gh, g.H, ylo, yhi);
   roi_axis_range(g.start_w, g.bin_w, a.PW, g.gw, g.W, xlo, xhi);
   const int fh = yhi - ylo + 1, fw = xhi - xlo + 1;
-  const bool empty = (fh <= 0) || (fw <= 0);
+  // an image index outside [0, B) (hand-built rois, batch mismatch) reads nothing: zeros,
+  // like the TMA kernels (block-uniform)
+  const bool empty = (fh <= 0) || (fw <= 0) || g.b < 0 || g.b >= a.B;
 
   // ---- pull the whole footprint towards L2 in one shot ----
   // Every footprint row is a contiguous run of fw*C floats; issuing all the

@@ -57,6 +57,52 @@ def fused_scalar_allreduce(named_scalars):
     return OrderedDict((k, packed[i]) for i, k in enumerate(named_scalars))
 
 
+def collect_detections(det_bboxes, det_labels, num_dets, size=None, interleaved=False):
+    """Result-side wire of the multi-GPU test loop (mmdet/apis/test.py:273-340
+    ``collect_results_cpu/gpu``): gather every rank's detections on rank 0.
+
+    The reference pickles per-image python lists, all-gathers their byte lengths, pads and
+    all-gathers the bytes (2 collectives + pickle on every rank).  The hot path already holds
+    fixed-capacity tensors — det_bboxes (b,M,5), det_labels (b,M), num_dets (b,) as returned by
+    ``simple_test_bboxes_padded`` — so ONE ``all_gather`` of a packed (b_max, M, 6) tensor +
+    one of the counts is enough.  Ranks may own different numbers of images (``shard_range``).
+
+    Returns on rank 0 a list with one (k,6) float32 tensor [x1,y1,x2,y2,score,label] per image,
+    in dataset order: concatenation of the contiguous shards, or the reference's round-robin
+    order (``interleaved=True``, DistributedSampler + ``zip(*part_list)``); truncated to
+    ``size`` (the sampler may pad).  Other ranks get None (like the reference)."""
+    rank, world = get_dist_info()
+    packed = torch.cat([det_bboxes, det_labels.to(det_bboxes.dtype).unsqueeze(-1)], dim=-1)
+    counts = num_dets.to(torch.int64)
+    if world > 1:
+        nb = torch.tensor([packed.size(0)], dtype=torch.int64, device=packed.device)
+        nbs = [torch.zeros_like(nb) for _ in range(world)]
+        dist.all_gather(nbs, nb)
+        bmax = int(max(int(x) for x in nbs))
+        pad = packed.new_zeros((bmax,) + tuple(packed.shape[1:]))
+        pad[:packed.size(0)] = packed
+        cpad = counts.new_zeros((bmax,))
+        cpad[:counts.numel()] = counts
+        parts = [torch.zeros_like(pad) for _ in range(world)]
+        cparts = [torch.zeros_like(cpad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        dist.all_gather(cparts, cpad)
+        if rank != 0:
+            return None
+        per_rank = [[p[i, :int(c[i])].cpu() for i in range(int(n))]
+                    for p, c, n in zip(parts, cparts, nbs)]
+    else:
+        per_rank = [[packed[i, :int(counts[i])].cpu() for i in range(packed.size(0))]]
+    if interleaved:
+        out, i = [], 0
+        while any(i < len(r) for r in per_rank):
+            out.extend(r[i] for r in per_rank if i < len(r))
+            i += 1
+    else:
+        out = [x for r in per_rank for x in r]
+    return out if size is None else out[:size]
+
+
 def max_over_ranks(value, device=None):
     """Timing rule of bench.py: device time of a step is the max over ranks."""
     _, world = get_dist_info()

@@ -27,6 +27,49 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _first_cuda_tensor(args):
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a
+        elif isinstance(a, (list, tuple)):
+            t = _first_cuda_tensor(a)
+            if t is not None:
+                return t
+    return None
+
+
+def _device_guard(fn):
+    """Run ``fn`` with the device of its first CUDA tensor argument current (like the mmcv ops'
+    device guard): launches, cudaFuncSetAttribute and ``_stream()`` then refer to the GPU the
+    tensors live on even when the caller never called ``torch.cuda.set_device``; all CUDA
+    tensor arguments must share that device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = _first_cuda_tensor(args)
+        if t is None:
+            t = _first_cuda_tensor(tuple(kwargs.values()))
+        if t is None:
+            return fn(*args, **kwargs)
+
+        def check_same(xs):
+            for a in xs:
+                if isinstance(a, torch.Tensor):
+                    if a.is_cuda and a.device != t.device:
+                        raise RuntimeError(f'{fn.__name__}: tensors on {a.device} and {t.device}')
+                elif isinstance(a, (list, tuple)):
+                    check_same(a)
+        check_same(args)
+        check_same(tuple(kwargs.values()))
+        if t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def _f32c(t, name):
     if not t.is_cuda:
         raise RuntimeError(
@@ -78,6 +121,7 @@ def rpn_workspace_layout(p):
     return lay
 
 
+@_device_guard
 def rpn_get_bboxes(p, cls_scores, bbox_preds, iou_preds, base_anchors, img_hw,
                    return_workspace=False):
     """Batched ATSSRPNHead.get_bboxes.  Returns (proposals (B,M,5) zero padded,
@@ -114,6 +158,7 @@ def rpn_get_bboxes(p, cls_scores, bbox_preds, iou_preds, base_anchors, img_hw,
     return proposals, num
 
 
+@_device_guard
 def delta2bbox(rois, deltas, means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.),
                max_shape=None, wh_ratio_clip=16 / 1000, clip_border=True):
     """mmdet delta2bbox for (N,4) rois and (N,4*k) deltas (one image)."""
@@ -223,6 +268,7 @@ class _RpnLossFunction(Function):
         return (None, None, None, None, None, *out)
 
 
+@_device_guard
 def rpn_loss(params, cls_scores, bbox_preds, iou_preds, base_anchors, gt_boxes, num_gt, pad_hw):
     """Fused ATSSRPNHead.loss (atss=False).  gt_boxes (B,max_gts,4) zero padded + num_gt (B,)
     int32, pad_hw (B,2) = img_meta['pad_shape'][:2].  Returns (loss_cls [L], loss_bbox [L],
@@ -236,7 +282,11 @@ def rpn_loss(params, cls_scores, bbox_preds, iou_preds, base_anchors, gt_boxes, 
 # --------------------------------------------------------------------------
 # mmcv.ops.nms / batched_nms mirrors
 # --------------------------------------------------------------------------
-def _nms_raw(boxes, scores, idxs, iou_threshold, offset):
+@_device_guard
+def _nms_raw(boxes, scores, idxs, iou_threshold, offset, num_ids=None):
+    """-> (dets (K,5), keep (K,), num (1,) int32): padded outputs + device count, no host sync.
+    ``num_ids``: caller's bound on the id range (ids in [0, num_ids)); None = unknown (the
+    library then treats the boxes as one segment of offset boxes, like mmcv)."""
     lib = _lib.load()
     boxes = _f32c(boxes, 'boxes')
     scores = _f32c(scores, 'scores')
@@ -246,22 +296,24 @@ def _nms_raw(boxes, scores, idxs, iou_threshold, offset):
     dets = torch.empty((K, 5), dtype=torch.float32, device=dev)
     num = torch.zeros((1,), dtype=torch.int32, device=dev)
     if K == 0:
-        return dets, keep
-    num_ids = 1
+        return dets, keep, num
+    nid = 1
     if idxs is not None:
         idxs = idxs.to(torch.int64).contiguous()
-        # bound on the id range: lets the library walk <= 8 ids (pyramid levels) as sorted
-        # lists on a CTA cluster; costs one host read, like the data-dependent output size
-        lo, hi = int(idxs.min().item()), int(idxs.max().item())
-        num_ids = hi + 1 if lo >= 0 else 0
+        nid = int(num_ids) if num_ids is not None else 0
     ws = _ws(lib.brcnn_nms_workspace_bytes(K), dev)
     rc = lib.brcnn_batched_nms(
         boxes.data_ptr(), scores.data_ptr(),
-        idxs.data_ptr() if idxs is not None else None, K, num_ids, float(iou_threshold),
+        idxs.data_ptr() if idxs is not None else None, K, nid, float(iou_threshold),
         int(offset), keep.data_ptr(), dets.data_ptr(), num.data_ptr(),
         ws.data_ptr(), ws.numel(), _stream())
     check(rc, 'brcnn_batched_nms')
-    n = int(num.item())  # the reference API returns variable-length tensors
+    return dets, keep, num
+
+
+def _trim(dets, keep, num):
+    """the reference API returns variable-length tensors: the one host read of the operator"""
+    n = int(num.item())
     return dets[:n], keep[:n]
 
 
@@ -274,7 +326,7 @@ def nms(boxes, scores, iou_threshold, offset=0, score_threshold=0, max_num=-1):
         valid_mask = scores > score_threshold
         valid_inds = torch.nonzero(valid_mask, as_tuple=False).squeeze(dim=1)
         boxes, scores = boxes[valid_mask], scores[valid_mask]
-    dets, inds = _nms_raw(boxes, scores, None, iou_threshold, offset)
+    dets, inds = _trim(*_nms_raw(boxes, scores, None, iou_threshold, offset))
     if max_num > 0:
         dets, inds = dets[:max_num], inds[:max_num]
     if valid_inds is not None:
@@ -285,7 +337,10 @@ def nms(boxes, scores, iou_threshold, offset=0, score_threshold=0, max_num=-1):
 def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
     """mmcv.ops.batched_nms.  ``split_thr`` is accepted and
     ignored: with the pinned (score desc, index asc) order the split and
-    unsplit paths return identical results."""
+    unsplit paths return identical results.  Extra key ``num_ids`` (bound on the id range,
+    e.g. the number of classes / pyramid levels) selects the per-id kernels without any host
+    read of ``idxs``; without it the bound is read from ``idxs.max()`` (one host sync, like
+    the data-dependent output size)."""
     nms_cfg_ = dict(nms_cfg)
     class_agnostic = nms_cfg_.pop('class_agnostic', class_agnostic)
     nms_type = nms_cfg_.pop('type', 'nms')
@@ -294,8 +349,11 @@ def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
     nms_cfg_.pop('split_thr', None)
     max_num = nms_cfg_.pop('max_num', -1)
     iou_threshold = nms_cfg_.pop('iou_threshold')
-    dets, keep = _nms_raw(boxes, scores, None if class_agnostic else idxs,
-                          iou_threshold, 0)
+    num_ids = nms_cfg_.pop('num_ids', None)
+    if not class_agnostic and num_ids is None and boxes.size(0) > 0:
+        num_ids = int(idxs.max().item()) + 1 if int(idxs.min().item()) >= 0 else 0
+    dets, keep = _trim(*_nms_raw(boxes, scores, None if class_agnostic else idxs,
+                                 iou_threshold, 0, num_ids))
     if max_num > 0:
         dets, keep = dets[:max_num], keep[:max_num]
     return dets, keep
@@ -318,6 +376,7 @@ def make_roi_params(batch, channels, featmap_sizes, spatial_scales, output_size,
     return p
 
 
+@_device_guard
 def to_nhwc(x):
     """(B,C,H,W) tensor -> NHWC-contiguous storage (returned as a (B,H,W,C)
     tensor).  channels_last inputs are a free view; NCHW-contiguous ones go
@@ -338,6 +397,7 @@ def to_nhwc(x):
     return out
 
 
+@_device_guard
 def nhwc_to_nchw(x):
     """(B,H,W,C) contiguous -> (B,C,H,W) contiguous via the library kernel."""
     B, H, W, C = x.shape
@@ -348,6 +408,7 @@ def nhwc_to_nchw(x):
     return out
 
 
+@_device_guard
 def _multi_transpose(fn_name, srcs, dst_shapes):
     """One launch for a whole pyramid: srcs are contiguous fp32 CUDA tensors
     sharing batch and channel counts."""
@@ -405,6 +466,7 @@ def pyramid_to_nchw(grads_nhwc):
                             [(g.shape[0], g.shape[3], g.shape[1], g.shape[2]) for g in grads_nhwc])
 
 
+@_device_guard
 def bbox2roi_padded(proposals, num):
     """Padded proposals (B,cap,5) + num (B) int32 -> rois (B*cap,5) with
     b = -1 padding rows, prior (B*cap).  One kernel (bbox2roi, transforms.py:59-78)."""
@@ -420,6 +482,7 @@ def bbox2roi_padded(proposals, num):
     return rois, prior
 
 
+@_device_guard
 def map_roi_levels(rois, num_levels, finest_scale=56):
     rois = _f32c(rois, 'rois')
     out = torch.empty((rois.size(0),), dtype=torch.int64, device=rois.device)
@@ -480,6 +543,7 @@ class _RoiExtractFunction(Function):
         return (None, None, None, None, None, None, None, *outs)
 
 
+@_device_guard
 def roi_extract_backward(params, grad_out, rois):
     """Gradient of ``roi_extract`` w.r.t. every pyramid level, NHWC (B,H,W,C) each.
     ``grad_out`` is the logical (R,C,oh,ow) tensor; bin-major storage ((R,oh,ow,C), what the
@@ -511,6 +575,7 @@ def roi_extract_backward(params, grad_out, rois):
     return grads
 
 
+@_device_guard
 def roi_extract(feats, rois, spatial_scales, output_size=7, sampling_ratio=0,
                 aligned=True, finest_scale=56, return_levels=False, channels_last_out=False):
     """Fused SingleRoIExtractor.forward: level mapping + RoIAlign on every
@@ -601,6 +666,7 @@ def sample_plan(counts, num, pos_fraction, neg_pos_ub=-1):
     return plan, perm_pos, perm_neg, rows
 
 
+@_device_guard
 def rcnn_assign_sample(proposals, num_props, gt_bboxes, gt_labels, num_classes,
                        pos_iou_thr, neg_iou_thr, min_pos_iou=0., num=512, pos_fraction=0.25,
                        neg_pos_ub=-1, means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.),
@@ -710,6 +776,7 @@ class _BoostLossFunction(Function):
         return (gc, gb) + (None,) * 12
 
 
+@_device_guard
 def boost_loss(cls_score, bbox_pred, labels, label_weights, prior, bbox_targets,
                bbox_weights, num_classes, reg_class_agnostic=False, gamma=0.5,
                alpha=0.0, loss_cls_weight=1.0, loss_bbox_weight=1.0,
@@ -746,6 +813,7 @@ def rcnn_workspace_layout(p):
     return lay
 
 
+@_device_guard
 def rcnn_get_bboxes(p, rois, prior, num_rois, cls_score, bbox_pred, img_hw,
                     scale_factor=None, return_workspace=False):
     """Batched fusion + ProbConvFCBBoxHead.get_bboxes + multiclass_nms on the

@@ -6,8 +6,11 @@ B200-native pieces:
     run batch-wide on the padded proposal layout with no host sync until the
     final ``bbox2result`` copy;
   * ``_bbox_forward_train_boost`` (:107-149) + ``norm_loss`` (:151-154): one
-    fused loss kernel (value, accuracy and gradients).
-Host glue kept in torch: assign/sample and the prior extraction (:39-64).
+    fused loss kernel (value, accuracy and gradients);
+  * the training front-end (:33-64: MaxIoUAssigner, RandomSampler, get_targets, prior
+    vector): two launches for the whole batch (``ops.rcnn_assign_sample``) + the reference's
+    own CPU ``torch.randperm``; the torch restatement in sampling.py is the fallback for
+    settings / sizes the fused kernels do not cover.
 Only ``boost=True, quality=False, ams=False`` (every configs/boosting_rcnn/*
 file) is supported; mask branches are out of scope.
 """
@@ -108,7 +111,10 @@ class ProbRoIHead(nn.Module):
         if gt_bboxes_ignore is None:
             gt_bboxes_ignore = [None for _ in range(num_imgs)]
         if self._fused_train_prep_ok(gt_bboxes_ignore):
-            return self._forward_train_fused(x, proposal_list, gt_bboxes, gt_labels)
+            cap = proposal_list.boxes.size(1) if isinstance(proposal_list, PaddedProposals) \
+                else max([int(p.size(0)) for p in proposal_list] + [1])
+            if self._fused_train_prep_fits(cap, gt_bboxes, self.bbox_sampler.num):
+                return self._forward_train_fused(x, proposal_list, gt_bboxes, gt_labels)
         if isinstance(proposal_list, PaddedProposals):
             n = proposal_list.num.tolist()
             proposal_list = [proposal_list.boxes[b, :k] for b, k in enumerate(n)]
@@ -143,6 +149,18 @@ class ProbRoIHead(nn.Module):
                 and not a.match_low_quality and isinstance(a.neg_iou_thr, float)
                 and s.add_gt_as_proposals and all(g is None for g in gt_bboxes_ignore)
                 and not getattr(self, 'force_python_train_prep', False))
+
+    @staticmethod
+    def _fused_train_prep_fits(num_props_cap, gt_bboxes, num):
+        """Limits of the fused kernels: <= 2048 GTs per image (brcnn_rcnn_assign) and a
+        candidate list + selection buffer within 200 KB of shared memory
+        (brcnn_rcnn_sample_targets); crowded images take the torch fallback instead of
+        raising in the middle of training."""
+        gmax = max([int(g.size(0)) for g in gt_bboxes] + [1])
+        sel = 1
+        while sel < max(1, num):
+            sel <<= 1
+        return gmax <= 2048 and sel * 8 + (gmax + num_props_cap) * 4 <= 200 * 1024
 
     def _forward_train_fused(self, x, proposal_list, gt_bboxes, gt_labels):
         props = proposal_list if isinstance(proposal_list, PaddedProposals) \
@@ -222,26 +240,31 @@ class ProbRoIHead(nn.Module):
         return [det[b, :k] for b, k in enumerate(n)], [lab[b, :k] for b, k in enumerate(n)]
 
     def _simple_test_bboxes_raw(self, x, img_metas, proposals, rescale):
-        """rcnn_test_cfg is None: return decoded boxes and fused scores without
-        NMS (convfc_bbox_head.py:323-324)."""
-        if isinstance(proposals, PaddedProposals):
-            n = proposals.num.tolist()
-            proposals = [proposals.boxes[b, :k] for b, k in enumerate(n)]
-        rois = bbox2roi(proposals)
-        prior = torch.cat([b[:, -1] for b in proposals], dim=0)
+        """rcnn_test_cfg is None: decoded boxes (n,4C) and fused scores (n,C+1) per image
+        without NMS (convfc_bbox_head.py:323-324).  Same fusion + decode kernel as the normal
+        test path: its intermediates are read back from the workspace of
+        ``brcnn_rcnn_get_bboxes`` (the class NMS behind them is run with a 1-detection budget
+        and ignored)."""
+        if not isinstance(proposals, PaddedProposals):
+            proposals = pad_proposals(proposals)
+        B, cap = proposals.boxes.shape[:2]
+        rois, prior = ops.bbox2roi_padded(proposals.boxes, proposals.num)
         res = self._bbox_forward(x, rois)
-        cls_score = res['cls_score']
-        if self.prob:
-            cls_score = (cls_score.softmax(1) * prior.reshape(-1, 1)) ** 0.5
-        counts = tuple(len(p) for p in proposals)
-        out_b, out_s = [], []
-        for i, (r, s, d) in enumerate(zip(rois.split(counts, 0), cls_score.split(counts, 0),
-                                          res['bbox_pred'].split(counts, 0))):
-            b, s = self.bbox_head.get_bboxes(r, s, d, img_metas[i]['img_shape'],
-                                             img_metas[i]['scale_factor'], rescale=rescale, cfg=None)
-            out_b.append(b)
-            out_s.append(s)
-        return out_b, out_s
+        hw, sf = self._img_consts(img_metas, rois.device)
+        h = self.bbox_head
+        p = ops.make_rcnn_params(B, cap, h.num_classes, 0.05, 0.5, 1, h.bbox_coder.means,
+                                 h.bbox_coder.stds, h.reg_class_agnostic, self.prob, rescale)
+        _, _, _, ws = ops.rcnn_get_bboxes(p, rois, prior, proposals.num, res['cls_score'],
+                                          res['bbox_pred'], hw, sf if rescale else None,
+                                          return_workspace=True)
+        lay = ops.rcnn_workspace_layout(p)
+        C = h.num_classes
+        nbox = 1 if h.reg_class_agnostic else C
+        scores = ws[lay.scores:lay.scores + B * cap * (C + 1) * 4].view(torch.float32).view(B, cap, C + 1)
+        bboxes = ws[lay.bboxes:lay.bboxes + B * cap * nbox * 16].view(torch.float32).view(B, cap, nbox * 4)
+        n = proposals.num.tolist()
+        return ([bboxes[b, :k].clone() for b, k in enumerate(n)],
+                [scores[b, :k].clone() for b, k in enumerate(n)])
 
     def simple_test(self, x, proposal_list, img_metas, proposals=None, rescale=False):
         det, lab, num = self.simple_test_bboxes_padded(x, img_metas, proposal_list, self.test_cfg,

@@ -1,6 +1,11 @@
-"""R-CNN assign + sample host glue (torch ops; SURVEY.md §8f rank 1 — sits
-between the proposal kernels and the RoI kernels in training and is NOT yet a
-CUDA kernel of this library).
+"""R-CNN assign + sample in torch ops — the FALLBACK of the training front-end.
+
+The hot path runs ``ops.rcnn_assign_sample`` (brcnn_rcnn_assign + brcnn_rcnn_sample_targets,
+csrc/rcnn_train_prep.cuh); these classes are used by
+``ProbRoIHead.forward_train`` only for settings the fused kernels do not cover
+(match_low_quality, ignore regions, > 2048 GTs per image, other samplers) and as the
+reference-shaped API (``build_assigner`` / ``build_sampler``).  Both paths are pinned to the
+same executed-reference goldens (tests/golden/make_golden_train.py).
 
 Semantics of mmdet/core/bbox/assigners/max_iou_assigner.py:61-212,
 samplers/base_sampler.py:35-102, random_sampler.py:32-82 and

@@ -26,8 +26,20 @@ def _worker(rank, world, port, out):
     fused = bdist.fused_scalar_allreduce(losses)
     each = {k: bdist.reduce_mean(v) for k, v in losses.items()}
     ms = bdist.max_over_ranks(1.5 + rank)
+    # result wire: rank r owns images [lo, hi) of 5; image i has i detections, rows tagged i
+    lo5, hi5 = bdist.shard_range(5)
+    M = 4
+    det = torch.zeros(hi5 - lo5, M, 5)
+    lab = torch.zeros(hi5 - lo5, M, dtype=torch.int64)
+    num = torch.zeros(hi5 - lo5, dtype=torch.int32)
+    for j, i in enumerate(range(lo5, hi5)):
+        det[j, :i] = float(i)
+        lab[j, :i] = i
+        num[j] = min(i, M)
+    col = bdist.collect_detections(det, lab, num, size=5)
+    col = None if col is None else [(tuple(c.shape), float(c.sum())) for c in col]
     out.put((rank, lo, hi, {k: float(v) for k, v in fused.items()},
-             {k: float(v) for k, v in each.items()}, ms))
+             {k: float(v) for k, v in each.items()}, ms, col))
     dist.destroy_process_group()
 
 
@@ -42,7 +54,10 @@ def test_two_rank_gloo_sharding_and_fused_allreduce():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, lo0, hi0, f0, e0, m0), (r1, lo1, hi1, f1, e1, m1) = res
+    (r0, lo0, hi0, f0, e0, m0, c0), (r1, lo1, hi1, f1, e1, m1, c1) = res
+    # collect_detections: rank 0 holds all 5 images in dataset order, rank 1 nothing
+    assert c1 is None and [c[0] for c in c0] == [(0, 6), (1, 6), (2, 6), (3, 6), (4, 6)]
+    assert [c[1] for c in c0] == [0.0, 6.0, 24.0, 54.0, 96.0]
     assert (lo0, hi0, lo1, hi1) == (0, 17, 17, 33)  # every image exactly once
     assert f0 == f1 == e0 == e1  # one fused collective == 7 separate reduce_means
     assert f0['loss_cls'] == (4 + 14) / 2 and list(f0) == list(e0)
@@ -55,3 +70,6 @@ def test_single_process_paths_are_identity():
     d = {'a': torch.tensor(2.0)}
     assert bdist.fused_scalar_allreduce(d)['a'].item() == 2.0
     assert [bdist.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    det = torch.arange(2 * 3 * 5, dtype=torch.float32).reshape(2, 3, 5)
+    col = bdist.collect_detections(det, torch.tensor([[1, 2, 3], [4, 5, 6]]), torch.tensor([2, 0]))
+    assert [tuple(c.shape) for c in col] == [(2, 6), (0, 6)] and col[0][1, 5] == 2

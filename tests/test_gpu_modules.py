@@ -367,3 +367,42 @@ def test_golden_multiclass_nms_coco_scale_cuda(cuda):
     dets, keep = ops.batched_nms(t(boxes), t(scores), t(labels), dict(type='nms', iou_threshold=0.5))
     np.testing.assert_array_equal(labels[keep.cpu().numpy()][:100], g['labels'])
     np.testing.assert_array_equal(dets[:100].cpu().numpy().view(np.uint32), g['dets'].view(np.uint32))
+
+
+def test_simple_test_bboxes_without_nms_cfg_goes_through_the_kernel(cuda):
+    """rcnn_test_cfg=None (convfc_bbox_head.py:323-324): per-image decoded boxes (n,4C) and
+    fused scores (n,C+1) come from the fusion + decode kernel (no eager torch path) and equal
+    the oracle's fuse_scores / delta2bbox on the head outputs (1e-5: the 2-fc head runs on a
+    differently padded batch here, cuBLAS may round its GEMMs differently)."""
+    from boosting_rcnn_b200 import _lib
+    torch.manual_seed(0)
+    _, roi, _ = configs.build_hot_path('utdac')
+    roi = roi.to(cuda).eval()
+    B, sizes = 2, synth.featmap_sizes(256, 320)
+    feats = [torch.from_numpy(f).to(cuda) for f in synth.fpn_feats(B, 256, sizes, seed=8)]
+    rng = np.random.RandomState(9)
+    plist = []
+    for b, n in enumerate((37, 12)):
+        bx = synth.random_boxes(n, 250, 317, seed=20 + b)
+        sc = np.sort(rng.rand(n).astype(np.float32))[::-1].copy()
+        plist.append(torch.from_numpy(np.concatenate([bx, sc[:, None]], 1).astype(np.float32)).to(cuda))
+    metas = _metas(B)
+    l0 = _lib.load().brcnn_launch_count()
+    with torch.no_grad():
+        bbs, scs = roi.simple_test_bboxes(feats, metas, plist, None, rescale=True)
+    assert _lib.load().brcnn_launch_count() - l0 >= 4
+    with torch.no_grad():
+        rois = bbox2roi(plist)
+        res = roi._bbox_forward(feats, rois)
+    cs, bp = res['cls_score'].cpu().numpy(), res['bbox_pred'].cpu().numpy()
+    off = 0
+    for b, p in enumerate(plist):
+        n = p.size(0)
+        assert bbs[b].shape == (n, 16) and scs[b].shape == (n, 5)
+        fused = oracle.fuse_scores(cs[off:off + n], p[:, 4].cpu().numpy())
+        np.testing.assert_allclose(scs[b].cpu().numpy(), fused, rtol=1e-5, atol=1e-6)
+        dec = oracle.delta2bbox(p[:, :4].cpu().numpy(), bp[off:off + n], (0., 0., 0., 0.),
+                                (.1, .1, .2, .2), max_shape=metas[b]['img_shape'])
+        dec = (dec.reshape(n, -1, 4) / np.asarray(metas[b]['scale_factor'], np.float32)).reshape(n, -1)
+        np.testing.assert_allclose(bbs[b].cpu().numpy(), dec, rtol=1e-5, atol=1e-3)
+        off += n

@@ -119,3 +119,37 @@ np.save(sys.argv[1], np.concatenate(res))
                            env=dict(os.environ, BRCNN_NMS_OP=mode))
             outs.append(np.load(path))
     np.testing.assert_array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize('n,nid,clustered', [(20480, 80, True), (20480, 80, False), (17000, 20, True)])
+def test_batched_nms_coco_scale_many_ids(cuda, n, nid, clustered):
+    """The reference's COCO multiclass_nms call shape (<= 20 480 candidates, 80 class ids,
+    bbox_nms.py:86): per-id fused kernels + rank-counting merge over the whole GPU (more kept
+    keys than one CTA sorts in shared memory); `num_ids` in the cfg avoids the host read."""
+    boxes = synth.random_boxes(n, 800, 1333, seed=n + nid, clustered=clustered)
+    scores = _scores(n, n + 3, dup=True)
+    ids = np.random.RandomState(n + 1).randint(0, nid, n).astype(np.int64)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    ref = oracle.batched_nms(boxes, scores, ids, 0.5)
+    for cfg in (dict(type='nms', iou_threshold=0.5), dict(type='nms', iou_threshold=0.5, num_ids=nid)):
+        dets, keep = ops.batched_nms(t(boxes), t(scores), t(ids), cfg)
+        np.testing.assert_array_equal(keep.cpu().numpy(), ref)
+        np.testing.assert_array_equal(dets.cpu().numpy()[:, 4], scores[ref])
+
+
+def test_batched_nms_one_id_with_more_keeps_than_shared_memory(cuda):
+    """One id keeps > 8192 boxes (its kept list spills from shared to global memory inside the
+    per-id kernel); ids > 8 so that the per-id path is taken."""
+    rng = np.random.RandomState(3)
+    n0 = 9000                     # a 100 x 90 lattice of disjoint 6x6 boxes: all kept
+    gx, gy = np.meshgrid(np.arange(100) * 10.0, np.arange(90) * 8.0)
+    b0 = np.stack([gx.ravel(), gy.ravel(), gx.ravel() + 6, gy.ravel() + 6], 1)
+    b1 = synth.random_boxes(3000, 800, 1333, seed=11, clustered=True)
+    boxes = np.concatenate([b0, b1]).astype(np.float32)
+    ids = np.concatenate([np.zeros(n0), rng.randint(1, 12, 3000)]).astype(np.int64)
+    scores = rng.permutation(len(boxes)).astype(np.float32) / len(boxes)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    dets, keep = ops.batched_nms(t(boxes), t(scores), t(ids), dict(type='nms', iou_threshold=0.5))
+    ref = oracle.batched_nms(boxes, scores, ids, 0.5)
+    assert (ids[ref] == 0).sum() == n0
+    np.testing.assert_array_equal(keep.cpu().numpy(), ref)

@@ -97,9 +97,11 @@ def test_plain_c_consumer_compiles_and_links(tmp_path):
 
 
 @pytest.mark.gpu
-def test_plain_c_consumer_runs_on_gpu(tmp_path):
+def test_plain_c_consumer_runs_on_gpu(tmp_path, cuda):
     import subprocess
     exe, env = _build_c_consumer(tmp_path)
     res = subprocess.run([exe], capture_output=True, text=True, env=env)
+    if res.returncode == 77:
+        pytest.skip('abi_smoke: no CUDA device')
     assert res.returncode == 0, (res.stdout, res.stderr)
     assert 'abi_smoke ok' in res.stdout
