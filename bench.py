@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument('--stress-input', default='boxes', choices=['boxes', 'clustered', 'anchors'],
                     help='--mode stress: random boxes (SURVEY §8d cfg 5), the clustered variant, '
                          'or RPN outputs on the COCO pyramid')
+    ap.add_argument('--lean', action='store_true',
+                    help='secondary workloads with large heads (VOC at 1000 proposals): one graph, '
+                         'no channels_last / TF32 / two-stream variants')
     ap.add_argument('--no-train-record', action='store_true',
                     help='skip the configs[2] training-step sub-record of the default line')
     ap.add_argument('--strong-total', type=int, default=16,
@@ -576,7 +579,7 @@ def bench_stress(args, rank, world, local_rank):
             boxes = torch.zeros((B, M, 5), dtype=torch.float32, device=dev)
             nums = []
             for b in range(B):   # mmcv batched_nms per image, ids = pyramid level (no host sync)
-                dets, _, num = ops._nms_raw(d_bx[b], d_sc[b], d_lv[b], 0.7, 0, num_ids=5)
+                dets, _, num = ops._nms_raw(d_bx[b], d_sc[b], d_lv[b], 0.7, 0, num_ids=5, max_num=M)
                 boxes[b] = dets[:M]
                 nums.append(num)
             return boxes, torch.cat(nums).clamp_(max=M)
@@ -709,6 +712,17 @@ def main():
     from boosting_rcnn_b200 import _lib, ops
     from boosting_rcnn_b200.registry import ConfigDict
     lib = _lib.load()
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # covers every timed loop
+    # ---- configs[2] training step at this N (gradient all-reduce over NVLink when N > 1).
+    # Runs first: it is an eager step that allocates through the default caching allocator,
+    # which slows down 3x once the inference graphs below hold most of the HBM in private pools
+    train = None
+    if not args.no_train_record:
+        import torch.distributed as tdist
+        train = train_record(args, rank, world, local_rank, tdist if world > 1 else None,
+                             cfg_name='coco', B=2, K=min(max(args.steps, 10), 20), W=3,
+                             with_stages=(rank == 0))
+        torch.cuda.empty_cache()
     rpn_head, roi_head = rpn_head.to(dev).eval(), roi_head.to(dev).eval()
     sizes, h_feats, h_cls, h_box, h_iou = make_inputs(B, pad_hw, A, C, seed=1234 + rank, pin=True)
     metas = img_metas_for(B, geom)
@@ -727,32 +741,36 @@ def main():
             props = rpn_head.get_bboxes_padded(d_cls, d_box, d_iou, metas)
             return roi_head.simple_test_bboxes_padded(feats, metas, props, test_rcnn, rescale=True)
         step, step_cl = (lambda: _eager(d_feats)), (lambda: _eager(d_feats_cl))
+        dual = g_tf32 = None
         l0 = lib.brcnn_launch_count()
         step()
         launches_per_step = int(lib.brcnn_launch_count() - l0)
     else:
         g_nchw = HotPathGraph(rpn_head, roi_head, metas, d_feats, d_cls, d_box, d_iou,
                               rcnn_test_cfg=test_rcnn, rescale=True)
-        g_cl = HotPathGraph(rpn_head, roi_head, metas, d_feats_cl, d_cls, d_box, d_iou,
-                            rcnn_test_cfg=test_rcnn, rescale=True)
-        step, step_cl = g_nchw.replay, g_cl.replay
+        step = g_nchw.replay
         launches_per_step = g_nchw.launches_per_replay
-        # two batches in flight on two streams (graph.py::DualStreamRunner)
-        from boosting_rcnn_b200.graph import DualStreamRunner
-        g_nchw2 = HotPathGraph(rpn_head, roi_head, metas, d_feats, d_cls, d_box, d_iou,
-                               rcnn_test_cfg=test_rcnn, rescale=True)
-        dual = DualStreamRunner([g_nchw, g_nchw2])
+        step_cl = dual = g_tf32 = None
+        if not args.lean:
+            g_cl = HotPathGraph(rpn_head, roi_head, metas, d_feats_cl, d_cls, d_box, d_iou,
+                                rcnn_test_cfg=test_rcnn, rescale=True)
+            step_cl = g_cl.replay
+            # two batches in flight on two streams (graph.py::DualStreamRunner)
+            from boosting_rcnn_b200.graph import DualStreamRunner
+            g_nchw2 = HotPathGraph(rpn_head, roi_head, metas, d_feats, d_cls, d_box, d_iou,
+                                   rcnn_test_cfg=test_rcnn, rescale=True)
+            dual = DualStreamRunner([g_nchw, g_nchw2])
 
-        # informational only: the reference pins PyTorch 1.7, whose default lets cuBLAS use
-        # TF32 for the 2-fc head on Ampere+; the headline keeps IEEE fp32 GEMMs
-        torch.backends.cuda.matmul.allow_tf32 = True
-        g_tf32 = HotPathGraph(rpn_head, roi_head, metas, d_feats, d_cls, d_box, d_iou,
-                              rcnn_test_cfg=test_rcnn, rescale=True)
-        torch.backends.cuda.matmul.allow_tf32 = False
+            # informational only: the reference pins PyTorch 1.7, whose default lets cuBLAS use
+            # TF32 for the 2-fc head on Ampere+; the headline keeps IEEE fp32 GEMMs
+            torch.backends.cuda.matmul.allow_tf32 = True
+            g_tf32 = HotPathGraph(rpn_head, roi_head, metas, d_feats, d_cls, d_box, d_iou,
+                                  rcnn_test_cfg=test_rcnn, rescale=True)
+            torch.backends.cuda.matmul.allow_tf32 = False
 
     # end to end: pinned host buffers -> H2D -> graph -> D2H, double buffered
     pipe = HostPipeline(rpn_head, roi_head, metas, (h_feats, h_cls, h_box, h_iou),
-                        rcnn_test_cfg=test_rcnn, rescale=True, slots=2)
+                        rcnn_test_cfg=test_rcnn, rescale=True, slots=1 if args.lean else 2)
 
     def barrier():
         if world > 1:
@@ -799,12 +817,11 @@ def main():
             torch.cuda.current_stream().wait_stream(pipe.compute_stream)
 
     W, K = max(args.warmup, 3), args.steps
-    sampler = ClockSampler(local_rank) if rank == 0 else None   # covers every timed loop
     ms_single = timed(step, K, W)
     launches = launches_per_step * K
-    ms_cl = timed(step_cl, K, W)
-    ms_tf32 = None if args.no_graph else timed(g_tf32.replay, K, W)
-    ms_dual = None if args.no_graph else timed(dual.step, K, W, drain=dual.drain)
+    ms_cl = timed(step_cl, K, W) if step_cl is not None else None
+    ms_tf32 = timed(g_tf32.replay, K, W) if (not args.no_graph and g_tf32 is not None) else None
+    ms_dual = timed(dual.step, K, W, drain=dual.drain) if (not args.no_graph and dual is not None) else None
     # headline: throughput with two batches in flight (one captured graph per stream);
     # --no-graph: the eager single-stream number
     ms = ms_dual if ms_dual is not None else ms_single
@@ -971,13 +988,6 @@ def main():
             strong['own_kernels_ms'] = sum(v for k, v in st.items() if k != 'fc_head_cublas')
             strong['limiter'] = max(st, key=st.get)
 
-    # ---- configs[2] training step at this N (gradient all-reduce over NVLink when N > 1) ----
-    train = None
-    if not args.no_train_record:
-        import torch.distributed as tdist
-        train = train_record(args, rank, world, local_rank, tdist if world > 1 else None,
-                             cfg_name='coco', B=2, K=min(max(K, 10), 20), W=3,
-                             with_stages=(rank == 0))
     clocks = sampler.stop() if sampler else None
 
     # ------------------------------------------------------------ CPU baseline
@@ -1009,7 +1019,7 @@ def main():
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': dict(base_cfg, feat_layout='NCHW-contiguous FPN maps in (reference neck '
                            'layout); NCHW->NHWC conversion kernels are inside the timed step'),
-            'value_single_stream_channels_last_feats': B * world * K / (ms_cl * 1e-3),
+            'value_single_stream_channels_last_feats': (B * world * K / (ms_cl * 1e-3)) if ms_cl else None,
             'value_single_stream': B * world * K / (ms_single * 1e-3),
             'two_stream_outputs_bit_identical': verified,
             'ms_per_step_single_stream': ms_single / K,

@@ -126,7 +126,7 @@ SIGNATURES = {
                                    c_float, c_float, c_void_p, c_void_p]),
     'brcnn_nms_workspace_bytes': (c_size_t, [c_int32]),
     'brcnn_batched_nms': (c_int32, [
-        c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_int32, c_void_p,
+        c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_int32, c_int32, c_void_p,
         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'brcnn_bbox2roi_padded': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
                                         c_void_p]),

@@ -79,20 +79,27 @@ __device__ __forceinline__ uint32_t ordered_bits(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// max over all 4K coordinates -> out[0] (single CTA; handles negatives)
-__global__ void __launch_bounds__(1024)
-nms_maxcoord_kernel(const float* __restrict__ boxes, int K, float* out) {
-  __shared__ float s[32];
+// max over all 4K coordinates (handles negatives).  Multi-CTA: every block reduces its slice
+// and does one atomicMax on the order-preserving bit pattern in `bits` (zeroed by the caller:
+// 0 orders below every float); nms_maxcoord_finish turns the pattern back into out[0].
+__global__ void __launch_bounds__(256)
+nms_maxcoord_kernel(const float* __restrict__ boxes, int K, unsigned int* __restrict__ bits) {
+  __shared__ float s[8];
   float m = -INFINITY;
-  for (int i = threadIdx.x; i < 4 * K; i += blockDim.x) m = fmaxf(m, boxes[i]);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * K; i += gridDim.x * blockDim.x)
+    m = fmaxf(m, boxes[i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s[w]);
-    out[0] = m;
+    atomicMax(bits, ordered_bits(m));
   }
+}
+__global__ void nms_maxcoord_finish_kernel(const unsigned int* __restrict__ bits, float* out) {
+  const unsigned int u = bits[0];
+  out[0] = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
 // rank by counting: rank_i = #{j : key_j > key_i}; scatter sorted arrays.
@@ -133,14 +140,15 @@ nms_rank_scatter_kernel(const float* __restrict__ boxes,
 }
 
 // Sort by (id asc, score desc, index asc) by counting: position of box i =
-// #{j : id_j < id_i} + #{j : id_j == id_i, key_j > key_i}.  Writes the raw boxes
-// and keys in that order plus the start / size of every id's list (ids in
-// [0, num_ids); idxs == nullptr: one list).
+// #{j : id_j < id_i} + #{j : id_j == id_i, key_j > key_i}.  The K x K comparison is split over
+// a 2-D grid (x: 256 boxes i, y: a slice of the boxes j) with integer atomics into lt / rank
+// (order independent, deterministic); nms_id_scatter_kernel then writes the raw boxes and keys
+// in that order plus the start / size of every id's list (ids in [0, num_ids); idxs == nullptr:
+// one list).  (One CTA column per 256 boxes looping over all K took 0.36 ms at K = 20 000.)
+constexpr int NMS_RANK_JSPLIT = 2048;   // boxes j per CTA row
 __global__ void __launch_bounds__(256)
-nms_id_rank_scatter_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
-                           const int64_t* __restrict__ idxs, int K, int num_ids,
-                           float4* __restrict__ sorted_boxes, u64* __restrict__ sorted_key,
-                           int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_count) {
+nms_id_rank_count_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idxs, int K,
+                         int32_t* __restrict__ lt_out, int32_t* __restrict__ rank_out) {
   __shared__ u64 t_key[256];
   __shared__ int t_id[256];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -151,27 +159,42 @@ nms_id_rank_scatter_kernel(const float* __restrict__ boxes, const float* __restr
     if (idxs != nullptr) my_id = (int)idxs[i];
   }
   int lt = 0, rank = 0;
-  for (int j0 = 0; j0 < K; j0 += 256) {
+  const int j_begin = blockIdx.y * NMS_RANK_JSPLIT, j_end = min(K, j_begin + NMS_RANK_JSPLIT);
+  for (int j0 = j_begin; j0 < j_end; j0 += 256) {
     const int j = j0 + threadIdx.x;
     __syncthreads();
-    t_key[threadIdx.x] = (j < K)
+    t_key[threadIdx.x] = (j < j_end)
         ? (((u64)ordered_bits(scores[j]) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)j)) : 0ull;
-    t_id[threadIdx.x] = (j < K) ? (idxs != nullptr ? (int)idxs[j] : 0) : 0x7fffffff;
+    t_id[threadIdx.x] = (j < j_end) ? (idxs != nullptr ? (int)idxs[j] : 0) : 0x7fffffff;
     __syncthreads();
-    const int m = min(256, K - j0);
+    const int m = min(256, j_end - j0);
     for (int t = 0; t < m; ++t) {
       const int id = t_id[t];
       lt += (id < my_id);
       rank += (id == my_id) && (t_key[t] > mine);
     }
   }
-  if (i < K && my_id >= 0 && my_id < num_ids) {
-    const int pos = lt + rank;
-    sorted_boxes[pos] = reinterpret_cast<const float4*>(boxes)[i];
-    sorted_key[pos] = mine;
-    if (rank == 0) seg_start[my_id] = lt;     // the best box of the id
-    atomicAdd(seg_count + my_id, 1);
+  if (i < K) {
+    if (lt) atomicAdd(lt_out + i, lt);
+    if (rank) atomicAdd(rank_out + i, rank);
   }
+}
+__global__ void __launch_bounds__(256)
+nms_id_scatter_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                      const int64_t* __restrict__ idxs, int K, int num_ids,
+                      const int32_t* __restrict__ lt_in, const int32_t* __restrict__ rank_in,
+                      float4* __restrict__ sorted_boxes, u64* __restrict__ sorted_key,
+                      int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const int my_id = idxs != nullptr ? (int)idxs[i] : 0;
+  if (my_id < 0 || my_id >= num_ids) return;
+  const int lt = lt_in[i], rank = rank_in[i];
+  const int pos = lt + rank;
+  sorted_boxes[pos] = reinterpret_cast<const float4*>(boxes)[i];
+  sorted_key[pos] = ((u64)ordered_bits(scores[i]) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)i);
+  if (rank == 0) seg_start[my_id] = lt;     // the best box of the id
+  atomicAdd(seg_count + my_id, 1);
 }
 
 __global__ void nms_finalize_kernel(const float* __restrict__ boxes,
@@ -701,12 +724,33 @@ struct OpMergeEpilogue {
   __device__ void pad(int, int) const {}
 };
 
+// (id asc, score desc, index asc) counting sort; lt / rank scratch = order + kept_pos arrays
+static int launch_id_sort(const float* boxes, const float* scores, const int64_t* idxs, int K,
+                          int num_ids, int32_t* lt, int32_t* rank, float4* sboxes, u64* skey,
+                          int32_t* seg_start, int32_t* seg_count, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(lt, 0, (size_t)K * 4, stream);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(rank, 0, (size_t)K * 4, stream);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((K + 255) / 256, (K + NMS_RANK_JSPLIT - 1) / NMS_RANK_JSPLIT);
+  nms_id_rank_count_kernel<<<grid, 256, 0, stream>>>(scores, idxs, K, lt, rank);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  nms_id_scatter_kernel<<<(K + 255) / 256, 256, 0, stream>>>(boxes, scores, idxs, K, num_ids, lt,
+                                                            rank, sboxes, skey, seg_start,
+                                                            seg_count);
+  g_launch_count_add(1);
+  BRCNN_CUDA_CHECK_LAST();
+  return BRCNN_OK;
+}
+
 int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* idxs,
                       int32_t K, int32_t num_ids, float iou_threshold, int32_t offset,
-                      int64_t* keep, float* dets, int32_t* num_keep,
+                      int32_t max_num, int64_t* keep, float* dets, int32_t* num_keep,
                       void* workspace, size_t workspace_bytes,
                       brcnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const int max_keep = (max_num > 0 && max_num < K) ? max_num : K;   // early stop of the sweeps
   if (K < 0 || !num_keep || (offset != 0 && offset != 1)) return BRCNN_ERR_ARG;
   if (K == 0) {
     cudaError_t e = cudaMemsetAsync(num_keep, 0, 4, stream);
@@ -727,8 +771,14 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
   int32_t* kept_pos = (int32_t*)(ws + w.kept_pos);
   int32_t* kept_count = (int32_t*)(ws + w.kept_count);
   if (idxs != nullptr) {
-    nms_maxcoord_kernel<<<1, 1024, 0, stream>>>(boxes, K, maxc);
-    g_launch_count_add(1);
+    unsigned int* maxbits = (unsigned int*)(ws + w.count);   // free until the fallback path
+    cudaError_t em = cudaMemsetAsync(maxbits, 0, 4, stream);
+    if (em != cudaSuccess) return (int)em;
+    int mb = (4 * K + 256 * 16 - 1) / (256 * 16);
+    if (mb > 512) mb = 512;
+    nms_maxcoord_kernel<<<mb, 256, 0, stream>>>(boxes, K, maxbits);
+    nms_maxcoord_finish_kernel<<<1, 1, 0, stream>>>(maxbits, maxc);
+    g_launch_count_add(2);
     BRCNN_CUDA_CHECK_LAST();
   }
   // ---- clustered path: the ids are <= BRCNN_MAX_LEVELS sorted lists walked in global
@@ -740,17 +790,16 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
       return e && e[0] == 'o';
     }();
     const int L = (idxs == nullptr) ? 1 : num_ids;
-    const RpnNmsImageSmem lay = rpn_nms_image_smem(L > 0 ? L : 1, K, RNI_CLUSTER);
+    const RpnNmsImageSmem lay = rpn_nms_image_smem(L > 0 ? L : 1, max_keep, RNI_CLUSTER);
     if (!force_old && L >= 1 && L <= BRCNN_MAX_LEVELS && lay.total <= 160 * 1024 &&
         lay.kp <= 65535) {
       int32_t* seg_start = (int32_t*)(ws + w.seg);
       int32_t* seg_count = seg_start + BRCNN_MAX_LEVELS;
       cudaError_t e = cudaMemsetAsync(seg_start, 0, 2 * BRCNN_MAX_LEVELS * 4, stream);
       if (e != cudaSuccess) return (int)e;
-      nms_id_rank_scatter_kernel<<<(K + 255) / 256, 256, 0, stream>>>(
-          boxes, scores, idxs, K, L, sboxes, skey, seg_start, seg_count);
-      g_launch_count_add(1);
-      BRCNN_CUDA_CHECK_LAST();
+      const int rcs = launch_id_sort(boxes, scores, idxs, K, L, order, kept_pos, sboxes, skey,
+                                     seg_start, seg_count, stream);
+      if (rcs) return rcs;
       if (lay.total > 32 * 1024) {
         e = ensure_dyn_smem((const void*)rpn_nms_image_kernel<RNI_CLUSTER>, lay.total);
         if (e != cudaSuccess) return (int)e;
@@ -772,7 +821,7 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
                              (const u64*)skey, (const uint8_t*)nullptr,
                              (const int32_t*)seg_count, L, (int)K, iou_threshold,
                              idxs != nullptr ? (const float*)maxc : (const float*)nullptr,
-                             (int)K, (float*)nullptr, num_keep, lay, (long long*)nullptr,
+                             (int)max_keep, (float*)nullptr, num_keep, lay, (long long*)nullptr,
                              (const int32_t*)seg_start, (float)offset, keep);
       if (e != cudaSuccess) return (int)e;
       g_launch_count_add(1);
@@ -805,10 +854,10 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
       int32_t* seg_count = seg_start + NMS_MAX_IDS;
       cudaError_t e = cudaMemsetAsync(seg_start, 0, 2 * NMS_MAX_IDS * 4, stream);
       if (e != cudaSuccess) return (int)e;
-      nms_id_rank_scatter_kernel<<<(K + 255) / 256, 256, 0, stream>>>(
-          boxes, scores, idxs, K, num_ids, sboxes, skey, seg_start, seg_count);
-      g_launch_count_add(1);
-      BRCNN_CUDA_CHECK_LAST();
+      const int rcs = launch_id_sort(boxes, scores, idxs, K, num_ids, order,
+                                     (int32_t*)(ws + w.mask), sboxes, skey, seg_start, seg_count,
+                                     stream);
+      if (rcs) return rcs;
       const size_t smem = (size_t)keep_pad * 20;
       if (smem > 48 * 1024) {
         e = ensure_dyn_smem((const void*)nms_fused_kernel, smem);
@@ -817,7 +866,7 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
       u64* kept_key = (u64*)(ws + w.mask);   // K u64, the bitmask area is unused on this path
       nms_fused_kernel<<<num_ids, NMS_FUSED_THREADS, smem, stream>>>(
           sboxes, nullptr, seg_count, K, iou_threshold, (float)offset, maxc, num_ids, skey,
-          kept_pos, kept_key, kept_count_ids(ws, w), K, K, keep_pad, seg_start);
+          kept_pos, kept_key, kept_count_ids(ws, w), K, max_keep, keep_pad, seg_start);
       g_launch_count_add(1);
       BRCNN_CUDA_CHECK_LAST();
       const size_t sm = (size_t)np2 * 8;
@@ -829,12 +878,13 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
         }
         OpMergeEpilogue ep{keep};
         nms_merge_sort_kernel<OpMergeEpilogue><<<1, 1024, sm, stream>>>(
-            kept_key, kept_count_ids(ws, w), num_ids, K, K, np2, num_keep, ep, seg_start);
+            kept_key, kept_count_ids(ws, w), num_ids, K, max_keep, np2, num_keep, ep, seg_start);
       } else {
         // COCO-scale inputs (K = 20 480, 80 ids): rank counting over the whole GPU
         dim3 mgrid((unsigned)((K + 255) / 256), (unsigned)num_ids);
         nms_op_merge_rank_kernel<<<mgrid, 256, 0, stream>>>(kept_key, kept_count_ids(ws, w),
-                                                           seg_start, num_ids, keep, num_keep);
+                                                           seg_start, num_ids, max_keep, keep,
+                                                           num_keep);
       }
       g_launch_count_add(1);
       BRCNN_CUDA_CHECK_LAST();
@@ -853,7 +903,7 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
   BRCNN_CUDA_CHECK_LAST();
   int rc = launch_nms_segments(sboxes, nullptr, count, 1, K, iou_threshold,
                                (float)offset, nullptr, 1, mask, nullptr, kept_pos,
-                               nullptr, kept_count, K, K, stream);
+                               nullptr, kept_count, K, max_keep, stream);
   if (rc) return rc;
   nms_finalize_kernel<<<(K + 255) / 256, 256, 0, stream>>>(
       boxes, scores, order, kept_pos, kept_count, keep, dets, num_keep);
@@ -1182,9 +1232,11 @@ static int roi_bwd3_launch(RoiArgs a, const float* grad_out, int out_layout, con
     for (int c = 0; c < 2; ++c)
       if (h[c * 8])
         fprintf(stderr, "[gather3 %s] ctas=%llu mean cycles: list=%llu first=%llu walk=%llu "
-                "store=%llu  rois/cta=%.2f\n", c ? "busy " : "empty", h[c * 8],
+                "store=%llu  rois/cta=%.2f  warp0: wait-in-walk=%llu stages=%.2f\n",
+                c ? "busy " : "empty", h[c * 8],
                 h[c * 8 + 1] / h[c * 8], h[c * 8 + 2] / h[c * 8], h[c * 8 + 3] / h[c * 8],
-                h[c * 8 + 4] / h[c * 8], (double)h[c * 8 + 5] / h[c * 8]);
+                h[c * 8 + 4] / h[c * 8], (double)h[c * 8 + 5] / h[c * 8], h[c * 8 + 6] / h[c * 8],
+                (double)h[c * 8 + 7] / h[c * 8]);
   }
 #else
   roi_bwd_gather3_kernel<<<grid, B3_THREADS, smem, stream>>>(ba, bucket_rec, bucket, bucket_cnt,

@@ -425,14 +425,14 @@ nms_merge_kernel(const int32_t* __restrict__ kept_pos,
 // grid (ceil(max_len / 256), Sg).
 __global__ void __launch_bounds__(256)
 nms_op_merge_rank_kernel(const u64* __restrict__ kept_key, const int32_t* __restrict__ kept_count,
-                         const int32_t* __restrict__ seg_start, int Sg,
+                         const int32_t* __restrict__ seg_start, int Sg, int max_out,
                          int64_t* __restrict__ keep, int32_t* __restrict__ num_keep) {
   const int g = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (g == 0 && j == 0) {
     int tot = 0;
     for (int i = 0; i < Sg; ++i) tot += kept_count[i];
-    num_keep[0] = tot;
+    num_keep[0] = min(tot, max_out);
   }
   if (j >= kept_count[g]) return;
   const u64 key = kept_key[(size_t)seg_start[g] + j];
@@ -440,9 +440,10 @@ nms_op_merge_rank_kernel(const u64* __restrict__ kept_key, const int32_t* __rest
   for (int g2 = 0; g2 < Sg; ++g2) {
     if (g2 == g) continue;
     const int n2 = kept_count[g2];
-    if (n2 > 0) rank += count_greater_desc(kept_key + (size_t)seg_start[g2], n2, key);
+    if (n2 > 0 && rank < max_out)
+      rank += count_greater_desc(kept_key + (size_t)seg_start[g2], n2, key);
   }
-  keep[rank] = (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+  if (rank < max_out) keep[rank] = (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
 }
 
 // Same contract, for epilogues that identify the element from its key alone

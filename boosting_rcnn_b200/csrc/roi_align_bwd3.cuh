@@ -94,7 +94,7 @@ roi_bwd_gather3_kernel(const __grid_constant__ RoiBwd3Args ba,
 #endif
                        ) {
 #ifdef BRCNN_DEBUG_TIMING
-  long long dt0 = clock64(), dt1 = dt0, dt2 = dt0, dt3 = dt0;
+  long long dt0 = clock64(), dt1 = dt0, dt2 = dt0, dt3 = dt0, dwait = 0, dstages = 0;
   int dn = 0, dfirst = 1;
 #endif
   extern __shared__ __align__(128) unsigned char b3_smem[];
@@ -310,9 +310,14 @@ roi_bwd_gather3_kernel(const __grid_constant__ RoiBwd3Args ba,
           while (true) {
             const unsigned char* st = b3_smem + (size_t)c_stage * B3_STAGE;
             const float* hdr = reinterpret_cast<const float*>(st);
+#ifdef BRCNN_DEBUG_TIMING
+            const long long dw0 = clock64();
+#endif
             mbar_wait_addr(full0 + 8u * c_stage, (uint32_t)(c_round & 1));
 #ifdef BRCNN_DEBUG_TIMING
             if (dfirst) { dt2 = clock64(); dfirst = 0; }
+            else { dwait += clock64() - dw0; }
+            ++dstages;
 #endif
             const int4 m = *reinterpret_cast<const int4*>(hdr + B3_OFF_META);
             const int npw = *reinterpret_cast<const int*>(hdr + B3_OFF_META + 4);
@@ -402,6 +407,8 @@ roi_bwd_gather3_kernel(const __grid_constant__ RoiBwd3Args ba,
     atomicAdd(dbg + cls * 8 + 3, (unsigned long long)(dt3 - dt2));   // walk
     atomicAdd(dbg + cls * 8 + 4, (unsigned long long)(dt4 - dt3));   // stores
     atomicAdd(dbg + cls * 8 + 5, (unsigned long long)dn);
+    atomicAdd(dbg + cls * 8 + 6, (unsigned long long)dwait);     // warp 0: waits after the first
+    atomicAdd(dbg + cls * 8 + 7, (unsigned long long)dstages);
   }
 #endif
 }

@@ -283,10 +283,11 @@ def rpn_loss(params, cls_scores, bbox_preds, iou_preds, base_anchors, gt_boxes, 
 # mmcv.ops.nms / batched_nms mirrors
 # --------------------------------------------------------------------------
 @_device_guard
-def _nms_raw(boxes, scores, idxs, iou_threshold, offset, num_ids=None):
+def _nms_raw(boxes, scores, idxs, iou_threshold, offset, num_ids=None, max_num=-1):
     """-> (dets (K,5), keep (K,), num (1,) int32): padded outputs + device count, no host sync.
     ``num_ids``: caller's bound on the id range (ids in [0, num_ids)); None = unknown (the
-    library then treats the boxes as one segment of offset boxes, like mmcv)."""
+    library then treats the boxes as one segment of offset boxes, like mmcv).  ``max_num``: only
+    the first max_num keeps are wanted (the sweeps stop there)."""
     lib = _lib.load()
     boxes = _f32c(boxes, 'boxes')
     scores = _f32c(scores, 'scores')
@@ -305,7 +306,7 @@ def _nms_raw(boxes, scores, idxs, iou_threshold, offset, num_ids=None):
     rc = lib.brcnn_batched_nms(
         boxes.data_ptr(), scores.data_ptr(),
         idxs.data_ptr() if idxs is not None else None, K, nid, float(iou_threshold),
-        int(offset), keep.data_ptr(), dets.data_ptr(), num.data_ptr(),
+        int(offset), int(max_num), keep.data_ptr(), dets.data_ptr(), num.data_ptr(),
         ws.data_ptr(), ws.numel(), _stream())
     check(rc, 'brcnn_batched_nms')
     return dets, keep, num
@@ -326,7 +327,7 @@ def nms(boxes, scores, iou_threshold, offset=0, score_threshold=0, max_num=-1):
         valid_mask = scores > score_threshold
         valid_inds = torch.nonzero(valid_mask, as_tuple=False).squeeze(dim=1)
         boxes, scores = boxes[valid_mask], scores[valid_mask]
-    dets, inds = _trim(*_nms_raw(boxes, scores, None, iou_threshold, offset))
+    dets, inds = _trim(*_nms_raw(boxes, scores, None, iou_threshold, offset, max_num=max_num))
     if max_num > 0:
         dets, inds = dets[:max_num], inds[:max_num]
     if valid_inds is not None:
@@ -353,7 +354,7 @@ def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
     if not class_agnostic and num_ids is None and boxes.size(0) > 0:
         num_ids = int(idxs.max().item()) + 1 if int(idxs.min().item()) >= 0 else 0
     dets, keep = _trim(*_nms_raw(boxes, scores, None if class_agnostic else idxs,
-                                 iou_threshold, 0, num_ids))
+                                 iou_threshold, 0, num_ids, max_num))
     if max_num > 0:
         dets, keep = dets[:max_num], keep[:max_num]
     return dets, keep

@@ -172,12 +172,14 @@ size_t brcnn_nms_workspace_bytes(int32_t num_boxes);
  *   8 < num_ids <= 1024 and num_boxes <= 8192 (class-wise NMS): one fused-NMS CTA
  *     per id on the id-sorted boxes, kept lists merged by an in-smem sort;
  *   otherwise: one segment of offset boxes (mmcv's formulation).
+ * max_num: mmcv's `max_num` (nms(...) argument / nms_cfg key): only the first max_num keeps
+ *   are wanted (<= 0: all); the sweep stops there instead of slicing afterwards.
  * keep: int64[num_boxes] (first *num_keep entries valid, score-descending),
  * dets: optional float[num_boxes][5] rows cat(boxes[keep], scores[keep]).     */
 int brcnn_batched_nms(const float* boxes, const float* scores,
                       const int64_t* idxs, int32_t num_boxes, int32_t num_ids,
-                      float iou_threshold, int32_t offset, int64_t* keep,
-                      float* dets, int32_t* num_keep, void* workspace,
+                      float iou_threshold, int32_t offset, int32_t max_num,
+                      int64_t* keep, float* dets, int32_t* num_keep, void* workspace,
                       size_t workspace_bytes, brcnn_stream_t stream);
 
 /* ------------------------------------------------------------------------

@@ -37,7 +37,7 @@ int main(void) {
   CK(cudaMalloc(&d_ws, ws_bytes));
   CK(cudaMemcpy(d_boxes, boxes, sizeof(boxes), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_scores, scores, sizeof(scores), cudaMemcpyHostToDevice));
-  int rc = brcnn_batched_nms(d_boxes, d_scores, NULL, 6, 1, 0.7f, 0, d_keep, d_dets, d_num, d_ws,
+  int rc = brcnn_batched_nms(d_boxes, d_scores, NULL, 6, 1, 0.7f, 0, -1, d_keep, d_dets, d_num, d_ws,
                              ws_bytes, NULL /* default stream */);
   if (rc != BRCNN_OK) { fprintf(stderr, "brcnn_batched_nms rc=%d\n", rc); return 1; }
   CK(cudaDeviceSynchronize());
@@ -53,9 +53,9 @@ int main(void) {
     return 1;
   }
   /* argument errors are return codes, not crashes */
-  if (brcnn_batched_nms(NULL, d_scores, NULL, 6, 1, 0.7f, 0, d_keep, d_dets, d_num, d_ws,
+  if (brcnn_batched_nms(NULL, d_scores, NULL, 6, 1, 0.7f, 0, -1, d_keep, d_dets, d_num, d_ws,
                         ws_bytes, NULL) != BRCNN_ERR_ARG) return 1;
-  if (brcnn_batched_nms(d_boxes, d_scores, NULL, 6, 1, 0.7f, 0, d_keep, d_dets, d_num, d_ws, 16,
+  if (brcnn_batched_nms(d_boxes, d_scores, NULL, 6, 1, 0.7f, 0, -1, d_keep, d_dets, d_num, d_ws, 16,
                         NULL) != BRCNN_ERR_WORKSPACE) return 1;
   /* ---- delta2bbox doctest: rois [0,0,1,1] / [5,5,5,5], zero deltas, max_shape (32,32) ---- */
   const float rois[2][4] = {{0, 0, 1, 1}, {5, 5, 5, 5}};

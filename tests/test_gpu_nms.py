@@ -130,7 +130,7 @@ def test_batched_nms_coco_scale_many_ids(cuda, n, nid, clustered):
     scores = _scores(n, n + 3, dup=True)
     ids = np.random.RandomState(n + 1).randint(0, nid, n).astype(np.int64)
     t = lambda a: torch.from_numpy(a).to(cuda)
-    ref = oracle.batched_nms(boxes, scores, ids, 0.5)
+    _, ref = oracle.batched_nms(boxes, scores, ids, 0.5)
     for cfg in (dict(type='nms', iou_threshold=0.5), dict(type='nms', iou_threshold=0.5, num_ids=nid)):
         dets, keep = ops.batched_nms(t(boxes), t(scores), t(ids), cfg)
         np.testing.assert_array_equal(keep.cpu().numpy(), ref)
@@ -150,6 +150,22 @@ def test_batched_nms_one_id_with_more_keeps_than_shared_memory(cuda):
     scores = rng.permutation(len(boxes)).astype(np.float32) / len(boxes)
     t = lambda a: torch.from_numpy(a).to(cuda)
     dets, keep = ops.batched_nms(t(boxes), t(scores), t(ids), dict(type='nms', iou_threshold=0.5))
-    ref = oracle.batched_nms(boxes, scores, ids, 0.5)
+    _, ref = oracle.batched_nms(boxes, scores, ids, 0.5)
     assert (ids[ref] == 0).sum() == n0
     np.testing.assert_array_equal(keep.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize('n,nid,max_num', [(4693, 5, 256), (20000, 5, 2000), (20480, 80, 100),
+                                           (5000, 80, 100), (300, 3, 1000)])
+def test_batched_nms_max_num_stops_early_with_the_same_prefix(cuda, n, nid, max_num):
+    """nms_cfg['max_num'] (mmcv slices keep[:max_num] after the full NMS): the library stops its
+    sweeps at max_num keeps; the result is the same prefix of the full keep list."""
+    boxes = synth.random_boxes(n, 800, 1333, seed=3 * n + nid, clustered=True)
+    scores = _scores(n, n + 5, dup=True)
+    ids = np.random.RandomState(n + 2).randint(0, nid, n).astype(np.int64)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    ref = oracle.batched_nms(boxes, scores, ids, 0.7)[1][:max_num]
+    dets, keep = ops.batched_nms(t(boxes), t(scores), t(ids),
+                                 dict(type='nms', iou_threshold=0.7, max_num=max_num, num_ids=nid))
+    np.testing.assert_array_equal(keep.cpu().numpy(), ref)
+    np.testing.assert_array_equal(dets.cpu().numpy()[:, :4], boxes[ref])

@@ -82,7 +82,7 @@ def summarize(tag, mode, traffic):
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+    tag = sys.argv[1] if len(sys.argv) > 1 else 'r02'
     os.makedirs(PROF, exist_ok=True)
     tool = os.path.join(ROOT, 'tools', 'ncu_launch_summary.py')
     for mode in ('infer', 'train'):
@@ -109,10 +109,17 @@ def main():
             traffic_all[key] = {k: sum(v) / len(v) for k, v in traffic.items()}
             traffic_all[key]['_source'] = f'profiles/{tag}_ncu_full_{mode}.txt'
     json.dump(traffic_all, open(os.path.join(PROF, 'ncu_traffic.json'), 'w'), indent=1, sort_keys=True)
-    for name in ('bench_infer', 'bench_train', 'bench_stress', 'bench_reference'):
-        src = os.path.join(OUT, f'{tag}_{name}.json')
+    for name in ('bench_infer.json', 'bench_train.json', 'bench_stress.json',
+                 'bench_stress_clustered.json', 'bench_stress_anchors.json', 'bench_voc1000.json',
+                 'bench_coco_infer.json', 'bench_reference.json', 'nms_microbench.txt',
+                 'roi_microbench_infer.json', 'roi_microbench_train.json'):
+        src = os.path.join(OUT, f'{tag}_{name}')
         if os.path.exists(src) and os.path.getsize(src) > 0:
-            open(os.path.join(PROF, f'{tag}_{name}.json'), 'w').write(open(src).read())
+            text = open(src).read()
+            if name.endswith('.json'):      # keep the JSON line only (NCCL / warnings go to stdout too)
+                js = [l for l in text.splitlines() if l.startswith('{')]
+                text = (js[-1] + '\n') if js else text
+            open(os.path.join(PROF, f'{tag}_{name}'), 'w').write(text)
     smi = os.path.join(OUT, f'{tag}_nvidia_smi.csv')
     if os.path.exists(smi):
         open(os.path.join(PROF, f'{tag}_nvidia_smi.csv'), 'w').write(open(smi).read())
