@@ -19,6 +19,7 @@
 #include "roi_align_bwd.cuh"
 #include "roi_align_bwd2.cuh"
 #include "roi_align_bwd3.cuh"
+#include "roi_align_bwd4.cuh"
 #include "roi_align_fwd3.cuh"
 #include "roi_align_tma.cuh"
 #include "rpn.cuh"
@@ -1197,6 +1198,8 @@ static int roi_bwd3_launch(RoiArgs a, const float* grad_out, int out_layout, con
     memset(&bk, 0, sizeof(bk));
     bk.bucket = bucket; bk.bucket_rec = bucket_rec; bk.bucket_cnt = bucket_cnt;
     bk.tile_cnt = tile_cnt; bk.tile_side = B3_TS;
+    bk.tile_r = (int32_t*)(ws + w.tile_r); bk.tile_rec = (RoiBwdRec*)(ws + w.tile_rec);
+    bk.tile_cap = B4_TILE_CAP;
     for (int l = 0; l < a.L; ++l) {
       bk.tiles_x[l] = ba.tiles_x[l]; bk.tiles_y[l] = ba.tiles_y[l];
       bk.tile_first[l] = ba.tile_first[l];
@@ -1213,6 +1216,26 @@ static int roi_bwd3_launch(RoiArgs a, const float* grad_out, int out_layout, con
   dim3 grid((unsigned)base, (a.C + B3_CS - 1) / B3_CS);
   if (grid.y > 65535) return BRCNN_ERR_UNSUPPORTED;
   const size_t smem = (size_t)B3_NS * B3_STAGE;
+  static const bool use_v3 = [] {
+    const char* e = getenv("BRCNN_ROI_BWD");
+    return e && e[0] == 'v' && e[1] == '3';
+  }();
+  if (!use_v3 && (long long)base * grid.y <= 0x7fffffffLL) {
+    // v4: persistent CTAs pulling (tile, slab) items from an atomic counter
+    static_assert(B4_TILE_CAP == B4_CAP, "tile list capacity");
+    e = ensure_dyn_smem((const void*)roi_bwd_gather4_kernel, smem, true);
+    if (e != cudaSuccess) return (int)e;
+    const long long items = (long long)base * grid.y;
+    const int slots = 3 * sm_count();
+    const unsigned nblk = (unsigned)(items < slots ? items : slots);
+    roi_bwd_gather4_kernel<<<nblk, B3_THREADS, smem, stream>>>(
+        ba, (const int32_t*)(ws + w.tile_r), (const RoiBwdRec*)(ws + w.tile_rec), tile_cnt,
+        bucket_rec, bucket, bucket_cnt, (int32_t*)(ws + w.work_counter), (int)base, (int)grid.y,
+        R, tab, gt);
+    g_launch_count_add(1);
+    BRCNN_CUDA_CHECK_LAST();
+    return BRCNN_OK;
+  }
   e = ensure_dyn_smem((const void*)roi_bwd_gather3_kernel, smem, true);
   if (e != cudaSuccess) return (int)e;
 #ifdef BRCNN_DEBUG_TIMING

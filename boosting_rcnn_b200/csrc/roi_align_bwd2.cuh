@@ -45,6 +45,9 @@ struct RoiBwdBuckets {
   RoiBwdRec* bucket_rec; // [B*L][R] their footprint boxes (same order)
   int32_t* bucket_cnt;   // [B*L]
   int32_t* tile_cnt;     // [tiles] number of RoIs whose footprint box touches the tile
+  int32_t* tile_r;       // [tiles][tile_cap] their ids (arrival order; only the first tile_cap)
+  RoiBwdRec* tile_rec;   // [tiles][tile_cap] and footprint boxes
+  int tile_cap;
   int tile_side;
   int tiles_x[BRCNN_MAX_LEVELS], tiles_y[BRCNN_MAX_LEVELS], tile_first[BRCNN_MAX_LEVELS];
 };
@@ -99,7 +102,13 @@ roi_bwd_prep_kernel(const __grid_constant__ RoiArgs a, const float* __restrict__
                   (size_t)g.b * bk.tiles_x[g.lvl] * bk.tiles_y[g.lvl];
     for (int i = tid; i < ntx * nty; i += 128) {
       const int dy = i / ntx, dx = i - dy * ntx;
-      atomicAdd(tc + (ty0 + dy) * bk.tiles_x[g.lvl] + tx0 + dx, 1);
+      int32_t* cell = tc + (ty0 + dy) * bk.tiles_x[g.lvl] + tx0 + dx;
+      const int pos = atomicAdd(cell, 1);
+      if (bk.tile_r != nullptr && pos < bk.tile_cap) {
+        const size_t slot = (size_t)(cell - bk.tile_cnt) * bk.tile_cap + pos;
+        bk.tile_r[slot] = r;
+        bk.tile_rec[slot] = rec;
+      }
     }
   }
   const int fh = rec.yhi - rec.ylo + 1, fw = rec.xhi - rec.xlo + 1;

@@ -414,8 +414,10 @@ roi_bwd_gather3_kernel(const __grid_constant__ RoiBwd3Args ba,
 }
 
 struct RoiBwd3Ws {
-  size_t recs, keys, tab, gt, bucket_cnt, tile_cnt, zero_bytes, bucket, bucket_rec, total;
+  size_t recs, keys, tab, gt, bucket_cnt, tile_cnt, work_counter, zero_bytes, bucket, bucket_rec,
+      tile_r, tile_rec, total;
 };
+constexpr int B4_TILE_CAP = 128;   // == B4_CAP (roi_align_bwd4.cuh)
 static inline long long roi_bwd3_tiles(const RoiArgs& a) {
   long long t = 0;
   for (int l = 0; l < a.L; ++l)
@@ -435,9 +437,12 @@ static inline RoiBwd3Ws roi_bwd3_ws(const RoiArgs& a, int R, bool need_transpose
   w.gt = o;   o = al(o + (need_transpose ? Rn * (size_t)a.PH * a.PW * a.C * 4 : 0));
   w.bucket_cnt = o; o = al(o + (size_t)a.B * a.L * 4);
   w.tile_cnt = o;   o = al(o + (size_t)roi_bwd3_tiles(a) * 4);
-  w.zero_bytes = o - w.bucket_cnt;                 // bucket_cnt + tile_cnt: one memset
+  w.work_counter = o; o = al(o + 4);
+  w.zero_bytes = o - w.bucket_cnt;                 // bucket_cnt + tile_cnt + counter: one memset
   w.bucket = o;     o = al(o + (size_t)a.B * a.L * Rn * 4);
   w.bucket_rec = o; o = al(o + (size_t)a.B * a.L * Rn * sizeof(RoiBwdRec));
+  w.tile_r = o;     o = al(o + (size_t)roi_bwd3_tiles(a) * B4_TILE_CAP * 4);
+  w.tile_rec = o;   o = al(o + (size_t)roi_bwd3_tiles(a) * B4_TILE_CAP * sizeof(RoiBwdRec));
   w.total = o;
   return w;
 }

@@ -72,6 +72,18 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
   } while (!ok);
 }
+// same, with a suspend-time hint: an idle waiter is parked by the hardware for up to `ns`
+// nanoseconds per try instead of spinning through the issue slots the busy warps need
+__device__ __forceinline__ void mbar_wait_addr_hint(uint32_t addr, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity), "r"(ns) : "memory");
+  } while (!ok);
+}
 // 1-D bulk copy global -> shared, completion bytes on `bar`
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes,
                                             uint64_t* bar) {

@@ -481,7 +481,7 @@ def rpn_anchor_targets(gt_bboxes, img_metas, base_anchors, strides, sizes, pos_i
 def rpn_loss(cls, box, iou, gt_bboxes, img_metas, base_anchors, strides, gamma=0.5,
              focal_gamma=2.0, focal_alpha=0.25, w_cls=1.0, w_bbox=1.0, w_iou=1.0, w_aug=1.0,
              pos_iou_thr=0.5, neg_iou_thr=0.5, min_pos_iou=0.0, wh_ratio_clip=16 / 1000,
-             world_size=1, other_ranks_num_pos=0.0, other_ranks_iou_sum=0.0):
+             world_size=1, other_ranks_num_pos=0.0, other_ranks_iou_sum=0.0, cls_loss='focal'):
     """ATSSRPNHead.loss / loss_single.  cls[l] (B,A,H,W), box[l] (B,4A,H,W), iou[l] (B,A,H,W).
     Returns dict: loss_rpn_cls / loss_rpn_bbox / loss_rpn_iou (L,) float32, grad_cls / grad_box /
     grad_iou (lists, gradients of the sum of all 3L losses), num_pos, iou_sum.
@@ -507,16 +507,18 @@ def rpn_loss(cls, box, iou, gt_bboxes, img_metas, base_anchors, strides, gamma=0
         lab = np.stack([t['labels'][sl] for t in tg])
         lw = np.stack([t['label_weights'][sl] for t in tg]).astype(np.float64)
         anc = np.stack([t['anchors'][sl] for t in tg]).astype(np.float64)
-        # ---- classification: py_sigmoid_focal_loss (focal_loss.py:13-58) ----
+        # ---- classification: py_sigmoid_focal_loss (focal_loss.py:13-58); the varifocal
+        # variant needs iou_target and is evaluated after the positives block ----
         t = (lab == 0).astype(np.float64)
         p = 1.0 / (1.0 + np.exp(-x))
-        bce = np.maximum(x, 0) - x * t + np.log1p(np.exp(-np.abs(x)))
-        pt = (1 - p) * t + p * (1 - t)
-        aw = focal_alpha * t + (1 - focal_alpha) * (1 - t)
-        fw = aw * pt ** focal_gamma
-        res['loss_rpn_cls'][l] = w_cls * (bce * fw * lw).sum() / nts
-        dfw = aw * focal_gamma * pt ** (focal_gamma - 1) * (1 - 2 * t) * p * (1 - p)
-        g_cls = w_cls * lw * (fw * (p - t) + bce * dfw) / nts
+        if cls_loss == 'focal':
+            bce = np.maximum(x, 0) - x * t + np.log1p(np.exp(-np.abs(x)))
+            pt = (1 - p) * t + p * (1 - t)
+            aw = focal_alpha * t + (1 - focal_alpha) * (1 - t)
+            fw = aw * pt ** focal_gamma
+            res['loss_rpn_cls'][l] = w_cls * (bce * fw * lw).sum() / nts
+            dfw = aw * focal_gamma * pt ** (focal_gamma - 1) * (1 - 2 * t) * p * (1 - p)
+            g_cls = w_cls * lw * (fw * (p - t) + bce * dfw) / nts
         # ---- positives ----
         g_box = np.zeros_like(d)
         g_iou = np.zeros_like(u)
@@ -578,6 +580,21 @@ def rpn_loss(cls, box, iou, gt_bboxes, img_metas, base_anchors, strides, gamma=0
             res['loss_rpn_iou'][l] = w_iou * (np.maximum(xu, 0) - xu * iou_t +
                                               np.log1p(np.exp(-np.abs(xu)))).sum() / nts
             g_iou[pm] = w_iou * (1.0 / (1.0 + np.exp(-xu)) - iou_t) / nts
+        if cls_loss == 'varifocal':
+            # VarifocalLoss(iou_weighted=True) on EVERY anchor (no label weights are passed,
+            # atss_rpn_head.py:393-397; varifocal_loss.py:45-57): target q = iou_target on
+            # positives, 0 elsewhere
+            q = np.zeros_like(x)
+            if pm.any():
+                q[pm] = iou_t
+            posq = q > 0
+            bce = np.maximum(x, 0) - x * q + np.log1p(np.exp(-np.abs(x)))
+            dq = p - q
+            fw = np.where(posq, q, focal_alpha * np.abs(dq) ** focal_gamma)
+            res['loss_rpn_cls'][l] = w_cls * (bce * fw).sum() / nts
+            dfw = np.where(posq, 0.0, focal_alpha * focal_gamma * np.abs(dq) ** (focal_gamma - 1)
+                           * np.sign(dq) * p * (1 - p))
+            g_cls = w_cls * (fw * (p - q) + bce * dfw) / nts
         raw_bbox.append((lb_sum, g_box))
         iou_sum_l.append(isum)
         res['grad_cls'].append(g_cls)

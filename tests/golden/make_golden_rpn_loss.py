@@ -14,7 +14,8 @@ Executed reference code (lifted with `ast`, unmodified):
     configs/boosting_rcnn/*), `PseudoSampler`, `AssignResult`, `SamplingResult`,
     `bbox_overlaps`; `delta2bbox` / `bbox2delta`;
   * the loss modules `FocalLoss` (on CPU its forward takes the reference's own
-    `py_sigmoid_focal_loss` branch, focal_loss.py:159-177), `IoULoss` + `iou_loss`,
+    `py_sigmoid_focal_loss` branch, focal_loss.py:159-177), `VarifocalLoss` + `varifocal_loss`
+    (the VOC config's loss_cls; cases `varifocal_*`), `IoULoss` + `iou_loss`,
     `MSELoss` + `mse_loss`, `CrossEntropyLoss(use_sigmoid=True)` + `binary_cross_entropy`,
     `weighted_loss` / `weight_reduce_loss` / `reduce_loss`.
 `reduce_mean` is the identity (single process), exactly as dist_utils.py:67-73 behaves
@@ -38,7 +39,7 @@ from make_golden import REF, AttrDict, lift  # noqa: E402
 from make_golden_train import lift_classes, reference_namespace  # noqa: E402
 
 
-def build_reference_head():
+def build_reference_head(cls_loss='focal'):
     ns = reference_namespace()
     ns['functools'] = __import__('functools')
     ns['nn'] = torch.nn
@@ -46,7 +47,6 @@ def build_reference_head():
     ns['reduce_mean'] = lambda t: t                      # no process group (dist_utils.py:69-70)
     ns['force_fp32'] = lambda *a, **k: (lambda f: f)
     ns['GHMR'] = type('GHMR', (), {})
-    ns['VarifocalLoss'] = type('VarifocalLoss', (), {})
     ns['_pair'] = torch.nn.modules.utils._pair
     lift('mmdet/core/anchor/utils.py', ['images_to_levels', 'anchor_inside_flags'], ns)
     lift('mmdet/core/utils/misc.py', ['unmap'], ns)
@@ -62,6 +62,8 @@ def build_reference_head():
     ns['sigmoid_focal_loss'] = None                       # mmcv CUDA op: never reached on CPU
     lift('mmdet/models/losses/cross_entropy_loss.py',
          ['_expand_onehot_labels', 'binary_cross_entropy', 'cross_entropy', 'mask_cross_entropy'], ns)
+    lift('mmdet/models/losses/varifocal_loss.py', ['varifocal_loss'], ns)
+    lift_classes('mmdet/models/losses/varifocal_loss.py', ['VarifocalLoss'], ns)
     lift_classes('mmdet/models/losses/focal_loss.py', ['FocalLoss'], ns)
     lift_classes('mmdet/models/losses/iou_loss.py', ['IoULoss'], ns)
     lift_classes('mmdet/models/losses/mse_loss.py', ['MSELoss'], ns)
@@ -97,7 +99,11 @@ def build_reference_head():
         encode=lambda b, g: ns['bbox2delta'](b, g, (0., 0., 0., 0.), (1., 1., 1., 1.)),
         decode=lambda b, p, max_shape=None: ns['delta2bbox'](b, p, (0., 0., 0., 0.),
                                                              (1., 1., 1., 1.), max_shape))
-    head.loss_cls = ns['FocalLoss'](use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0)
+    if cls_loss == 'varifocal':      # the VOC config's RPN classification loss
+        head.loss_cls = ns['VarifocalLoss'](use_sigmoid=True, alpha=0.75, gamma=2.0,
+                                            iou_weighted=True, loss_weight=1.0)
+    else:
+        head.loss_cls = ns['FocalLoss'](use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0)
     head.loss_centerness = ns['CrossEntropyLoss'](use_sigmoid=True, loss_weight=1.0)
     head.loss_bbox = ns['IoULoss'](loss_weight=1.0)
     head.aug_loss = ns['MSELoss'](loss_weight=1.0)
@@ -126,9 +132,11 @@ def run_case(head, case):
 
 def main():
     head = build_reference_head()
+    vhead = build_reference_head('varifocal')
     gold = {}
-    for case in synth.RPN_LOSS_CASES:
-        res = run_case(head, case)
+    for case in synth.RPN_LOSS_CASES + tuple('varifocal_' + c for c in ('basic', 'partial_valid')):
+        vf = case.startswith('varifocal_')
+        res = run_case(vhead if vf else head, case[len('varifocal_'):] if vf else case)
         for k, v in res.items():
             gold[f'{case}/{k}'] = v
         print(case, {k: res[k].round(4).tolist() for k in ('loss_rpn_cls', 'loss_rpn_bbox', 'loss_rpn_iou')})

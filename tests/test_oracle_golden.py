@@ -366,12 +366,17 @@ RPN_LOSS_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden
                              'reference_golden_rpn_loss.npz')
 
 
+RPN_LOSS_GOLD_CASES = synth.RPN_LOSS_CASES + ('varifocal_basic', 'varifocal_partial_valid')
+
+
 def _rpn_loss_oracle(case):
-    c = synth.rpn_loss_case(case)
+    vf = case.startswith('varifocal_')
+    c = synth.rpn_loss_case(case[len('varifocal_'):] if vf else case)
     gen = AnchorGenerator(strides=[8, 16, 32, 64, 128], ratios=[0.5, 1.0, 2.0],
                           octave_base_scale=4, scales_per_octave=3)
+    kw = dict(cls_loss='varifocal', focal_alpha=0.75, focal_gamma=2.0) if vf else {}
     return c, oracle.rpn_loss(c['cls'], c['box'], c['iou'], c['gt_bboxes'], c['img_metas'],
-                              gen.base_anchor_table().numpy(), synth.STRIDES)
+                              gen.base_anchor_table().numpy(), synth.STRIDES, **kw)
 
 
 def _rel(a, b):
@@ -379,7 +384,7 @@ def _rel(a, b):
         max(float(np.abs(b).max()), 1e-12)
 
 
-@pytest.mark.parametrize('case', synth.RPN_LOSS_CASES)
+@pytest.mark.parametrize('case', RPN_LOSS_GOLD_CASES)
 def test_rpn_loss_oracle_equals_executed_reference(case):
     g = np.load(RPN_LOSS_GOLD)
     c, o = _rpn_loss_oracle(case)
