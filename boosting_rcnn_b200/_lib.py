@@ -41,7 +41,7 @@ class RpnLossParams(Structure):
         ('max_gts', c_int32),
         ('pos_iou_thr', c_float), ('neg_iou_thr', c_float), ('min_pos_iou', c_float),
         ('gamma', c_float), ('focal_gamma', c_float), ('focal_alpha', c_float),
-        ('loss_cls_weight', c_float), ('loss_bbox_weight', c_float),
+        ('cls_loss_type', c_int32), ('loss_cls_weight', c_float), ('loss_bbox_weight', c_float),
         ('loss_iou_weight', c_float), ('loss_aug_weight', c_float), ('max_ratio', c_float),
     ]
 

@@ -600,6 +600,8 @@ static int rpn_loss_args(const brcnn_rpn_loss_params* p, RpnLossArgs* a) {
   a->pos_iou_thr = p->pos_iou_thr; a->neg_iou_thr = p->neg_iou_thr;
   a->min_pos_iou = p->min_pos_iou; a->gamma = p->gamma;
   a->focal_gamma = p->focal_gamma; a->focal_alpha = p->focal_alpha;
+  if (p->cls_loss_type != 0 && p->cls_loss_type != 1) return BRCNN_ERR_ARG;
+  a->cls_loss_type = p->cls_loss_type;
   a->w_cls = p->loss_cls_weight; a->w_bbox = p->loss_bbox_weight;
   a->w_iou = p->loss_iou_weight; a->w_aug = p->loss_aug_weight;
   a->max_ratio = p->max_ratio;
@@ -1009,7 +1011,28 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
     if (e != cudaSuccess) return (int)e;
     const int slots = 2 * sm_count();
     dim3 grid(R < slots ? R : slots, (a.C + chunk - 1) / chunk);
+#ifdef BRCNN_DEBUG_TIMING
+    static unsigned long long* fdbg = [] {
+      unsigned long long* pbuf = nullptr;
+      cudaMalloc(&pbuf, 16 * 8);
+      return pbuf;
+    }();
+    cudaMemsetAsync(fdbg, 0, 16 * 8, stream);
+    roi_align_fwd3_kernel<<<grid, RT_THREADS, lay.total, stream>>>(a, rois, R, out, roi_levels, lay,
+                                                                   fdbg);
+    {
+      unsigned long long h[16];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h, fdbg, sizeof(h), cudaMemcpyDeviceToHost);
+      if (h[0] && h[8])
+        fprintf(stderr, "[fwd3] ctas=%llu rois/cta=%.1f | consumer0 cycles: total=%llu tab-wait=%llu "
+                "row-wait=%llu stores=%llu | producer: total=%llu publish=%llu slot-wait=%llu\n",
+                h[0], (double)h[5] / h[0], h[1] / h[0], h[2] / h[0], h[3] / h[0], h[4] / h[0],
+                h[9] / h[8], h[10] / h[8], h[11] / h[8]);
+    }
+#else
     roi_align_fwd3_kernel<<<grid, RT_THREADS, lay.total, stream>>>(a, rois, R, out, roi_levels, lay);
+#endif
     g_launch_count_add(1);
     BRCNN_CUDA_CHECK_LAST();
     return BRCNN_OK;

@@ -76,7 +76,21 @@ __device__ __forceinline__ void r3_fold3(float2 (&a0)[RT_P][2], float2 (&a1)[RT_
 __global__ void __launch_bounds__(RT_THREADS, 2)
 roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict__ rois, int R,
                       float* __restrict__ out, int32_t* __restrict__ roi_levels,
-                      const Roi3Smem lay) {
+                      const Roi3Smem lay
+#ifdef BRCNN_DEBUG_TIMING
+                      , unsigned long long* __restrict__ dbg
+#endif
+                      ) {
+#ifdef BRCNN_DEBUG_TIMING
+  const long long d_t0 = clock64();
+  long long d_a = 0, d_b = 0, d_c = 0, d_d = 0;   // role-specific phase sums
+  long long d_x;
+#define R3_TIC() d_x = clock64()
+#define R3_TOC(v) v += clock64() - d_x
+#else
+#define R3_TIC()
+#define R3_TOC(v)
+#endif
   extern __shared__ __align__(128) unsigned char r3_smem[];
   float* ring = reinterpret_cast<float*>(r3_smem);
   float* tabs = reinterpret_cast<float*>(r3_smem + (size_t)lay.ns * lay.slot_bytes);
@@ -188,7 +202,9 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
         const int pass = j / q.fh, dy = j - pass * q.fh;
         const int x0 = pass * q.cw;
         const int cwe = min(q.cw, q.fw - x0);
+        R3_TIC();
         if (round > 0) mbar_wait_addr(empty0 + 8u * s, (uint32_t)((round - 1) & 1));
+        R3_TOC(d_b);
         const float* src = fbase + ((size_t)(q.ylo + dy) * q.g.W + q.xlo + x0) * a.C;
         float* slot = ring + (size_t)s * slot_floats;
         if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(cwe * px_bytes));
@@ -222,7 +238,9 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
       if (rn < R) {
         nxt = geo_of(rv);
         load_roi(rn + gridDim.x, rv);
+        R3_TIC();
         publish(nxt, k + 1);
+        R3_TOC(d_a);
       }
       issue_rows(cur, pre, rows);
       cur = nxt;
@@ -240,7 +258,9 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
       const float* wy = tb + R3_DESC;
       const float* wxp = wy + (size_t)a.max_h * 8 + (size_t)(act0 ? pw : 0) * a.max_w;
       float* dst = out + (size_t)r * a.PH * a.PW * a.C + c0 + (size_t)pw * bin_stride;
+      R3_TIC();
       mbar_wait_addr(tfull0 + 8u * (k & 1), (uint32_t)((k >> 1) & 1));
+      R3_TOC(d_a);
       const int4 d0 = *reinterpret_cast<const int4*>(desc);        // dead, ylo, fh, fw
       const int npass = desc[4], cw = desc[5];
       const int fh = d0.z, fw = d0.w;
@@ -258,7 +278,9 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
           const int xs = max(bxs, x0), xe = min(bxe, x0 + cwe - 1);
           const bool work = act0 && (xs <= xe);
           for (int dy = 0; dy < fh; ++dy) {
+            R3_TIC();
             mbar_wait_addr(full0 + 8u * s, (uint32_t)(round & 1));
+            R3_TOC(d_b);
             float2 h0[2], h1[2];
             h0[0] = h0[1] = h1[0] = h1[1] = make_float2(0.f, 0.f);
             if (work) {
@@ -316,6 +338,7 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
       // tables no longer needed: the producer may overwrite this buffer two RoIs ahead
       __syncwarp();
       if (lane == 0) mbar_arrive_addr(tempty0 + 8u * (k & 1));
+      R3_TIC();
       if (pw < a.PW) {
 #pragma unroll
         for (int ph = 0; ph < RT_P; ++ph) {
@@ -328,8 +351,21 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
           }
         }
       }
+      R3_TOC(d_c);
     }
   }
+#ifdef BRCNN_DEBUG_TIMING
+  if (dbg != nullptr && lane == 0 && (warp == RT_CONS_WARPS || warp == 0)) {
+    const int o = warp == 0 ? 0 : 8;      // consumer warp 0 | producer
+    atomicAdd(dbg + o + 0, 1ull);
+    atomicAdd(dbg + o + 1, (unsigned long long)(clock64() - d_t0));
+    atomicAdd(dbg + o + 2, (unsigned long long)d_a);   // consumer: table waits | producer: publish
+    atomicAdd(dbg + o + 3, (unsigned long long)d_b);   // consumer: row waits   | producer: slot waits
+    atomicAdd(dbg + o + 4, (unsigned long long)d_c);   // consumer: stores
+    atomicAdd(dbg + o + 5, (unsigned long long)k);
+  }
+  (void)d_d;
+#endif
 }
 
 }  // namespace brcnn

@@ -64,6 +64,7 @@ struct RpnLossArgs {
   float pos_iou_thr, neg_iou_thr, min_pos_iou;
   float gamma;                   // bbox weight = iou_target ** gamma
   float focal_gamma, focal_alpha;
+  int cls_loss_type;             // 0 sigmoid focal loss, 1 varifocal loss (iou_weighted)
   float w_cls, w_bbox, w_iou, w_aug;
   float max_ratio;
 };
@@ -183,26 +184,9 @@ rpn_loss_main_kernel(const __grid_constant__ RpnLossArgs a, const float* __restr
     const bool is_pos = gt_ind > 0;
     const float lw = gt_ind >= 0 ? 1.f : 0.f;             // pos_weight <= 0 -> 1 (anchor_head.py:247-252)
     const size_t plane = ((size_t)b * a.A + an) * hw + pos;
-    // ---- focal loss on the objectness logit ----
-    {
-      const float xv = lv.cls[plane];
-      float g = 0.f;
-      if (lw > 0.f) {
-        const float tt = is_pos ? 1.f : 0.f;
-        const float p = 1.f / (1.f + expf(-xv));
-        const float bce = fmaxf(xv, 0.f) - xv * tt + log1pf(expf(-fabsf(xv)));
-        const float pt = is_pos ? 1.f - p : p;
-        const float aw = is_pos ? a.focal_alpha : 1.f - a.focal_alpha;
-        const float ptg1 = a.focal_gamma == 2.f ? pt : powf(pt, a.focal_gamma - 1.f);
-        const float fw = aw * ptg1 * pt;
-        s_cls = bce * fw;
-        const float dfw = aw * a.focal_gamma * ptg1 * (is_pos ? -1.f : 1.f) * p * (1.f - p);
-        g = a.w_cls * (fw * (p - tt) + bce * dfw);
-      }
-      lv.g_cls[plane] = g;
-    }
     // ---- positives: regression + IoU branch ----
     float gd0 = 0.f, gd1 = 0.f, gd2 = 0.f, gd3 = 0.f, gu = 0.f;
+    float iou_q = 0.f;                                      // varifocal target (0 off positives)
     const size_t bplane = ((size_t)b * a.A * 4 + an * 4) * hw + pos;
     if (is_pos) {
       const float4 gt = s_gt[gt_ind - 1];
@@ -238,6 +222,7 @@ rpn_loss_main_kernel(const __grid_constant__ RpnLossArgs a, const float* __restr
       s_bbox = 0.5f * (l_iou + l_aug);
       s_iou = iou_t;
       s_pos = 1.f;
+      iou_q = iou_t;
       // d(-log iou) / d(box), then through the decode
       const float mw = iwr >= 0.f ? 1.f : 0.f, mh = ihr >= 0.f ? 1.f : 0.f;
       const float di0 = -ih * mw * rl_dmax(x1, gt.x), di1 = -iw * mh * rl_dmax(y1, gt.y);
@@ -260,6 +245,46 @@ rpn_loss_main_kernel(const __grid_constant__ RpnLossArgs a, const float* __restr
       const float xu = lv.iou[plane];
       s_bce = fmaxf(xu, 0.f) - xu * iou_t + log1pf(expf(-fabsf(xu)));
       gu = a.w_iou * (1.f / (1.f + expf(-xu)) - iou_t);
+    }
+    // ---- classification loss on the objectness logit ----
+    {
+      const float xv = lv.cls[plane];
+      const float p = 1.f / (1.f + expf(-xv));
+      float g = 0.f;
+      if (a.cls_loss_type == 0) {
+        // sigmoid focal loss (focal_loss.py:13-58 == mmcv sigmoid_focal_loss), weighted by the
+        // label weight: invalid / ignored anchors contribute nothing
+        if (lw > 0.f) {
+          const float tt = is_pos ? 1.f : 0.f;
+          const float bce = fmaxf(xv, 0.f) - xv * tt + log1pf(expf(-fabsf(xv)));
+          const float pt = is_pos ? 1.f - p : p;
+          const float aw = is_pos ? a.focal_alpha : 1.f - a.focal_alpha;
+          const float ptg1 = a.focal_gamma == 2.f ? pt : powf(pt, a.focal_gamma - 1.f);
+          const float fw = aw * ptg1 * pt;
+          s_cls = bce * fw;
+          const float dfw = aw * a.focal_gamma * ptg1 * (is_pos ? -1.f : 1.f) * p * (1.f - p);
+          g = a.w_cls * (fw * (p - tt) + bce * dfw);
+        }
+      } else {
+        // VarifocalLoss(iou_weighted=True) against q = iou_target on positives, 0 elsewhere;
+        // the reference passes no weights here, so EVERY anchor counts
+        // (atss_rpn_head.py:393-397, varifocal_loss.py:45-57)
+        const float q = iou_q;
+        const float bce = fmaxf(xv, 0.f) - xv * q + log1pf(expf(-fabsf(xv)));
+        if (q > 0.f) {
+          s_cls = bce * q;
+          g = a.w_cls * q * (p - q);
+        } else {
+          const float dq = p - q, ad = fabsf(dq);
+          const float adg1 = a.focal_gamma == 2.f ? ad : powf(ad, a.focal_gamma - 1.f);
+          const float fw = a.focal_alpha * adg1 * ad;
+          s_cls = bce * fw;
+          const float dfw = a.focal_alpha * a.focal_gamma * adg1 * (dq > 0.f ? 1.f : (dq < 0.f ? -1.f : 0.f))
+                            * p * (1.f - p);
+          g = a.w_cls * (fw * (p - q) + bce * dfw);
+        }
+      }
+      lv.g_cls[plane] = g;
     }
     lv.g_bbox[bplane] = gd0;
     lv.g_bbox[bplane + hw] = gd1;

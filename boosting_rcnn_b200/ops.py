@@ -188,7 +188,8 @@ def delta2bbox(rois, deltas, means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.),
 def make_rpn_loss_params(batch, featmap_sizes, strides, num_anchors, max_gts, pos_iou_thr=0.5,
                          neg_iou_thr=0.5, min_pos_iou=0.0, gamma=0.5, focal_gamma=2.0,
                          focal_alpha=0.25, loss_cls_weight=1.0, loss_bbox_weight=1.0,
-                         loss_iou_weight=1.0, loss_aug_weight=1.0, wh_ratio_clip=16 / 1000):
+                         loss_iou_weight=1.0, loss_aug_weight=1.0, wh_ratio_clip=16 / 1000,
+                         cls_loss='focal'):
     p = RpnLossParams()
     p.batch, p.num_levels, p.num_anchors = int(batch), len(featmap_sizes), int(num_anchors)
     for l, ((h, w), s) in enumerate(zip(featmap_sizes, strides)):
@@ -198,6 +199,7 @@ def make_rpn_loss_params(batch, featmap_sizes, strides, num_anchors, max_gts, po
     p.max_gts = int(max_gts)
     p.pos_iou_thr, p.neg_iou_thr, p.min_pos_iou = float(pos_iou_thr), float(neg_iou_thr), float(min_pos_iou)
     p.gamma, p.focal_gamma, p.focal_alpha = float(gamma), float(focal_gamma), float(focal_alpha)
+    p.cls_loss_type = {'focal': 0, 'varifocal': 1}[cls_loss]
     p.loss_cls_weight, p.loss_bbox_weight = float(loss_cls_weight), float(loss_bbox_weight)
     p.loss_iou_weight, p.loss_aug_weight = float(loss_iou_weight), float(loss_aug_weight)
     p.max_ratio = max_ratio_f32(wh_ratio_clip)

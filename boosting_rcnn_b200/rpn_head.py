@@ -15,8 +15,9 @@ dispatches to when ``atss=False``) is B200-native as well: anchor targets (MaxIo
 match_low_quality + PseudoSampler), sigmoid focal loss, IoU-log + MSE regression losses and
 the BCE IoU branch run in three launches (``brcnn_rpn_loss_forward``) with hand-derived
 gradients; the two ``reduce_mean(...).item()`` normalisers become one device-side fused
-all-reduce.  Unsupported variants (atss=True, VarifocalLoss, GHM, reg_decoded_bbox=False)
-raise NotImplementedError at the first ``loss`` call.
+all-reduce.  FocalLoss (UTDAC / COCO configs) and VarifocalLoss (VOC config) are covered;
+unsupported variants (atss=True, GHM, reg_decoded_bbox=False) raise NotImplementedError at the
+first ``loss`` call.
 """
 import math
 from collections import namedtuple
@@ -224,10 +225,13 @@ class ATSSRPNHead(nn.Module):
             problems.append('reg_decoded_bbox=False')
         if self.num_classes != 1:
             problems.append('num_classes != 1')
-        for name, want in (('loss_cls', 'FocalLoss'), ('loss_bbox', 'IoULoss'),
-                           ('loss_centerness', 'CrossEntropyLoss')):
-            if type(getattr(self, name)).__name__ != want:
+        for name, want in (('loss_cls', ('FocalLoss', 'VarifocalLoss')), ('loss_bbox', ('IoULoss',)),
+                           ('loss_centerness', ('CrossEntropyLoss',))):
+            if type(getattr(self, name)).__name__ not in want:
                 problems.append(f'{name}={type(getattr(self, name)).__name__}')
+        if type(self.loss_cls).__name__ == 'VarifocalLoss' and \
+                not self.loss_cls.cfg.get('iou_weighted', True):
+            problems.append('VarifocalLoss(iou_weighted=False)')
         if self.with_aug_loss and type(self.aug_loss).__name__ != 'MSELoss':
             problems.append(f'aug_reg_loss={type(self.aug_loss).__name__}')
         if self.loss_bbox.cfg.get('mode', 'log') != 'log' or self.loss_bbox.cfg.get('linear', False):
@@ -256,7 +260,7 @@ class ATSSRPNHead(nn.Module):
             problems.append('gt_bboxes_ignore')
         if problems:
             raise NotImplementedError('the fused RPN loss covers the ATSSRPNHead settings of '
-                                      'configs/boosting_rcnn/*_utdac / *_coco; unsupported: '
+                                      'configs/boosting_rcnn/*; unsupported: '
                                       + '; '.join(problems))
         B = cls_scores[0].size(0)
         assert len(img_metas) == B and len(gt_bboxes) == B
@@ -275,12 +279,15 @@ class ATSSRPNHead(nn.Module):
         pad_hw = torch.tensor([[m['pad_shape'][0], m['pad_shape'][1]] for m in img_metas],
                               dtype=torch.float32).to(dev, non_blocking=True)
         a = self.train_cfg.assigner
+        varifocal = type(self.loss_cls).__name__ == 'VarifocalLoss'
         p = ops.make_rpn_loss_params(
             B, sizes, self.anchor_generator.strides, self.num_anchors, Gmax, a.pos_iou_thr,
             a.neg_iou_thr, a.get('min_pos_iou', 0.0), self.gamma,
-            self.loss_cls.cfg.get('gamma', 2.0), self.loss_cls.cfg.get('alpha', 0.25),
+            self.loss_cls.cfg.get('gamma', 2.0),
+            self.loss_cls.cfg.get('alpha', 0.75 if varifocal else 0.25),
             self.loss_cls.loss_weight, self.loss_bbox.loss_weight, self.loss_centerness.loss_weight,
-            self.aug_loss.loss_weight if self.with_aug_loss else 0.0)
+            self.aug_loss.loss_weight if self.with_aug_loss else 0.0,
+            cls_loss='varifocal' if varifocal else 'focal')
         l_cls, l_bbox, l_iou, _ = ops.rpn_loss(p, cls_scores, bbox_preds, iou_preds, base, gtb,
                                                num_gt, pad_hw)
         if not self.with_aug_loss:

@@ -126,7 +126,9 @@ typedef struct brcnn_rpn_loss_params {
   int32_t max_gts;                 /* row capacity of gt_boxes per image (<= 1024)    */
   float pos_iou_thr, neg_iou_thr, min_pos_iou;   /* train_cfg.rpn.assigner              */
   float gamma;                     /* ATSSRPNHead.gamma: bbox weight = iou_target**gamma */
-  float focal_gamma, focal_alpha;  /* loss_cls                                        */
+  float focal_gamma, focal_alpha;  /* loss_cls gamma / alpha                          */
+  int32_t cls_loss_type;           /* 0 FocalLoss (sigmoid), 1 VarifocalLoss (iou_weighted,
+                                      losses/varifocal_loss.py:10-57; every anchor counts)  */
   float loss_cls_weight, loss_bbox_weight, loss_iou_weight, loss_aug_weight;
   float max_ratio;                 /* |ln(wh_ratio_clip)| as fp32                     */
 } brcnn_rpn_loss_params;

@@ -27,9 +27,13 @@ def _rel(a, b):
     return float(np.abs(a - b).max()) / max(float(np.abs(b).max()), 1e-12)
 
 
-def _run_head(dev, c, cfg='utdac'):
+def _run_head(dev, c, cfg='utdac', varifocal=False):
     torch.manual_seed(0)
     rpn, _, _ = configs.build_hot_path(cfg, train=True)
+    if varifocal:     # the VOC config's RPN classification loss on the 9-anchor head
+        from boosting_rcnn_b200.registry import build_loss
+        rpn.loss_cls = build_loss(dict(type='VarifocalLoss', use_sigmoid=True, alpha=0.75,
+                                       gamma=2.0, iou_weighted=True, loss_weight=1.0))
     rpn = rpn.to(dev)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     cls = [t(a).requires_grad_(True) for a in c['cls']]
@@ -43,15 +47,17 @@ def _run_head(dev, c, cfg='utdac'):
     return rpn, losses, cls, box, iou
 
 
-@pytest.mark.parametrize('case', synth.RPN_LOSS_CASES)
+@pytest.mark.parametrize('case', synth.RPN_LOSS_CASES + ('varifocal_basic', 'varifocal_partial_valid'))
 def test_rpn_loss_equals_executed_reference_and_oracle(cuda, case):
     g = np.load(GOLD)
-    c = synth.rpn_loss_case(case)
-    rpn, losses, cls, box, iou = _run_head(cuda, c)
+    vf = case.startswith('varifocal_')
+    c = synth.rpn_loss_case(case[len('varifocal_'):] if vf else case)
+    rpn, losses, cls, box, iou = _run_head(cuda, c, varifocal=vf)
     gen = AnchorGenerator(strides=[8, 16, 32, 64, 128], ratios=[0.5, 1.0, 2.0],
                           octave_base_scale=4, scales_per_octave=3)
+    kw = dict(cls_loss='varifocal', focal_alpha=0.75, focal_gamma=2.0) if vf else {}
     o = oracle.rpn_loss(c['cls'], c['box'], c['iou'], c['gt_bboxes'], c['img_metas'],
-                        gen.base_anchor_table().numpy(), synth.STRIDES)
+                        gen.base_anchor_table().numpy(), synth.STRIDES, **kw)
     for k in ('loss_rpn_cls', 'loss_rpn_bbox', 'loss_rpn_iou'):
         got = np.array([float(v) for v in losses[k]], dtype=np.float32)
         np.testing.assert_allclose(got, g[f'{case}/{k}'], rtol=RTOL, atol=1e-7, err_msg=k)
@@ -151,10 +157,24 @@ def test_forward_train_returns_reference_keys(cuda):
     assert rpn.rpn_iou.weight.grad.abs().sum() > 0 and rpn.scales[0].scale.grad is not None
 
 
-def test_unsupported_rpn_loss_variants_raise(cuda):
-    rpn, _, _ = configs.build_hot_path('voc', train=True)     # VarifocalLoss
+def test_voc_config_rpn_loss_runs_and_unsupported_variants_raise(cuda):
+    """VOC head (1 anchor / location, VarifocalLoss, gamma 2, loss weights 2) against the oracle;
+    atss=True is refused with a clear message."""
+    rpn, _, _ = configs.build_hot_path('voc', train=True)
     c = synth.rpn_loss_case('basic', num_anchors=1)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
-    with pytest.raises(NotImplementedError, match='VarifocalLoss'):
-        rpn.to(cuda).loss([t(a) for a in c['cls']], [t(a) for a in c['box']],
-                          [t(a) for a in c['iou']], [t(g) for g in c['gt_bboxes']], c['img_metas'])
+    cls = [t(a).requires_grad_(True) for a in c['cls']]
+    losses = rpn.to(cuda).loss(cls, [t(a) for a in c['box']], [t(a) for a in c['iou']],
+                               [t(g) for g in c['gt_bboxes']], c['img_metas'])
+    gen = AnchorGenerator(strides=[8, 16, 32, 64, 128], ratios=[1.0], octave_base_scale=8,
+                          scales_per_octave=1)
+    o = oracle.rpn_loss(c['cls'], c['box'], c['iou'], c['gt_bboxes'], c['img_metas'],
+                        gen.base_anchor_table().numpy(), synth.STRIDES, gamma=2, w_bbox=2.0,
+                        w_aug=2.0, cls_loss='varifocal', focal_alpha=0.75)
+    for k in ('loss_rpn_cls', 'loss_rpn_bbox', 'loss_rpn_iou'):
+        got = np.array([float(v.detach()) for v in losses[k]], dtype=np.float32)
+        np.testing.assert_allclose(got, o[k], rtol=RTOL, atol=1e-7, err_msg=k)
+    rpn.atss = True
+    with pytest.raises(NotImplementedError, match='atss=True'):
+        rpn.loss(cls, [t(a) for a in c['box']], [t(a) for a in c['iou']],
+                 [t(g) for g in c['gt_bboxes']], c['img_metas'])
