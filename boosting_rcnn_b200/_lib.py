@@ -132,9 +132,10 @@ SIGNATURES = {
                                         c_void_p]),
     'brcnn_map_roi_levels': (c_int32, [c_void_p, c_int32, c_float, c_int32,
                                        c_void_p, c_void_p]),
+    'brcnn_roi_extract_forward_workspace_bytes': (c_size_t, [POINTER(RoiParams)]),
     'brcnn_roi_extract_forward': (c_int32, [
         POINTER(RoiParams), POINTER(c_void_p), c_void_p, c_int32, c_void_p,
-        c_void_p, c_void_p]),
+        c_void_p, c_void_p, c_size_t, c_void_p]),
     'brcnn_roi_extract_backward_workspace_bytes': (c_size_t, [POINTER(RoiParams), c_int32]),
     'brcnn_roi_extract_backward': (c_int32, [
         POINTER(RoiParams), c_void_p, c_void_p, c_int32, POINTER(c_void_p),

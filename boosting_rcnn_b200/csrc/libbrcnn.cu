@@ -962,11 +962,19 @@ static int roi_args_from(const brcnn_roi_params* p, RoiArgs* a) {
   return BRCNN_OK;
 }
 
+size_t brcnn_roi_extract_forward_workspace_bytes(const brcnn_roi_params* p) {
+  (void)p;
+  return 256;   // 2 counters per channel chunk (<= 32 chunks)
+}
+
 int brcnn_roi_extract_forward(const brcnn_roi_params* p,
                               const float* const* feats_nhwc_host,
                               const float* rois, int32_t R, float* out,
-                              int32_t* roi_levels, brcnn_stream_t stream_) {
+                              int32_t* roi_levels, void* workspace, size_t workspace_bytes,
+                              brcnn_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (workspace != nullptr && (workspace_bytes < 256 || ((uintptr_t)workspace & 3)))
+    return BRCNN_ERR_WORKSPACE;
   RoiArgs a;
   int rc = roi_args_from(p, &a);
   if (rc) return rc;
@@ -989,7 +997,7 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
     const int chunk = a.C < 4 * RT_SLAB_Q ? a.C : 4 * RT_SLAB_Q;
     Roi3Smem lay;
     lay.tab_floats = (R3_DESC + a.max_h * 8 + 8 * a.max_w + 31) & ~31;
-    const size_t tables = (size_t)2 * lay.tab_floats * 4;
+    const size_t tables = (size_t)R3_TABS * lay.tab_floats * 4;
     const size_t budget = 110 * 1024;           // two CTAs per SM
     // a slot holds up to 16 footprint pixels of the channel chunk (wider rows: x-chunk passes)
     static const int slot_px = [] {
@@ -1007,31 +1015,51 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
     if (lay.ns > R3_MAX_STAGES) lay.ns = R3_MAX_STAGES;
     lay.total = (int)((size_t)lay.ns * lay.slot_bytes + tables);
     a.chunk_c = chunk;
-    cudaError_t e = ensure_dyn_smem((const void*)roi_align_fwd3_kernel, lay.total, true);
+    static const bool split = [] {
+      const char* e = getenv("BRCNN_R3_SPLIT");     // tuning knob (developer)
+      return e ? atoi(e) != 0 : true;
+    }();
+    cudaError_t e = split
+        ? ensure_dyn_smem((const void*)roi_align_fwd3_kernel<true>, lay.total, true)
+        : ensure_dyn_smem((const void*)roi_align_fwd3_kernel<false>, lay.total, true);
     if (e != cudaSuccess) return (int)e;
     const int slots = 2 * sm_count();
     dim3 grid(R < slots ? R : slots, (a.C + chunk - 1) / chunk);
+    unsigned int* sched = grid.y <= 32 ? (unsigned int*)workspace : nullptr;
 #ifdef BRCNN_DEBUG_TIMING
     static unsigned long long* fdbg = [] {
       unsigned long long* pbuf = nullptr;
-      cudaMalloc(&pbuf, 16 * 8);
+      cudaMalloc(&pbuf, 24 * 8);
       return pbuf;
     }();
-    cudaMemsetAsync(fdbg, 0, 16 * 8, stream);
-    roi_align_fwd3_kernel<<<grid, RT_THREADS, lay.total, stream>>>(a, rois, R, out, roi_levels, lay,
-                                                                   fdbg);
+    cudaMemsetAsync(fdbg, 0, 24 * 8, stream);
+    if (split)
+      roi_align_fwd3_kernel<true><<<grid, R3_THREADS, lay.total, stream>>>(
+          a, rois, R, out, roi_levels, lay, sched, fdbg);
+    else
+      roi_align_fwd3_kernel<false><<<grid, RT_THREADS, lay.total, stream>>>(
+          a, rois, R, out, roi_levels, lay, sched, fdbg);
     {
-      unsigned long long h[16];
+      unsigned long long h[24];
       cudaStreamSynchronize(stream);
       cudaMemcpy(h, fdbg, sizeof(h), cudaMemcpyDeviceToHost);
-      if (h[0] && h[8])
-        fprintf(stderr, "[fwd3] ctas=%llu rois/cta=%.1f | consumer0 cycles: total=%llu tab-wait=%llu "
-                "row-wait=%llu stores=%llu | producer: total=%llu publish=%llu slot-wait=%llu\n",
+      if (h[0] && h[8]) {
+        if (!h[16]) h[16] = 1;
+        fprintf(stderr, "[fwd3] ctas=%llu rois/cta=%.1f | consumer0: total=%llu tab-wait=%llu "
+                "row-wait=%llu stores=%llu | issuer: total=%llu tab-wait=%llu slot-wait=%llu "
+                "publish=%llu | publisher: total=%llu tables=%llu buf-wait=%llu\n",
                 h[0], (double)h[5] / h[0], h[1] / h[0], h[2] / h[0], h[3] / h[0], h[4] / h[0],
-                h[9] / h[8], h[10] / h[8], h[11] / h[8]);
+                h[9] / h[8], h[10] / h[8], h[11] / h[8], h[12] / h[8], h[17] / h[16],
+                h[18] / h[16], h[19] / h[16]);
+      }
     }
 #else
-    roi_align_fwd3_kernel<<<grid, RT_THREADS, lay.total, stream>>>(a, rois, R, out, roi_levels, lay);
+    if (split)
+      roi_align_fwd3_kernel<true><<<grid, R3_THREADS, lay.total, stream>>>(
+          a, rois, R, out, roi_levels, lay, sched);
+    else
+      roi_align_fwd3_kernel<false><<<grid, RT_THREADS, lay.total, stream>>>(
+          a, rois, R, out, roi_levels, lay, sched);
 #endif
     g_launch_count_add(1);
     BRCNN_CUDA_CHECK_LAST();
@@ -1265,7 +1293,7 @@ static int roi_bwd3_launch(RoiArgs a, const float* grad_out, int out_layout, con
   // developer build only (-DBRCNN_DEBUG_TIMING): per-phase cycle sums of the gather CTAs
   static unsigned long long* dbg = [] {
     unsigned long long* pbuf = nullptr;
-    cudaMalloc(&pbuf, 16 * 8);
+    cudaMalloc(&pbuf, 24 * 8);
     return pbuf;
   }();
   cudaMemsetAsync(dbg, 0, 16 * 8, stream);

@@ -7,7 +7,8 @@
 //     out[ph][pw][c] = sum_y Wy[ph][y] * ( sum_x Wx[pw][x] * F[y][x][c] ),
 // evaluated x-first one footprint row at a time; what changes is the schedule and the
 // instruction count (the v2 kernel was issue-bound: 61 M warp instructions per 4096 RoIs):
-//   * one CTA per SM slot (2 per SM) loops over RoIs r = blockIdx.x, += gridDim.x.  The ring of
+//   * one CTA per SM slot (2 per SM) loops over RoIs pulled from an atomic counter (static
+//     stride without a scheduling scratch).  The ring of
 //     fixed-size row slots and its mbarriers live across RoIs: the producer warp streams RoI
 //     i+1's footprint rows (1-D `cp.async.bulk`) while the consumer warps are still folding /
 //     storing RoI i — no per-RoI barrier init, table build or output staging bubble;
@@ -35,6 +36,19 @@ namespace brcnn {
 
 constexpr int R3_MAX_STAGES = 8;
 constexpr int R3_DESC = 32;   // descriptor ints at the head of a table buffer
+constexpr int R3_TABS = 2;    // descriptor + table buffers (publisher runs R3_TABS - 1 ahead)
+constexpr int R3_THREADS = (RT_CONS_WARPS + 2) * 32;
+
+__device__ __forceinline__ void mbar_expect_tx_addr(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_1d_addr(uint32_t dst, const void* src, uint32_t bytes,
+                                                 uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
 struct Roi3Smem {
   int slot_bytes, ns, tab_floats, total;
@@ -70,20 +84,26 @@ __device__ __forceinline__ void r3_fold3(float2 (&a0)[RT_P][2], float2 (&a1)[RT_
   if (P + 2 <= pb) r3_fold1<P + 2>(a0, a1, wv, h0, h1);
 }
 
-// dynamic smem: ring ns*slot_bytes | tab[2], each: desc[32 ints] | wy[max_h][8] | wx[8][max_w]
-//   desc: 0 dead, 1 ylo(unused by consumers), 2 fh, 3 fw, 4 npass, 5 cw, 8..15 xs[pw], 16..23 xe[pw]
+// dynamic smem: ring ns*slot_bytes | tab[R3_TABS], each: desc[32 ints] | wy[max_h][8] | wx[8][max_w]
+//   desc: 0 state (0 live, 1 dead, 2 end), 1 ylo(unused by consumers), 2 fh, 3 fw, 4 npass, 5 cw,
+//         6 RoI index, 7 row pitch (floats), 8..15 xs[pw], 16..23 xe[pw],
+//         24/25 global address of the footprint origin (channel c0)
 //   wy row: 7 weights (1/count folded in) + packed non-zero band pa | pb << 8
-__global__ void __launch_bounds__(RT_THREADS, 2)
+// warps: 0..6 consumers (pooled column pw), 7 row issuer, 8 table publisher (SPLIT); without
+// SPLIT warp 7 does both jobs (publishes RoI k+1 between the first ring-full of RoI k's rows
+// and the rest) and the kernel keeps 128 registers per thread
+template <bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? R3_THREADS : RT_THREADS, 2)
 roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict__ rois, int R,
                       float* __restrict__ out, int32_t* __restrict__ roi_levels,
-                      const Roi3Smem lay
+                      const Roi3Smem lay, unsigned int* __restrict__ sched
 #ifdef BRCNN_DEBUG_TIMING
                       , unsigned long long* __restrict__ dbg
 #endif
                       ) {
 #ifdef BRCNN_DEBUG_TIMING
   const long long d_t0 = clock64();
-  long long d_a = 0, d_b = 0, d_c = 0, d_d = 0;   // role-specific phase sums
+  long long d_a = 0, d_b = 0, d_c = 0;   // role-specific phase sums
   long long d_x;
 #define R3_TIC() d_x = clock64()
 #define R3_TOC(v) v += clock64() - d_x
@@ -96,8 +116,8 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
   float* tabs = reinterpret_cast<float*>(r3_smem + (size_t)lay.ns * lay.slot_bytes);
   __shared__ __align__(8) uint64_t full_bar[R3_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[R3_MAX_STAGES];
-  __shared__ __align__(8) uint64_t tab_full[2];
-  __shared__ __align__(8) uint64_t tab_empty[2];
+  __shared__ __align__(8) uint64_t tab_full[R3_TABS];
+  __shared__ __align__(8) uint64_t tab_empty[R3_TABS];
 
   const int c0 = blockIdx.y * a.chunk_c;
   const int cc = min(a.chunk_c, a.C - c0);
@@ -113,9 +133,9 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], RT_CONS_WARPS);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < R3_TABS; ++s) {
       mbar_init(&tab_full[s], 1);
-      mbar_init(&tab_empty[s], RT_CONS_WARPS);
+      mbar_init(&tab_empty[s], RT_CONS_WARPS + (SPLIT ? 1 : 0));   // consumers (+ issuer)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -123,127 +143,183 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
   const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
   const uint32_t tfull0 = smem_u32(tab_full), tempty0 = smem_u32(tab_empty);
 
-  int s = 0, round = 0;   // ring position (both roles advance identically)
-  int k = 0;              // RoIs processed so far by this CTA (table buffer = k & 1)
+  int s = 0, round = 0;   // ring position (issuer and consumers advance identically)
+  int k = 0;              // RoIs processed so far by this CTA
+  int tb_i = 0, tb_ph = 0;   // table buffer of RoI k and its barrier phase
 
-  if (warp == RT_CONS_WARPS) {
-    // ============================= producer warp =============================
-    // Schedule per RoI k: (1) issue its first NS footprint rows (their slots were last used
-    // by earlier RoIs, so this never waits on RoI k's own rows), (2) build and publish the
-    // tables of RoI k+1 while those rows fly / are consumed, (3) issue the remaining rows.
-    struct Geo {
-      RoiGeom g;
-      int ylo, xlo, fh, fw, npass, cw, lvl;
-      bool dead;
-    };
-    auto geo_of = [&](const float (&rv)[5]) {
-      Geo q;
+  if (warp >= RT_CONS_WARPS) {
+    // ============================= table publisher ===========================
+    // Claims RoIs (atomic counter, or a static stride without the scheduling scratch), does
+    // ALL per-RoI scalar work once and publishes descriptor + separable weight tables into
+    // the next free table buffer (at most R3_TABS - 1 RoIs ahead of the consumers).
+    unsigned int* ctr = sched ? sched + 2 * blockIdx.y : nullptr;
+    int r_static = blockIdx.x;
+    int pk = 0, pb_i = 0, pb_ph = 0;      // RoIs published, next buffer and its phase
+    auto publish_next = [&]() -> bool {
+      int r;
+      if (ctr != nullptr) {
+        r = 0;
+        if (lane == 0) r = (int)atomicAdd(ctr, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+      } else {
+        r = r_static;
+        r_static += gridDim.x;
+      }
+      const bool end = r >= R;
+      float rv[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) rv[i] = end ? -1.f : __ldg(rois + (size_t)r * 5 + i);
       const bool padding = rv[0] < 0.f;
+      RoiGeom g;
       int ylo = 1, yhi = 0, xlo = 1, xhi = 0;
-      q.g.b = -1; q.g.lvl = 0;
+      g.b = -1; g.lvl = 0; g.W = 0;
       if (!padding) {
-        q.g = roi_geometry(a, rv);
-        roi_axis_range(q.g.start_h, q.g.bin_h, a.PH, q.g.gh, q.g.H, ylo, yhi);
-        roi_axis_range(q.g.start_w, q.g.bin_w, a.PW, q.g.gw, q.g.W, xlo, xhi);
+        g = roi_geometry(a, rv);
+        roi_axis_range(g.start_h, g.bin_h, a.PH, g.gh, g.H, ylo, yhi);
+        roi_axis_range(g.start_w, g.bin_w, a.PW, g.gw, g.W, xlo, xhi);
       }
-      q.ylo = ylo; q.xlo = xlo;
-      q.fh = yhi - ylo + 1; q.fw = xhi - xlo + 1;
-      q.dead = padding || q.fh <= 0 || q.fw <= 0 || q.g.b < 0 || q.g.b >= a.B;
-      q.lvl = padding ? -1 : q.g.lvl;
-      q.npass = 1; q.cw = q.fw;
-      if (!q.dead && q.fw > cw_max) {
-        q.npass = (q.fw + cw_max - 1) / cw_max;
-        q.cw = (q.fw + q.npass - 1) / q.npass;
+      const int fh = yhi - ylo + 1, fw = xhi - xlo + 1;
+      const bool dead = padding || fh <= 0 || fw <= 0 || g.b < 0 || g.b >= a.B;
+      int npass = 1, cw = fw;
+      if (!dead && fw > cw_max) {
+        npass = (fw + cw_max - 1) / cw_max;
+        cw = (fw + npass - 1) / npass;
       }
-      return q;
-    };
-    // descriptor + separable weight tables of RoI number kk (of this CTA) -> buffer kk & 1
-    auto publish = [&](const Geo& q, int kk) {
-      float* tb = tabs + (size_t)(kk & 1) * lay.tab_floats;
+      if (!end && roi_levels != nullptr && blockIdx.y == 0 && lane == 0)
+        roi_levels[r] = padding ? -1 : g.lvl;
+      float* tb = tabs + (size_t)pb_i * lay.tab_floats;
       int* desc = reinterpret_cast<int*>(tb);
       float* wy = tb + R3_DESC;                        // [fh][8]
       float* wx = wy + (size_t)a.max_h * 8;            // [pw][max_w]
-      if (kk >= 2) mbar_wait_addr(tempty0 + 8u * (kk & 1), (uint32_t)(((kk >> 1) & 1) ^ 1));
+      R3_TIC();
+      if (pk >= R3_TABS) mbar_wait_addr(tempty0 + 8u * pb_i, (uint32_t)(pb_ph ^ 1));
+      R3_TOC(d_b);
+      R3_TIC();
       if (lane == 0) {
-        desc[0] = q.dead ? 1 : 0; desc[1] = q.ylo; desc[2] = q.fh; desc[3] = q.fw;
-        desc[4] = q.npass; desc[5] = q.cw;
+        desc[0] = end ? 2 : (dead ? 1 : 0); desc[1] = ylo; desc[2] = fh; desc[3] = fw;
+        desc[4] = npass; desc[5] = cw; desc[6] = r; desc[7] = g.W * a.C;
+        if (!dead) {
+          const float* org = a.feat[g.lvl] +
+                             (((size_t)g.b * g.H + ylo) * g.W + xlo) * a.C + c0;
+          *reinterpret_cast<const float**>(desc + 24) = org;
+        }
       }
-      if (lane < 8) { desc[8 + lane] = q.fw; desc[16 + lane] = -1; }
+      if (lane < 8) { desc[8 + lane] = fw; desc[16 + lane] = -1; }
       __syncwarp();
-      if (!q.dead) {
+      if (!dead) {
         // Wy: lane = (row, pooled row); the band of a row comes from a ballot over its 8 lanes
-        for (int i0 = 0; i0 < 8 * q.fh; i0 += 32) {
+        for (int i0 = 0; i0 < 8 * fh; i0 += 32) {
           const int i = i0 + lane, dy = i >> 3, ph = i & 7;
           float v = 0.f;
-          if (dy < q.fh && ph < a.PH)
-            v = roi_axis_weight(q.g.start_h, q.g.bin_h, q.g.gh, q.g.H, ph, q.ylo + dy) *
-                q.g.inv_count;
+          if (dy < fh && ph < a.PH)
+            v = roi_axis_weight(g.start_h, g.bin_h, g.gh, g.H, ph, ylo + dy) * g.inv_count;
           const unsigned nz = (__ballot_sync(0xffffffffu, v != 0.f) >> (lane & 24)) & 0x7fu;
           if (ph == 7) v = __int_as_float(nz ? ((__ffs(nz) - 1) | ((31 - __clz(nz)) << 8)) : 1);
-          if (dy < q.fh) wy[i] = v;
+          if (dy < fh) wy[i] = v;
         }
         // Wx: lane = (column, pooled column); bands through shared-memory min / max
-        for (int i0 = 0; i0 < 8 * q.fw; i0 += 32) {
+        for (int i0 = 0; i0 < 8 * fw; i0 += 32) {
           const int i = i0 + lane, dx = i >> 3, pw = i & 7;
-          if (dx < q.fw && pw < a.PW) {
-            const float v = roi_axis_weight(q.g.start_w, q.g.bin_w, q.g.gw, q.g.W, pw, q.xlo + dx);
+          if (dx < fw && pw < a.PW) {
+            const float v = roi_axis_weight(g.start_w, g.bin_w, g.gw, g.W, pw, xlo + dx);
             wx[pw * a.max_w + dx] = v;
             if (v != 0.f) { atomicMin(&desc[8 + pw], dx); atomicMax(&desc[16 + pw], dx); }
           }
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tab_full[kk & 1]);
+      if (lane == 0) mbar_arrive(&tab_full[pb_i]);
+      R3_TOC(d_a);
+      if (++pb_i == R3_TABS) { pb_i = 0; pb_ph ^= 1; }
+      ++pk;
+      return end;
     };
-    auto issue_rows = [&](const Geo& q, int j0, int j1) {   // rows [j0, j1) of pass-major order
-      const float* fbase = a.feat[q.g.lvl] + ((size_t)q.g.b * q.g.H * q.g.W) * a.C + c0;
-      const bool contiguous = (cc == a.C);
-      for (int j = j0; j < j1; ++j) {
-        const int pass = j / q.fh, dy = j - pass * q.fh;
-        const int x0 = pass * q.cw;
-        const int cwe = min(q.cw, q.fw - x0);
-        R3_TIC();
-        if (round > 0) mbar_wait_addr(empty0 + 8u * s, (uint32_t)((round - 1) & 1));
-        R3_TOC(d_b);
-        const float* src = fbase + ((size_t)(q.ylo + dy) * q.g.W + q.xlo + x0) * a.C;
-        float* slot = ring + (size_t)s * slot_floats;
-        if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(cwe * px_bytes));
-        if (contiguous) {
-          if (lane == 0) tma_load_1d(slot, src, (uint32_t)(cwe * px_bytes), &full_bar[s]);
-        } else {
-          __syncwarp();
-          for (int px = lane; px < cwe; px += 32)
-            tma_load_1d(slot + (size_t)px * cc, src + (size_t)px * a.C, (uint32_t)px_bytes,
-                        &full_bar[s]);
+    auto rearm = [&]() {
+      // the last CTA to run dry re-arms the counters for the next launch
+      if (ctr != nullptr && lane == 0) {
+        __threadfence();
+        if (atomicAdd(ctr + 1, 1u) == gridDim.x - 1) {
+          atomicExch(ctr, 0u);
+          atomicExch(ctr + 1, 0u);
         }
-        if (++s == NS) { s = 0; ++round; }
       }
     };
-    auto load_roi = [&](int r, float (&rv)[5]) {
-#pragma unroll
-      for (int i = 0; i < 5; ++i) rv[i] = (r < R) ? __ldg(rois + (size_t)r * 5 + i) : -1.f;
-    };
-    float rv[5];
-    load_roi(blockIdx.x, rv);
-    Geo cur = geo_of(rv);
-    load_roi(blockIdx.x + gridDim.x, rv);
-    if ((int)blockIdx.x < R) publish(cur, 0);
-    for (int r = blockIdx.x; r < R; r += gridDim.x, ++k) {
-      if (roi_levels != nullptr && blockIdx.y == 0 && lane == 0) roi_levels[r] = cur.lvl;
-      const int rows = cur.dead ? 0 : cur.npass * cur.fh;
-      const int pre = min(rows, NS);
-      issue_rows(cur, 0, pre);
-      const int rn = r + gridDim.x;
-      Geo nxt = cur;
-      if (rn < R) {
-        nxt = geo_of(rv);
-        load_roi(rn + gridDim.x, rv);
-        R3_TIC();
-        publish(nxt, k + 1);
-        R3_TOC(d_a);
+    if (SPLIT && warp == RT_CONS_WARPS + 1) {
+      while (!publish_next()) {}
+      rearm();
+    } else {
+      // ============================== row issuer =============================
+      // One 1-D bulk copy per footprint row (per x-chunk pass) into the next ring slot; the
+      // loop carries pointers and slot / barrier addresses, nothing is recomputed per row.
+      const bool contiguous = (cc == a.C);
+      const uint32_t ring0 = smem_u32(ring);
+      uint32_t slot_addr = ring0;
+      bool more = true;                     // !SPLIT: RoIs left to publish
+      if (!SPLIT) more = !publish_next();
+      for (;; ++k) {
+        const int* desc = reinterpret_cast<const int*>(tabs + (size_t)tb_i * lay.tab_floats);
+        if (SPLIT) {
+          R3_TIC();
+          mbar_wait_addr(tfull0 + 8u * tb_i, (uint32_t)tb_ph);
+          R3_TOC(d_a);
+        }
+        const int4 d0 = *reinterpret_cast<const int4*>(desc);        // state, ylo, fh, fw
+        if (d0.x == 2) break;
+        const int4 d1 = *reinterpret_cast<const int4*>(desc + 4);    // npass, cw, r, pitch
+        const float* org = *reinterpret_cast<const float* const*>(desc + 24);
+        const int fh = d0.z, fw = d0.w;
+        int rows_left = d0.x == 0 ? d1.x * fh : 0;
+        int budget = SPLIT ? rows_left : min(rows_left, NS);          // rows before the publish
+        int pass = 0, dy = 0;
+        int cwe = min(d1.y, fw);
+        uint32_t bytes = (uint32_t)(cwe * px_bytes);
+        const float* src = org;
+        for (int phase = 0; phase < 2; ++phase) {
+          for (; budget > 0; --budget, --rows_left) {
+            R3_TIC();
+            if (round > 0) mbar_wait_addr(empty0 + 8u * s, (uint32_t)((round - 1) & 1));
+            R3_TOC(d_b);
+            const uint32_t fb = full0 + 8u * s;
+            if (contiguous) {
+              if (lane == 0) {
+                mbar_expect_tx_addr(fb, bytes);
+                tma_load_1d_addr(slot_addr, src, bytes, fb);
+              }
+            } else {
+              if (lane == 0) mbar_expect_tx_addr(fb, bytes);
+              __syncwarp();
+              for (int px = lane; px < cwe; px += 32)
+                tma_load_1d_addr(slot_addr + (uint32_t)(px * px_bytes), src + (size_t)px * a.C,
+                                 (uint32_t)px_bytes, fb);
+            }
+            src += d1.w;
+            slot_addr += (uint32_t)lay.slot_bytes;
+            if (++s == NS) { s = 0; ++round; slot_addr = ring0; }
+            if (++dy == fh) {                 // next x-chunk pass
+              dy = 0;
+              ++pass;
+              const int x0 = pass * d1.y;
+              cwe = min(d1.y, fw - x0);
+              bytes = (uint32_t)(cwe * px_bytes);
+              src = org + (size_t)x0 * a.C;
+            }
+          }
+          if (phase == 0) {
+            if (!SPLIT && more) {
+              R3_TIC();
+              more = !publish_next();
+              R3_TOC(d_c);
+            }
+            budget = rows_left;
+          }
+        }
+        if (SPLIT) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_addr(tempty0 + 8u * tb_i);
+        }
+        if (++tb_i == R3_TABS) { tb_i = 0; tb_ph ^= 1; }
       }
-      issue_rows(cur, pre, rows);
-      cur = nxt;
+      if (!SPLIT) rearm();
     }
   } else {
     // ============================= consumer warps ============================
@@ -252,17 +328,18 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
     const bool act1 = (pw < a.PW) && (lane + 32 < ncq);
     const int q1 = act1 ? lane + 32 : lane;   // inactive second quad re-reads the first
     const size_t bin_stride = (size_t)a.C;
-    for (int r = blockIdx.x; r < R; r += gridDim.x, ++k) {
-      const float* tb = tabs + (size_t)(k & 1) * lay.tab_floats;
+    for (;; ++k) {
+      const float* tb = tabs + (size_t)tb_i * lay.tab_floats;
       const int* desc = reinterpret_cast<const int*>(tb);
       const float* wy = tb + R3_DESC;
       const float* wxp = wy + (size_t)a.max_h * 8 + (size_t)(act0 ? pw : 0) * a.max_w;
-      float* dst = out + (size_t)r * a.PH * a.PW * a.C + c0 + (size_t)pw * bin_stride;
       R3_TIC();
-      mbar_wait_addr(tfull0 + 8u * (k & 1), (uint32_t)((k >> 1) & 1));
+      mbar_wait_addr(tfull0 + 8u * tb_i, (uint32_t)tb_ph);
       R3_TOC(d_a);
-      const int4 d0 = *reinterpret_cast<const int4*>(desc);        // dead, ylo, fh, fw
+      const int4 d0 = *reinterpret_cast<const int4*>(desc);        // state, ylo, fh, fw
+      if (d0.x == 2) break;                                        // no RoI left
       const int npass = desc[4], cw = desc[5];
+      float* dst = out + (size_t)desc[6] * a.PH * a.PW * a.C + c0 + (size_t)pw * bin_stride;
       const int fh = d0.z, fw = d0.w;
       float2 acc0[RT_P][2], acc1[RT_P][2];
 #pragma unroll
@@ -335,9 +412,10 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
           }
         }
       }
-      // tables no longer needed: the producer may overwrite this buffer two RoIs ahead
+      // tables no longer needed: the publisher may overwrite this buffer
       __syncwarp();
-      if (lane == 0) mbar_arrive_addr(tempty0 + 8u * (k & 1));
+      if (lane == 0) mbar_arrive_addr(tempty0 + 8u * tb_i);
+      if (++tb_i == R3_TABS) { tb_i = 0; tb_ph ^= 1; }
       R3_TIC();
       if (pw < a.PW) {
 #pragma unroll
@@ -355,16 +433,15 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
     }
   }
 #ifdef BRCNN_DEBUG_TIMING
-  if (dbg != nullptr && lane == 0 && (warp == RT_CONS_WARPS || warp == 0)) {
-    const int o = warp == 0 ? 0 : 8;      // consumer warp 0 | producer
+  if (dbg != nullptr && lane == 0 && (warp == 0 || warp >= RT_CONS_WARPS)) {
+    const int o = warp == 0 ? 0 : (warp == RT_CONS_WARPS ? 8 : 16);
     atomicAdd(dbg + o + 0, 1ull);
     atomicAdd(dbg + o + 1, (unsigned long long)(clock64() - d_t0));
-    atomicAdd(dbg + o + 2, (unsigned long long)d_a);   // consumer: table waits | producer: publish
-    atomicAdd(dbg + o + 3, (unsigned long long)d_b);   // consumer: row waits   | producer: slot waits
+    atomicAdd(dbg + o + 2, (unsigned long long)d_a);   // consumer / issuer: table waits | publisher: tables
+    atomicAdd(dbg + o + 3, (unsigned long long)d_b);   // consumer: row waits | issuer: slot waits | publisher: buffer waits
     atomicAdd(dbg + o + 4, (unsigned long long)d_c);   // consumer: stores
     atomicAdd(dbg + o + 5, (unsigned long long)k);
   }
-  (void)d_d;
 #endif
 }
 

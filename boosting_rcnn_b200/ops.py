@@ -27,6 +27,39 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_SCHED_SLOT_INTS = 64          # brcnn_roi_extract_forward_workspace_bytes / 4
+_SCHED_POOLS = {}              # device index -> [zeroed int32 pool, next free slot, {stream: slot}]
+
+
+def _sched_scratch(device, nbytes):
+    """Zero-filled scheduling scratch of the persistent RoIAlign forward.  The kernel leaves
+    it zero-filled, so a slot is cleared exactly once, when its pool is allocated.  Eager
+    calls share one slot per stream (calls on a stream are ordered); every call recorded
+    into a CUDA graph takes a slot of its own, because graphs captured on one stream may
+    later replay concurrently on several."""
+    assert nbytes <= 4 * _SCHED_SLOT_INTS
+    capturing = torch.cuda.is_current_stream_capturing()
+    pool = _SCHED_POOLS.get(device.index)
+    if pool is None and not capturing:
+        pool = [torch.zeros((1024, _SCHED_SLOT_INTS), dtype=torch.int32, device=device), 0, {}]
+        _SCHED_POOLS[device.index] = pool
+    if pool is not None and pool[1] < pool[0].size(0):
+        if capturing:
+            slot = pool[1]
+            pool[1] += 1
+            return pool[0][slot]
+        key = _stream()
+        if key not in pool[2]:
+            pool[2][key] = pool[1]
+            pool[1] += 1
+        return pool[0][pool[2][key]]
+    if not capturing and _stream() in pool[2]:
+        return pool[0][pool[2][_stream()]]
+    # pool exhausted / first use inside a capture: a fresh cleared buffer (inside a capture the
+    # clear is recorded into the graph: one extra fill per replay)
+    return torch.zeros((_SCHED_SLOT_INTS,), dtype=torch.int32, device=device)
+
+
 def _first_cuda_tensor(args):
     for a in args:
         if isinstance(a, torch.Tensor):
@@ -525,9 +558,12 @@ class _RoiExtractFunction(Function):
             out = torch.empty((R, C, p.pooled_h, p.pooled_w), dtype=torch.float32,
                               device=rois.device)
         lvls = torch.empty((R,), dtype=torch.int32, device=rois.device)
+        ws_bytes = lib.brcnn_roi_extract_forward_workspace_bytes(p)
+        ws = _sched_scratch(rois.device, ws_bytes)
         check(lib.brcnn_roi_extract_forward(
             p, ptr_array([t.data_ptr() for t in nhwc]), rois.data_ptr(), R,
-            out.data_ptr(), lvls.data_ptr(), _stream()), 'brcnn_roi_extract_forward')
+            out.data_ptr(), lvls.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+            'brcnn_roi_extract_forward')
         ctx.save_for_backward(rois)
         ctx.params = p
         ctx.channels_last = [f.permute(0, 2, 3, 1).is_contiguous() for f in feats]

@@ -228,11 +228,19 @@ int brcnn_map_roi_levels(const float* rois, int32_t num_rois,
  * and produce zeros.  out: (R, C, pooled_h, pooled_w) NCHW-contiguous, the
  * layout ConvFCBBoxHead flattens (convfc_bbox_head.py:164), or
  * (R, pooled_h, pooled_w, C) when p->out_layout == 1.
- * roi_levels: optional int32[R] (level used for each RoI).                 */
+ * roi_levels: optional int32[R] (level used for each RoI).
+ * workspace: optional scheduling scratch of brcnn_roi_extract_forward_workspace_bytes
+ * bytes, ZERO-FILLED by the caller once; every call leaves it zero-filled, so one
+ * buffer serves all calls issued on the same stream (calls that may run concurrently
+ * need a buffer each).  With it the persistent CTAs pull RoIs from an atomic counter
+ * (RoI cost varies ~4x with the footprint); NULL selects a static round-robin
+ * schedule - same results bit for bit, longer tail.                          */
+size_t brcnn_roi_extract_forward_workspace_bytes(const brcnn_roi_params* p);
 int brcnn_roi_extract_forward(const brcnn_roi_params* p,
                               const float* const* feats_nhwc_host,
                               const float* rois, int32_t num_rois, float* out,
-                              int32_t* roi_levels, brcnn_stream_t stream);
+                              int32_t* roi_levels, void* workspace,
+                              size_t workspace_bytes, brcnn_stream_t stream);
 
 size_t brcnn_roi_extract_backward_workspace_bytes(const brcnn_roi_params* p,
                                                   int32_t num_rois);
