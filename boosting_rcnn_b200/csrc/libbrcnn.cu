@@ -20,6 +20,7 @@
 #include "roi_align_bwd2.cuh"
 #include "roi_align_bwd3.cuh"
 #include "roi_align_bwd4.cuh"
+#include "roi_align_bwd5.cuh"
 #include "roi_align_fwd3.cuh"
 #include "roi_align_tma.cuh"
 #include "rpn.cuh"
@@ -1189,7 +1190,7 @@ static int roi_bwd2_launch(RoiArgs a, const float* grad_out, int out_layout, con
   if (R > 0) {
     RoiBwdBuckets nob;
     memset(&nob, 0, sizeof(nob));
-    roi_bwd_prep_kernel<<<R, 128, 0, stream>>>(ba.a, rois, R, ba.TR, recs, keys, tab, nob);
+    roi_bwd_prep_kernel<<<R, B2_PREP_THREADS, 0, stream>>>(ba.a, rois, R, ba.TR, recs, keys, tab, nob);
     g_launch_count_add(1);
     BRCNN_CUDA_CHECK_LAST();
     if (out_layout == 0) {
@@ -1242,6 +1243,17 @@ static int roi_bwd3_launch(RoiArgs a, const float* grad_out, int out_layout, con
   RoiBwdRec* bucket_rec = (RoiBwdRec*)(ws + w.bucket_rec);
   const float* gt = grad_out;
   const int nbins = a.PH * a.PW;
+  static const int use_v = [] {
+    const char* e = getenv("BRCNN_ROI_BWD");       // developer knob: v3 / v4 select the older gathers
+    return (e && e[0] == 'v' && e[1] >= '3' && e[1] <= '5') ? e[1] - '0' : 5;
+  }();
+  if (use_v == 5 && R == 0) {              // nothing to gather: every level gets zeros
+    for (int l = 0; l < a.L; ++l) {
+      cudaError_t e0 = cudaMemsetAsync(ba.grad[l], 0, (size_t)a.B * a.H[l] * a.W[l] * a.C * 4, stream);
+      if (e0 != cudaSuccess) return (int)e0;
+    }
+    return BRCNN_OK;
+  }
   cudaError_t e = cudaMemsetAsync(bucket_cnt, 0, w.zero_bytes, stream);
   if (e != cudaSuccess) return (int)e;
   if (R > 0) {
@@ -1255,7 +1267,7 @@ static int roi_bwd3_launch(RoiArgs a, const float* grad_out, int out_layout, con
       bk.tiles_x[l] = ba.tiles_x[l]; bk.tiles_y[l] = ba.tiles_y[l];
       bk.tile_first[l] = ba.tile_first[l];
     }
-    roi_bwd_prep_kernel<<<R, 128, 0, stream>>>(ba.a, rois, R, ba.TR, recs, keys, tab, bk);
+    roi_bwd_prep_kernel<<<R, B2_PREP_THREADS, 0, stream>>>(ba.a, rois, R, ba.TR, recs, keys, tab, bk);
     g_launch_count_add(1);
     BRCNN_CUDA_CHECK_LAST();
     if (out_layout == 0) {
@@ -1267,10 +1279,19 @@ static int roi_bwd3_launch(RoiArgs a, const float* grad_out, int out_layout, con
   dim3 grid((unsigned)base, (a.C + B3_CS - 1) / B3_CS);
   if (grid.y > 65535) return BRCNN_ERR_UNSUPPORTED;
   const size_t smem = (size_t)B3_NS * B3_STAGE;
-  static const bool use_v3 = [] {
-    const char* e = getenv("BRCNN_ROI_BWD");
-    return e && e[0] == 'v' && e[1] == '3';
-  }();
+  if (use_v == 5) {
+    // v5: one CTA per (tile, slab), warp-private cp.async rings (roi_align_bwd5.cuh)
+    static_assert(B4_TILE_CAP == B5_WIN, "tile list capacity");
+    e = ensure_dyn_smem((const void*)roi_bwd_gather5_kernel, B5_RING_BYTES, true);
+    if (e != cudaSuccess) return (int)e;
+    roi_bwd_gather5_kernel<<<grid, B5_THREADS, B5_RING_BYTES, stream>>>(
+        ba, (const int32_t*)(ws + w.tile_r), (const RoiBwdRec*)(ws + w.tile_rec), tile_cnt,
+        bucket_rec, bucket, bucket_cnt, R, tab, gt);
+    g_launch_count_add(1);
+    BRCNN_CUDA_CHECK_LAST();
+    return BRCNN_OK;
+  }
+  const bool use_v3 = use_v == 3;
   if (!use_v3 && (long long)base * grid.y <= 0x7fffffffLL) {
     // v4: persistent CTAs pulling (tile, slab) items from an atomic counter
     static_assert(B4_TILE_CAP == B4_CAP, "tile list capacity");

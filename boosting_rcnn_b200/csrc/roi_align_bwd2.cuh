@@ -34,6 +34,7 @@ constexpr int B2_CCH = 16 * B2_QPT;  // channels per CTA (4 quad groups x B2_QPT
 constexpr int B2_THREADS = 256;     // 8 rows x 8 px x 4 quad groups
 constexpr int B2_LIST = 1024;       // RoIs gathered per round
 constexpr int B2_P = 7;             // max pooled side on this path
+constexpr int B2_PREP_THREADS = 128;   // 16 table rows per pass (a RoI has ~20)
 
 struct RoiBwdRec {      // 16 B, read by every tile CTA
   int ylo, yhi, xlo, xhi;   // inclusive footprint; empty if ylo > yhi
@@ -60,8 +61,8 @@ struct RoiBwd2Args {
   int TR;               // table rows per RoI = max_h + max_w
 };
 
-// grid R, block 128.  tab: [R][TR][8] floats, key: uint16 (b*L + lvl, 0xFFFF = none)
-__global__ void __launch_bounds__(128)
+// grid R, block B2_PREP_THREADS.  tab: [R][TR][8] floats, key: uint16 (b*L + lvl, 0xFFFF = none)
+__global__ void __launch_bounds__(B2_PREP_THREADS)
 roi_bwd_prep_kernel(const __grid_constant__ RoiArgs a, const float* __restrict__ rois, int R,
                     int TR, RoiBwdRec* __restrict__ recs, unsigned short* __restrict__ keys,
                     float* __restrict__ tab, const RoiBwdBuckets bk) {
@@ -100,7 +101,7 @@ roi_bwd_prep_kernel(const __grid_constant__ RoiArgs a, const float* __restrict__
     const int ntx = rec.xhi / ts - tx0 + 1, nty = rec.yhi / ts - ty0 + 1;
     int32_t* tc = bk.tile_cnt + bk.tile_first[g.lvl] +
                   (size_t)g.b * bk.tiles_x[g.lvl] * bk.tiles_y[g.lvl];
-    for (int i = tid; i < ntx * nty; i += 128) {
+    for (int i = tid; i < ntx * nty; i += B2_PREP_THREADS) {
       const int dy = i / ntx, dx = i - dy * ntx;
       int32_t* cell = tc + (ty0 + dy) * bk.tiles_x[g.lvl] + tx0 + dx;
       const int pos = atomicAdd(cell, 1);
@@ -111,27 +112,23 @@ roi_bwd_prep_kernel(const __grid_constant__ RoiArgs a, const float* __restrict__
       }
     }
   }
+  // tables: thread = (table row, pooled index); 8 consecutive lanes own one row, the row's
+  // non-zero band comes from a ballot over them
   const int fh = rec.yhi - rec.ylo + 1, fw = rec.xhi - rec.xlo + 1;
   float* t = tab + (size_t)r * TR * 8;
-  for (int row = tid; row < fh + fw; row += 128) {
+  const int lane = tid & 31, p = tid & 7;
+  for (int row0 = 0; row0 < fh + fw; row0 += B2_PREP_THREADS / 8) {
+    const int row = row0 + (tid >> 3);
+    const bool live = row < fh + fw;
     const bool isy = row < fh;
     const int pos = isy ? rec.ylo + row : rec.xlo + (row - fh);
-    float w[8];
-    int pa = 8, pb = -1;
-    const int np = isy ? a.PH : a.PW;
-#pragma unroll
-    for (int p = 0; p < B2_P; ++p) {
-      float v = 0.f;
-      if (p < np)
-        v = isy ? roi_axis_weight(g.start_h, g.bin_h, g.gh, g.H, p, pos) * g.inv_count
-                : roi_axis_weight(g.start_w, g.bin_w, g.gw, g.W, p, pos);
-      w[p] = v;
-      if (v != 0.f) { pa = min(pa, p); pb = p; }
-    }
-    w[7] = __int_as_float(pb < 0 ? (1 | (0 << 8)) : (pa | (pb << 8)));
-    float4* dst = reinterpret_cast<float4*>(t + (size_t)(isy ? row : a.max_h + (row - fh)) * 8);
-    dst[0] = make_float4(w[0], w[1], w[2], w[3]);
-    dst[1] = make_float4(w[4], w[5], w[6], w[7]);
+    float v = 0.f;
+    if (live && p < (isy ? a.PH : a.PW))
+      v = isy ? roi_axis_weight(g.start_h, g.bin_h, g.gh, g.H, p, pos) * g.inv_count
+              : roi_axis_weight(g.start_w, g.bin_w, g.gw, g.W, p, pos);
+    const unsigned nz = (__ballot_sync(0xffffffffu, v != 0.f) >> (lane & 24)) & 0x7fu;
+    if (p == 7) v = __int_as_float(nz ? ((__ffs(nz) - 1) | ((31 - __clz(nz)) << 8)) : 1);
+    if (live) t[(size_t)(isy ? row : a.max_h + (row - fh)) * 8 + p] = v;
   }
 }
 

@@ -53,6 +53,7 @@ def main():
     ap.add_argument('--train', action='store_true')
     ap.add_argument('--rois-per-img', type=int, default=0)
     ap.add_argument('--reps', type=int, default=20)
+    ap.add_argument('--dump-rois', default='', help='write the (R,5) RoIs to this .npy file')
     args = ap.parse_args()
     from boosting_rcnn_b200 import configs, ops
     dev = torch.device('cuda', 0)
@@ -76,6 +77,8 @@ def main():
     rois, _ = ops.bbox2roi_padded(boxes, num)
     scales = [1.0 / s for s in bench.STRIDES]
     R = rois.size(0)
+    if args.dump_rois:
+        np.save(args.dump_rois, rois.cpu().numpy())
     out = {'cfg': args.cfg, 'batch': B, 'rois': int(R), 'live': int((rois[:, 0] >= 0).sum()),
            'bwd_env': os.environ.get('BRCNN_ROI_BWD', 'default')}
     with torch.no_grad():
