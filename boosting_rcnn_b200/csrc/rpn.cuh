@@ -1,16 +1,19 @@
 // K1: RPN proposal generation for a whole batch (every image, every level).
 //
-//   rpn_score_kernel        whole-GPU pass over the RPN outputs: key =
-//       bits(sqrt(sigmoid(cls) * sigmoid(iou))) written once (plane order,
-//       coalesced) plus a 2048-bin histogram of the score VALUE
-//       (bin = floor(s * 2048), uniform over [0,1]) per (image, level)
-//       segment (shared-memory privatised, flushed with integer atomics).
-//   rpn_collect_kernel      whole-GPU pass over the L2-resident keys: every CTA
-//       re-derives its segment's threshold bin d (#(bins > d) < k <= #(bins >=
-//       d)) from the histogram and appends the keys with s >= d/2048 -- a
-//       superset of the top-k, typically k + ~100 -- as 64-bit composites
-//       (score_bits << 32 | ~anchor_index) to the segment's candidate buffer
-//       (CTA-aggregated: one global atomic per CTA).
+//   rpn_score_kernel        whole-GPU pass over the RPN outputs: an APPROXIMATE score
+//       sqrt(sigmoid(cls) * sigmoid(iou)) from the special-function unit (|error| < 2e-5,
+//       25 instructions instead of the 130 of the pinned IEEE chain that made this kernel
+//       ALU-bound at 29 % of the HBM roofline) written once (plane order, coalesced) plus a
+//       2048-bin histogram of the score VALUE (bin = floor(s * 2048), uniform over [0,1]) per
+//       (image, level) segment (shared-memory privatised, flushed with integer atomics).
+//   rpn_collect_kernel      whole-GPU pass over the L2-resident approximate scores: every CTA
+//       re-derives its segment's threshold bin d (#(bins > d) < k <= #(bins >= d)) from the
+//       histogram, keeps the elements of bins >= d - 1 -- a superset of the EXACT top-k,
+//       because the approximation error is a small fraction of a bin -- and recomputes their
+//       scores with the pinned arithmetic: 64-bit composites (exact_score_bits << 32 |
+//       ~anchor_index) go to the segment's candidate buffer (CTA-aggregated: one global atomic
+//       per CTA).  Only ~2 % of the anchors pay for the exact arithmetic.  Segments that go to
+//       the radix path below get their keys rewritten with exact scores here.
 //   rpn_topk_decode_kernel  one CTA per segment: bitonic sort of the collected
 //       composites in shared memory = (score desc, index asc) with no ties,
 //       first k decoded (anchor built on the fly + delta2bbox + clip +
@@ -68,6 +71,23 @@ __device__ __forceinline__ u64 rpn_make_key(uint32_t score_bits, uint32_t concat
   return ((u64)score_bits << 32) | (u64)(0xFFFFFFFFu - concat_idx);
 }
 
+// Approximate sqrt(sigmoid(c) * sigmoid(i)) from the special-function unit (ex2 / rcp / sqrt
+// .approx, ~25 instructions instead of ~130 for the pinned IEEE chain).  Absolute error
+// < 2e-5 on [0, 1] (relative error of each approximate op <= 2^-21, argument rounding of the
+// exponential <= |x| * 2^-23 where the sigmoid's slope is <= 1/4), i.e. far below one histogram
+// bin (1 / 2048).  Only the per-level CANDIDATE SELECTION uses it: every candidate's key is
+// recomputed with the pinned arithmetic (rpn_exact_key) before anything is ranked.
+__device__ __forceinline__ float rpn_fast_score(float c, float i) {
+  const float p = __fdividef(1.0f, 1.0f + __expf(-c)) * __fdividef(1.0f, 1.0f + __expf(-i));
+  float s;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(p));
+  return s;
+}
+// the reference's score, op for op (atss_rpn_head.py:722: (cls.sigmoid() * iou.sigmoid()).sqrt())
+__device__ __forceinline__ uint32_t rpn_exact_key(float c, float i) {
+  return __float_as_uint(sqrtf(pinned_sigmoid(c) * pinned_sigmoid(i)));
+}
+
 // grid (chunks_per_image, B)
 __global__ void __launch_bounds__(RPN_SCORE_THREADS)
 rpn_score_kernel(const __grid_constant__ RpnArgs a, uint32_t* __restrict__ keys,
@@ -83,7 +103,7 @@ rpn_score_kernel(const __grid_constant__ RpnArgs a, uint32_t* __restrict__ keys,
   const float* cls = lv.cls + (size_t)b * lv.n;
   const float* iou = lv.iou + (size_t)b * lv.n;
   uint32_t* kout = keys + (size_t)b * a.key_stride + lv.key_off;
-  // all 16 loads of the thread in flight before the (ALU-heavy) sigmoids
+  // all 16 loads of the thread in flight before the arithmetic
   constexpr int NJ = RPN_SCORE_CHUNK / RPN_SCORE_THREADS;
   float vc[NJ], vi[NJ];
 #pragma unroll
@@ -96,9 +116,8 @@ rpn_score_kernel(const __grid_constant__ RpnArgs a, uint32_t* __restrict__ keys,
   for (int j = 0; j < NJ; ++j) {
     const int e = e0 + j * RPN_SCORE_THREADS + threadIdx.x;
     if (e < lv.n) {
-      const float s = sqrtf(pinned_sigmoid(vc[j]) * pinned_sigmoid(vi[j]));
-      const uint32_t key = __float_as_uint(s);
-      kout[e] = key;
+      const float s = rpn_fast_score(vc[j], vi[j]);
+      kout[e] = __float_as_uint(s);
       atomicAdd(&sh[rpn_value_bin(s)], 1u);
     }
   }
@@ -181,9 +200,16 @@ __device__ __forceinline__ void rpn_find_digit_256(const uint32_t* __restrict__ 
   __syncthreads();
 }
 
-// grid (chunks_per_image, B), same chunking as the score kernel
+// grid (chunks_per_image, B), same chunking as the score kernel.
+// `keys` hold the APPROXIMATE scores of rpn_score_kernel.  With d = the histogram bin of the
+// k-th best approximate score, every element of the exact top-k has an approximate score in
+// bin >= d - 1 (the approximation error is a small fraction of a bin), so the chunk keeps the
+// elements of bins >= d - 1 and recomputes THEIR keys with the pinned arithmetic; the top-k
+// kernel ranks exact keys only.  A segment whose candidates would not fit (degenerate score
+// distribution) goes to the top-k kernel's exact radix path instead: this kernel then rewrites
+// the segment's keys with exact scores in place.
 __global__ void __launch_bounds__(RPN_SCORE_THREADS)
-rpn_collect_kernel(const __grid_constant__ RpnArgs a, const uint32_t* __restrict__ keys,
+rpn_collect_kernel(const __grid_constant__ RpnArgs a, uint32_t* __restrict__ keys,
                    const uint32_t* __restrict__ ghist, u64* __restrict__ cand_raw,
                    int32_t* __restrict__ cand_n) {
   __shared__ u64 s_buf[RPN_SCORE_CHUNK];
@@ -200,7 +226,9 @@ rpn_collect_kernel(const __grid_constant__ RpnArgs a, const uint32_t* __restrict
   // this thread's keys: loads issued before the (latency-bound) threshold search
   constexpr int NJ = RPN_SCORE_CHUNK / RPN_SCORE_THREADS;
   const int e0 = ((int)blockIdx.x - lv.chunk_base) * RPN_SCORE_CHUNK;
-  const uint32_t* kseg = keys + (size_t)b * a.key_stride + lv.key_off;
+  uint32_t* kseg = keys + (size_t)b * a.key_stride + lv.key_off;
+  const float* cls = lv.cls + (size_t)b * lv.n;
+  const float* iou = lv.iou + (size_t)b * lv.n;
   uint32_t kreg[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
@@ -208,42 +236,57 @@ rpn_collect_kernel(const __grid_constant__ RpnArgs a, const uint32_t* __restrict
     kreg[j] = (e < n) ? __ldg(kseg + e) : 0u;
   }
   uint32_t thr = 0u;
+  bool exact_path = false;           // block-uniform
   if (k < n) {
-    rpn_find_digit_256(ghist + (size_t)seg * RPN_BINS, RPN_BINS, (uint32_t)k, s_warp, s_out);
-    if (s_out[1] + s_out[2] > a.cand_cap) return;   // over-populated bin: slow path (block-uniform)
-    thr = rpn_bin_floor_bits(s_out[0]);
+    const uint32_t* hist = ghist + (size_t)seg * RPN_BINS;
+    rpn_find_digit_256(hist, RPN_BINS, (uint32_t)k, s_warp, s_out);
+    const int d = s_out[0];
+    const int margin = d > 0 ? (int)hist[d - 1] : 0;
+    if (s_out[1] + s_out[2] + margin > a.cand_cap) exact_path = true;   // same rule as the top-k kernel
+    else thr = rpn_bin_floor_bits(d > 0 ? d - 1 : 0);
   } else if (n > a.cand_cap) {
+    exact_path = true;
+  }
+  if (exact_path) {
+#pragma unroll 1
+    for (int j = 0; j < NJ; ++j) {
+      const int e = e0 + j * RPN_SCORE_THREADS + tid;
+      if (e < n) kseg[e] = rpn_exact_key(__ldg(cls + e), __ldg(iou + e));
+    }
     return;
   }
   if (tid == 0) s_cnt = 0;
   __syncthreads();
-  const float inv_P = 1.0f / (float)P;
+  // ---- compact the chunk's candidates (element numbers) ----
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const int e = e0 + j * RPN_SCORE_THREADS + tid;
-    const uint32_t key = kreg[j];
-    const bool take = (e < n) && (key >= thr);
+    const bool take = (e < n) && (kreg[j] >= thr);
     const unsigned m = __ballot_sync(0xffffffffu, take);
     if (m) {
       const int leader = __ffs(m) - 1;
       int base = 0;
       if (lane == leader) base = atomicAdd(&s_cnt, __popc(m));
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (take) {
-        // e = an*P + p -> concatenated anchor index idx_base + p*A + an
-        int an = (n < (1 << 24)) ? __float2int_rz(__int2float_rn(e) * inv_P) : e / P;
-        int rem = e - an * P;
-        an += (rem >= P) - (rem < 0);
-        const int p = e - an * P;
-        s_buf[base + __popc(m & ((1u << lane) - 1u))] =
-            rpn_make_key(key, (uint32_t)(lv.idx_base + p * A + an));
-      }
+      if (take) s_buf[base + __popc(m & ((1u << lane) - 1u))] = (u64)(uint32_t)e;
     }
   }
   __syncthreads();
   const int cnt = s_cnt;
   if (cnt == 0) return;
   if (tid == 0) s_base = atomicAdd(cand_n + seg, cnt);
+  // ---- exact keys of the candidates, all lanes busy ----
+  const float inv_P = 1.0f / (float)P;
+  for (int i = tid; i < cnt; i += RPN_SCORE_THREADS) {
+    const int e = (int)(uint32_t)s_buf[i];     // slot i is read and rewritten by this thread only
+    const uint32_t key = rpn_exact_key(__ldg(cls + e), __ldg(iou + e));
+    // e = an*P + p -> concatenated anchor index idx_base + p*A + an
+    int an = (n < (1 << 24)) ? __float2int_rz(__int2float_rn(e) * inv_P) : e / P;
+    int rem = e - an * P;
+    an += (rem >= P) - (rem < 0);
+    const int p = e - an * P;
+    s_buf[i] = rpn_make_key(key, (uint32_t)(lv.idx_base + p * A + an));
+  }
   __syncthreads();
   u64* dst = cand_raw + (size_t)seg * a.cand_cap + s_base;
   for (int i = tid; i < cnt; i += RPN_SCORE_THREADS) dst[i] = s_buf[i];
@@ -317,16 +360,42 @@ rpn_topk_decode_kernel(const __grid_constant__ RpnArgs a,
     for (int i = tid; i < RPN_BINS; i += RPN_TOPK_THREADS) sh[i] = ghist[(size_t)seg * RPN_BINS + i];
     __syncthreads();
     rpn_find_digit(sh, RPN_BINS, (uint32_t)k, s_warp, s_out);
-    fast = (s_out[1] + s_out[2] <= a.cand_cap);   // same rule as rpn_collect_kernel
+    // same rule as rpn_collect_kernel (bins >= d - 1 were collected)
+    fast = (s_out[1] + s_out[2] + (s_out[0] > 0 ? (int)sh[s_out[0] - 1] : 0) <= a.cand_cap);
     __syncthreads();
   } else {
     fast = (n <= a.cand_cap);
   }
   if (fast) {
+    // The collected set is bins >= d - 1 of the approximate score.  If at least k of its
+    // EXACT scores lie in bins >= d, nothing below bin d can be in the top-k: drop it, so the
+    // margin bin does not push the bitonic sort over the next power of two (k = 1000 sits
+    // just under 1024).
     const int nc = cand_n[seg];
     const u64* src = cand_raw + (size_t)seg * a.cand_cap;
-    for (int i = tid; i < nc; i += RPN_TOPK_THREADS) cand[i] = src[i];
-    if (tid == 0) s_ncand = nc;
+    const uint32_t cut = (k < n && s_out[0] > 0) ? rpn_bin_floor_bits(s_out[0]) : 0u;
+    if (tid == 0) { s_ncand = 0; s_out[1] = 0; }
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < nc; i += RPN_TOPK_THREADS) mine += ((uint32_t)(src[i] >> 32) >= cut);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0 && mine) atomicAdd(&s_out[1], mine);
+    __syncthreads();
+    const uint32_t keep_from = (s_out[1] >= k) ? cut : 0u;
+    for (int i0 = 0; i0 < nc; i0 += RPN_TOPK_THREADS) {
+      const int i = i0 + tid;
+      const u64 c = (i < nc) ? src[i] : 0ull;
+      const bool take = (i < nc) && ((uint32_t)(c >> 32) >= keep_from);
+      const unsigned m = __ballot_sync(0xffffffffu, take);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&s_ncand, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (take) cand[base + __popc(m & ((1u << lane) - 1u))] = c;
+      }
+    }
     __syncthreads();
   } else {
   // ---- slow path: exact selection threshold on the 64-bit composite ----
