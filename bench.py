@@ -469,7 +469,7 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
         bwd_bytes = R * C * 49 * 4 + feat_bytes
         ach = bwd_bytes / (st['roi_align_bwd'] * 1e-3) / 1e9
         rec['stages_ms'] = st
-        rec['roofline'] = dict(kernel='roi_bwd_gather3_kernel (+ roi_bwd_prep_kernel)', bound='hbm',
+        rec['roofline'] = dict(kernel='roi_bwd_prep_kernel + roi_bwd_gather5_kernel', bound='hbm',
                                achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,
                                peak_source=peak_src, algorithmic_bytes_per_launch=bwd_bytes,
                                ms_per_launch=st['roi_align_bwd'],

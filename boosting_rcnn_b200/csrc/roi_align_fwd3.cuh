@@ -61,6 +61,22 @@ __device__ __forceinline__ void r3_ffma2(float2& d, const float2 a, const float2
         "l"(reinterpret_cast<const unsigned long long&>(b)));
 }
 
+__device__ __forceinline__ float2 r3_fmul2(const float2 a, const float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)),
+        "l"(reinterpret_cast<const unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float4 r3_lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+template <int N> struct R3Int { static constexpr int value = N; };
+
 // acc[PH] += w[PH] * h (static pooled-row index)
 template <int PH>
 __device__ __forceinline__ void r3_fold1(float2 (&a0)[RT_P][2], float2 (&a1)[RT_P][2],
@@ -114,8 +130,9 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
   extern __shared__ __align__(128) unsigned char r3_smem[];
   float* ring = reinterpret_cast<float*>(r3_smem);
   float* tabs = reinterpret_cast<float*>(r3_smem + (size_t)lay.ns * lay.slot_bytes);
-  __shared__ __align__(8) uint64_t full_bar[R3_MAX_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[R3_MAX_STAGES];
+  __shared__ __align__(8) uint64_t ring_bar[2 * R3_MAX_STAGES];   // full[i] | empty[i] 64 B apart
+  uint64_t* full_bar = ring_bar;
+  uint64_t* empty_bar = ring_bar + R3_MAX_STAGES;
   __shared__ __align__(8) uint64_t tab_full[R3_TABS];
   __shared__ __align__(8) uint64_t tab_empty[R3_TABS];
 
@@ -140,7 +157,7 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const uint32_t full0 = smem_u32(ring_bar), empty0 = full0 + 8u * R3_MAX_STAGES;
   const uint32_t tfull0 = smem_u32(tab_full), tempty0 = smem_u32(tab_empty);
 
   int s = 0, round = 0;   // ring position (issuer and consumers advance identically)
@@ -192,7 +209,7 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
       float* wy = tb + R3_DESC;                        // [fh][8]
       float* wx = wy + (size_t)a.max_h * 8;            // [pw][max_w]
       R3_TIC();
-      if (pk >= R3_TABS) mbar_wait_addr(tempty0 + 8u * pb_i, (uint32_t)(pb_ph ^ 1));
+      if (pk >= R3_TABS) mbar_wait_addr_hint(tempty0 + 8u * pb_i, (uint32_t)(pb_ph ^ 1), 4000u);
       R3_TOC(d_b);
       R3_TIC();
       if (lane == 0) {
@@ -260,7 +277,7 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
         const int* desc = reinterpret_cast<const int*>(tabs + (size_t)tb_i * lay.tab_floats);
         if (SPLIT) {
           R3_TIC();
-          mbar_wait_addr(tfull0 + 8u * tb_i, (uint32_t)tb_ph);
+          mbar_wait_addr_hint(tfull0 + 8u * tb_i, (uint32_t)tb_ph, 4000u);
           R3_TOC(d_a);
         }
         const int4 d0 = *reinterpret_cast<const int4*>(desc);        // state, ylo, fh, fw
@@ -277,7 +294,7 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
         for (int phase = 0; phase < 2; ++phase) {
           for (; budget > 0; --budget, --rows_left) {
             R3_TIC();
-            if (round > 0) mbar_wait_addr(empty0 + 8u * s, (uint32_t)((round - 1) & 1));
+            if (round > 0) mbar_wait_addr_hint(empty0 + 8u * s, (uint32_t)((round - 1) & 1), 4000u);
             R3_TOC(d_b);
             const uint32_t fb = full0 + 8u * s;
             if (contiguous) {
@@ -334,7 +351,7 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
       const float* wy = tb + R3_DESC;
       const float* wxp = wy + (size_t)a.max_h * 8 + (size_t)(act0 ? pw : 0) * a.max_w;
       R3_TIC();
-      mbar_wait_addr(tfull0 + 8u * tb_i, (uint32_t)tb_ph);
+      mbar_wait_addr_hint(tfull0 + 8u * tb_i, (uint32_t)tb_ph, 2000u);
       R3_TOC(d_a);
       const int4 d0 = *reinterpret_cast<const int4*>(desc);        // state, ylo, fh, fw
       if (d0.x == 2) break;                                        // no RoI left
@@ -349,35 +366,8 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
       }
       if (d0.x == 0) {
         const int bxs = act0 ? desc[8 + pw] : 1, bxe = act0 ? desc[16 + pw] : 0;
-        for (int pass = 0; pass < npass; ++pass) {
-          const int x0 = pass * cw;
-          const int cwe = min(cw, fw - x0);
-          const int xs = max(bxs, x0), xe = min(bxe, x0 + cwe - 1);
-          const bool work = act0 && (xs <= xe);
-          for (int dy = 0; dy < fh; ++dy) {
-            R3_TIC();
-            mbar_wait_addr(full0 + 8u * s, (uint32_t)(round & 1));
-            R3_TOC(d_b);
-            float2 h0[2], h1[2];
-            h0[0] = h0[1] = h1[0] = h1[1] = make_float2(0.f, 0.f);
-            if (work) {
-              const float4* px = reinterpret_cast<const float4*>(ring + (size_t)s * slot_floats) +
-                                 (xs - x0) * ncq;
-              for (int x = xs; x <= xe; ++x) {
-                const float4 v0 = px[lane];
-                const float4 v1 = px[q1];
-                const float w = wxp[x];
-                px += ncq;
-                const float2 w2 = make_float2(w, w);
-                r3_ffma2(h0[0], w2, make_float2(v0.x, v0.y));
-                r3_ffma2(h0[1], w2, make_float2(v0.z, v0.w));
-                r3_ffma2(h1[0], w2, make_float2(v1.x, v1.y));
-                r3_ffma2(h1[1], w2, make_float2(v1.z, v1.w));
-              }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive_addr(empty0 + 8u * s);
-            if (work) {
+        // y-fold of one x-folded footprint row into the pooled rows of its band
+        auto fold = [&](int dy, const float2 (&h0)[2], const float2 (&h1)[2]) {
               const float4 wa = *reinterpret_cast<const float4*>(wy + dy * 8);
               const float4 wb = *reinterpret_cast<const float4*>(wy + dy * 8 + 4);
               const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, 0.f};
@@ -407,9 +397,101 @@ roi_align_fwd3_kernel(const __grid_constant__ RoiArgs a, const float* __restrict
                   }
                 }
               }
+        };
+        const int nb = bxe - bxs + 1;                  // this pooled column's pixel band
+        if (npass == 1 && nb <= 4) {
+          // ---- common case: one x-chunk pass, band of <= 4 pixels.  The band's weights are
+          // per-RoI constants of the warp (registers), the row loop is specialised on the band
+          // length: no inner loop, no per-row weight loads, slot / barrier addresses carried ----
+          float wq[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) wq[i] = (i < nb) ? wxp[bxs + i] : 0.f;
+          const uint32_t ps = (uint32_t)ncq * 16u;                       // bytes per pixel
+          const uint32_t q1off = (uint32_t)(q1 - lane) * 16u;
+          const uint32_t ring_end = smem_u32(ring) + (uint32_t)(NS * lay.slot_bytes);
+          uint32_t c_slot = smem_u32(ring) + (uint32_t)(s * lay.slot_bytes) +
+                            (nb > 0 ? (uint32_t)(bxs * ncq + lane) * 16u : 0u);
+          uint32_t c_fb = full0 + 8u * s;
+          uint32_t c_par = (uint32_t)(round & 1);
+          auto rows = [&](auto nbc) {
+            constexpr int NB = decltype(nbc)::value;
+#pragma unroll 1
+            for (int dy = 0; dy < fh; ++dy) {
+              R3_TIC();
+              mbar_wait_addr(c_fb, c_par);
+              R3_TOC(d_b);
+              float2 h0[2], h1[2];
+              if constexpr (NB > 0) {
+                float4 v0 = r3_lds128(c_slot), v1 = r3_lds128(c_slot + q1off);
+                float2 w2 = make_float2(wq[0], wq[0]);
+                h0[0] = r3_fmul2(w2, make_float2(v0.x, v0.y));
+                h0[1] = r3_fmul2(w2, make_float2(v0.z, v0.w));
+                h1[0] = r3_fmul2(w2, make_float2(v1.x, v1.y));
+                h1[1] = r3_fmul2(w2, make_float2(v1.z, v1.w));
+#pragma unroll
+                for (int i = 1; i < NB; ++i) {
+                  v0 = r3_lds128(c_slot + i * ps);
+                  v1 = r3_lds128(c_slot + i * ps + q1off);
+                  w2 = make_float2(wq[i], wq[i]);
+                  r3_ffma2(h0[0], w2, make_float2(v0.x, v0.y));
+                  r3_ffma2(h0[1], w2, make_float2(v0.z, v0.w));
+                  r3_ffma2(h1[0], w2, make_float2(v1.x, v1.y));
+                  r3_ffma2(h1[1], w2, make_float2(v1.z, v1.w));
+                }
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive_addr(c_fb + 8u * R3_MAX_STAGES);
+              if constexpr (NB > 0) fold(dy, h0, h1);
+              c_slot += (uint32_t)lay.slot_bytes;
+              c_fb += 8u;
+              if (++s == NS) {
+                s = 0; ++round; c_par ^= 1u;
+                c_slot -= (uint32_t)(NS * lay.slot_bytes);
+                c_fb = full0;
+              }
             }
+          };
+          switch (nb) {
+            case 1: rows(R3Int<1>()); break;
+            case 2: rows(R3Int<2>()); break;
+            case 3: rows(R3Int<3>()); break;
+            case 4: rows(R3Int<4>()); break;
+            default: rows(R3Int<0>()); break;       // nothing of this column (or inactive lanes)
+          }
+          (void)ring_end;
+        } else {
+        for (int pass = 0; pass < npass; ++pass) {
+          const int x0 = pass * cw;
+          const int cwe = min(cw, fw - x0);
+          const int xs = max(bxs, x0), xe = min(bxe, x0 + cwe - 1);
+          const bool work = act0 && (xs <= xe);
+          for (int dy = 0; dy < fh; ++dy) {
+            R3_TIC();
+            mbar_wait_addr(full0 + 8u * s, (uint32_t)(round & 1));
+            R3_TOC(d_b);
+            float2 h0[2], h1[2];
+            h0[0] = h0[1] = h1[0] = h1[1] = make_float2(0.f, 0.f);
+            if (work) {
+              const float4* px = reinterpret_cast<const float4*>(ring + (size_t)s * slot_floats) +
+                                 (xs - x0) * ncq;
+              for (int x = xs; x <= xe; ++x) {
+                const float4 v0 = px[lane];
+                const float4 v1 = px[q1];
+                const float w = wxp[x];
+                px += ncq;
+                const float2 w2 = make_float2(w, w);
+                r3_ffma2(h0[0], w2, make_float2(v0.x, v0.y));
+                r3_ffma2(h0[1], w2, make_float2(v0.z, v0.w));
+                r3_ffma2(h1[0], w2, make_float2(v1.x, v1.y));
+                r3_ffma2(h1[1], w2, make_float2(v1.z, v1.w));
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_addr(empty0 + 8u * s);
+            if (work) fold(dy, h0, h1);
             if (++s == NS) { s = 0; ++round; }
           }
+        }
         }
       }
       // tables no longer needed: the publisher may overwrite this buffer

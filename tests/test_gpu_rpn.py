@@ -115,6 +115,28 @@ def test_rpn_concentrated_scores_slow_path(cuda):
               max_per_img=100, iou_thr=0.7, seed=23, mutate=level0_const)
 
 
+def test_rpn_scores_clustered_on_histogram_bin_edges(cuda):
+    """Candidate selection runs on approximate scores (2048 value bins), ranking on the
+    pinned ones: pile the scores of every level onto bin edges d/2048 (+- a few ulp, where the
+    approximate and the exact score fall into different bins) so that the k-th score sits in
+    such a pile; indices, scores and proposals must still equal the oracle bit for bit."""
+    def on_edges(cls, iou):
+        rng = np.random.RandomState(77)
+        for c, u in zip(cls, iou):
+            u[...] = 30.0                                  # sigmoid(iou) == 1: s = sqrt(sigmoid(cls))
+            edges = rng.randint(900, 1100, size=c.shape).astype(np.float64) / 2048.0
+            p = edges * edges                              # sigmoid(cls) that lands ON the edge
+            x = np.log(p / (1.0 - p))
+            x32 = x.astype(np.float32)
+            # +-3 ulp jitter around the edge logit
+            jit = rng.randint(-3, 4, size=c.shape).astype(np.int32)
+            c[...] = (x32.view(np.int32) + jit).view(np.float32)
+    _run_case(cuda, batch=2, pad_hw=(256, 320), img_hw=(250, 317), nms_pre=300,
+              max_per_img=100, iou_thr=0.7, seed=31, mutate=on_edges)
+    _run_case(cuda, batch=1, pad_hw=(512, 640), img_hw=(500, 600), nms_pre=1000,
+              max_per_img=300, iou_thr=0.7, seed=32, mutate=on_edges)
+
+
 def test_rpn_single_anchor_voc_like(cuda):
     _run_case(cuda, batch=2, pad_hw=(608, 1024), img_hw=(600, 1000), nms_pre=1000,
               max_per_img=256, iou_thr=0.7, seed=3, num_scales=1, ratios=(1.0,))
