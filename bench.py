@@ -329,7 +329,7 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
     """configs[2]: R-CNN training step on B200-generated proposals: train-cfg proposal
     generation (nms_pre 4000 / 2000 per image), fused assign + sample + targets + prior
     (2 launches + the reference's CPU randperm), RoIAlign forward ((R,7,7,C) hand-off), 2-fc
-    head, boost loss, backward (head GEMMs on cuBLAS, TMA-staged RoIAlign backward gather),
+    head, boost loss, backward (head GEMMs on cuBLAS, cp.async-staged RoIAlign backward gather),
     then the reference's collectives: NCCL all-reduce of the head gradients (one flat bucket,
     mmdet/apis/train.py:75-83) + ONE fused scalar all-reduce for the logged losses
     (detectors/base.py:201-207).  Returns the record (rank 0) or None."""

@@ -343,3 +343,44 @@ def test_head_consumes_hwc_features_as_a_view(cuda):
     assert torch.allclose(y, y_ref, rtol=1e-4, atol=1e-4)
     (cs1.sum() + bp1.sum()).backward()
     assert xcl.grad.permute(0, 2, 3, 1).is_contiguous()
+
+
+def test_roi_forward_schedule_is_invisible(cuda):
+    """brcnn_roi_extract_forward pulls RoIs from an atomic counter when the caller passes the
+    scheduling scratch and strides statically without it: same bits either way, the scratch is
+    left zero-filled (one buffer serves every later call on the stream), and a scratch that
+    is too small is refused."""
+    from boosting_rcnn_b200 import _lib
+    lib = _lib.load()
+    B, C, pad_hw = 2, 256, (256, 320)
+    sizes = synth.featmap_sizes(*pad_hw)
+    scales = [1.0 / s for s in synth.STRIDES]
+    feats = [torch.from_numpy(f).to(cuda).permute(0, 2, 3, 1).contiguous()
+             for f in synth.fpn_feats(B, C, sizes, seed=5)]
+    rois = torch.from_numpy(synth.random_rois(B, 700, pad_hw[0], pad_hw[1], seed=6)).to(cuda)
+    R = rois.size(0)
+    p = ops.make_roi_params(B, C, sizes, scales, 7, 0, True, 56, out_layout=1)
+    ptrs = ops.ptr_array([f.data_ptr() for f in feats])
+    stream = torch.cuda.current_stream().cuda_stream
+    nbytes = lib.brcnn_roi_extract_forward_workspace_bytes(p)
+    assert 0 < nbytes <= 4096
+    outs = []
+    ws = torch.zeros(nbytes // 4, dtype=torch.int32, device=cuda)
+    for scratch in (None, ws, ws):           # the second dynamic call reuses the buffer as left
+        out = torch.full((R, 7, 7, C), float('nan'), device=cuda)
+        lv = torch.empty(R, dtype=torch.int32, device=cuda)
+        rc = lib.brcnn_roi_extract_forward(p, ptrs, rois.data_ptr(), R, out.data_ptr(),
+                                           lv.data_ptr(),
+                                           scratch.data_ptr() if scratch is not None else None,
+                                           nbytes if scratch is not None else 0, stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert int(ws.abs().sum()) == 0, 'scheduling scratch must be left zero-filled'
+        outs.append((out, lv))
+    for out, lv in outs[1:]:
+        assert torch.equal(out.view(torch.int32), outs[0][0].view(torch.int32))
+        assert torch.equal(lv, outs[0][1])
+    out = torch.empty((R, 7, 7, C), device=cuda)
+    rc = lib.brcnn_roi_extract_forward(p, ptrs, rois.data_ptr(), R, out.data_ptr(), None,
+                                       ws.data_ptr(), 16, stream)
+    assert rc == -2          # BRCNN_ERR_WORKSPACE

@@ -16,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'boosting_rcnn_b200', 'libbrcnn.so')
-DEFAULT = ['roi_align_fwd3_kernel', 'roi_bwd_gather3_kernel', 'roi_align_fwd_tma_kernel',
+DEFAULT = ['roi_align_fwd3_kernel', 'roi_bwd_gather5_kernel', 'roi_align_fwd_tma_kernel',
            'rpn_nms_image_kernel', 'rpn_loss_main_kernel', 'roi_bwd_prep_kernel']
 KEY = re.compile(r'\b(UBLKCP|SYNCS|LDGSTS|FFMA2|UCGABAR|CGAERRBAR|ATOMS?|ATOMG|RED|REDUX|BAR|'
                  r'LDS|STS|STG|LDG|MATCH|VOTE|SHFL|BRX)\b')
