@@ -462,9 +462,14 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
             }
         dcls, dbox, diou = ([t.detach() for t in ts] for ts in (cls, box, iou))
         with torch.no_grad():
-            # eager (the GT / pad tensors are built from host lists inside loss())
-            st['rpn_loss_fwd_eager (targets + losses + raw grads)'] = _dev_time(
-                lambda: rpn_head.loss(dcls, dbox, diou, gts, metas), 10, dev)
+            # eager (the GT / pad tensors are built from host lists inside loss()).  This stage
+            # timer runs on rank 0 only: the loss must not issue its reduce_mean all-reduce here
+            ops.RPN_LOSS_REDUCE_MEAN = False
+            try:
+                st['rpn_loss_fwd_eager (targets + losses + raw grads)'] = _dev_time(
+                    lambda: rpn_head.loss(dcls, dbox, diou, gts, metas), 10, dev)
+            finally:
+                ops.RPN_LOSS_REDUCE_MEAN = True
         feat_bytes = sum(f.numel() * 4 for f in feats)
         bwd_bytes = R * C * 49 * 4 + feat_bytes
         ach = bwd_bytes / (st['roi_align_bwd'] * 1e-3) / 1e9
@@ -641,6 +646,10 @@ def bench_stress(args, rank, world, local_rank):
 
 def main():
     args = parse_args()
+    # a hung rank (GPU or collective) must not sit in NCCL's 10-minute timeout: dump every
+    # thread's stack and leave after BENCH_WATCHDOG_S seconds (a normal run takes 1-3 minutes)
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('BENCH_WATCHDOG_S', '420')), exit=True)
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

@@ -27,6 +27,11 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+#: reduce_mean of the RPN loss normalisers over the ranks (atss_rpn_head.py:441,459).  A caller
+#: that evaluates the loss on ONE rank only (a profiler, a per-stage timer) must switch it off:
+#: a collective the other ranks do not issue desynchronises the process group.
+RPN_LOSS_REDUCE_MEAN = True
+
 _SCHED_SLOT_INTS = 64          # brcnn_roi_extract_forward_workspace_bytes / 4
 _SCHED_POOLS = {}              # device index -> [zeroed int32 pool, next free slot, {stream: slot}]
 
@@ -276,7 +281,8 @@ class _RpnLossFunction(Function):
         # normalisers: reduce_mean over the ranks, clamp at 1 (one fused all-reduce, on device)
         norm = sums[3 * L:].clone()
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if RPN_LOSS_REDUCE_MEAN and dist.is_available() and dist.is_initialized() \
+                and dist.get_world_size() > 1:
             dist.all_reduce(norm.div_(dist.get_world_size()), op=dist.ReduceOp.SUM)
         norm = norm.clamp_(min=1.0)                  # [num_total_samples, bbox_avg_factor]
         inv = torch.cat([norm[0:1].expand(L), norm[1:2].expand(L), norm[0:1].expand(L)]).reciprocal()
