@@ -414,6 +414,25 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_comm = float(t.item())
     ms_nocomm = _timed_steps(lambda: step(False), K, 1, world, dist, dev) if world > 1 else ms
+    # the collective alone: the same flat bucket all-reduced back to back after a barrier (the
+    # in-step figure above also contains the wait for the slowest rank of an eager step)
+    ms_coll = 0.0
+    if world > 1:
+        flat = torch.zeros(n_grad, device=dev)
+        for _ in range(3):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dist.all_reduce(flat)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_coll = float(t.item())
+        del flat
     if rank != 0:
         return None
     rec = {
@@ -423,6 +442,11 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
         'value': B * world * K / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world,
         'images_per_gpu': B, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
         'ms_allreduce': ms_comm, 'ms_per_step_no_comm': ms_nocomm / K,
+        'ms_allreduce_collective_only': ms_coll,
+        'allreduce_note': 'ms_allreduce = device time from the end of backward to the end of the '
+                          'gradient exchange inside the step (bucket copies + NCCL all-reduce + the '
+                          'wait for the slowest rank of an eager, launch-bound step); '
+                          'ms_allreduce_collective_only = the same bucket all-reduced back to back',
         'allreduce_bytes': n_grad * 4,
         'collectives': ('none (1 GPU)' if world == 1 else
                         'NCCL all-reduce of the head gradients (one flat fp32 bucket) + one fused '
@@ -502,6 +526,7 @@ def bench_train(args, rank, world, local_rank):
             'gpu_launches': rec['gpu_launches_per_step'] * rec['steps'], 'clocks': clocks,
             'roofline': rec.get('roofline'), 'stages_ms': rec.get('stages_ms'),
             'ms_allreduce': rec['ms_allreduce'], 'ms_per_step_no_comm': rec['ms_per_step_no_comm'],
+            'ms_allreduce_collective_only': rec.get('ms_allreduce_collective_only'),
             'losses': rec['losses'],
         }
         print(json.dumps(out))
