@@ -19,7 +19,6 @@
 #include "roi_align_bwd.cuh"
 #include "roi_align_bwd2.cuh"
 #include "roi_align_bwd3.cuh"
-#include "roi_align_bwd4.cuh"
 #include "roi_align_bwd5.cuh"
 #include "roi_align_fwd3.cuh"
 #include "roi_align_tma.cuh"
@@ -1122,7 +1121,8 @@ int brcnn_roi_extract_forward(const brcnn_roi_params* p,
   return BRCNN_OK;
 }
 
-// 0 = v1 (pooled sizes > 7), 2 = v2 gather (BRCNN_ROI_BWD=v2), 3 = v3 TMA-staged gather
+// 1 = v1 (pooled sizes > 7), 2 = v2 gather (whole-R key scan; BRCNN_ROI_BWD=v2, or buckets too
+// large), 3 = per-tile lists + roi_bwd_gather5_kernel (the default)
 static int roi_bwd_version(const RoiArgs& a, int R) {
   static const int forced = [] {
     const char* e = getenv("BRCNN_ROI_BWD");
@@ -1132,7 +1132,7 @@ static int roi_bwd_version(const RoiArgs& a, int R) {
   }();
   const bool small = a.PH <= B2_P && a.PW <= B2_P && (long long)a.B * a.L < 65535;
   if (forced == 1 || !small) return 1;
-  // the (image, level) buckets of v3 hold R entries each
+  // the (image, level) buckets of the tiled path hold R entries each
   const bool buckets_ok = (size_t)a.B * a.L * (size_t)(R > 0 ? R : 1) * 20 <= ((size_t)256 << 20);
   if (forced == 2 || !buckets_ok) return 2;
   return 3;
@@ -1243,11 +1243,7 @@ static int roi_bwd3_launch(RoiArgs a, const float* grad_out, int out_layout, con
   RoiBwdRec* bucket_rec = (RoiBwdRec*)(ws + w.bucket_rec);
   const float* gt = grad_out;
   const int nbins = a.PH * a.PW;
-  static const int use_v = [] {
-    const char* e = getenv("BRCNN_ROI_BWD");       // developer knob: v3 / v4 select the older gathers
-    return (e && e[0] == 'v' && e[1] >= '3' && e[1] <= '5') ? e[1] - '0' : 5;
-  }();
-  if (use_v == 5 && R == 0) {              // nothing to gather: every level gets zeros
+  if (R == 0) {              // nothing to gather: every level gets zeros
     for (int l = 0; l < a.L; ++l) {
       cudaError_t e0 = cudaMemsetAsync(ba.grad[l], 0, (size_t)a.B * a.H[l] * a.W[l] * a.C * 4, stream);
       if (e0 != cudaSuccess) return (int)e0;
@@ -1278,65 +1274,13 @@ static int roi_bwd3_launch(RoiArgs a, const float* grad_out, int out_layout, con
   }
   dim3 grid((unsigned)base, (a.C + B3_CS - 1) / B3_CS);
   if (grid.y > 65535) return BRCNN_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)B3_NS * B3_STAGE;
-  if (use_v == 5) {
-    // v5: one CTA per (tile, slab), warp-private cp.async rings (roi_align_bwd5.cuh)
-    static_assert(B4_TILE_CAP == B5_WIN, "tile list capacity");
-    e = ensure_dyn_smem((const void*)roi_bwd_gather5_kernel, B5_RING_BYTES, true);
-    if (e != cudaSuccess) return (int)e;
-    roi_bwd_gather5_kernel<<<grid, B5_THREADS, B5_RING_BYTES, stream>>>(
-        ba, (const int32_t*)(ws + w.tile_r), (const RoiBwdRec*)(ws + w.tile_rec), tile_cnt,
-        bucket_rec, bucket, bucket_cnt, R, tab, gt);
-    g_launch_count_add(1);
-    BRCNN_CUDA_CHECK_LAST();
-    return BRCNN_OK;
-  }
-  const bool use_v3 = use_v == 3;
-  if (!use_v3 && (long long)base * grid.y <= 0x7fffffffLL) {
-    // v4: persistent CTAs pulling (tile, slab) items from an atomic counter
-    static_assert(B4_TILE_CAP == B4_CAP, "tile list capacity");
-    e = ensure_dyn_smem((const void*)roi_bwd_gather4_kernel, smem, true);
-    if (e != cudaSuccess) return (int)e;
-    const long long items = (long long)base * grid.y;
-    const int slots = 3 * sm_count();
-    const unsigned nblk = (unsigned)(items < slots ? items : slots);
-    roi_bwd_gather4_kernel<<<nblk, B3_THREADS, smem, stream>>>(
-        ba, (const int32_t*)(ws + w.tile_r), (const RoiBwdRec*)(ws + w.tile_rec), tile_cnt,
-        bucket_rec, bucket, bucket_cnt, (int32_t*)(ws + w.work_counter), (int)base, (int)grid.y,
-        R, tab, gt);
-    g_launch_count_add(1);
-    BRCNN_CUDA_CHECK_LAST();
-    return BRCNN_OK;
-  }
-  e = ensure_dyn_smem((const void*)roi_bwd_gather3_kernel, smem, true);
+  // one CTA per (tile, slab), warp-private cp.async rings (roi_align_bwd5.cuh)
+  static_assert(B4_TILE_CAP == B5_WIN, "tile list capacity");
+  e = ensure_dyn_smem((const void*)roi_bwd_gather5_kernel, B5_RING_BYTES, true);
   if (e != cudaSuccess) return (int)e;
-#ifdef BRCNN_DEBUG_TIMING
-  // developer build only (-DBRCNN_DEBUG_TIMING): per-phase cycle sums of the gather CTAs
-  static unsigned long long* dbg = [] {
-    unsigned long long* pbuf = nullptr;
-    cudaMalloc(&pbuf, 24 * 8);
-    return pbuf;
-  }();
-  cudaMemsetAsync(dbg, 0, 16 * 8, stream);
-  roi_bwd_gather3_kernel<<<grid, B3_THREADS, smem, stream>>>(ba, bucket_rec, bucket, bucket_cnt,
-                                                            tile_cnt, R, tab, gt, dbg);
-  {
-    unsigned long long h[16];
-    cudaStreamSynchronize(stream);
-    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-    for (int c = 0; c < 2; ++c)
-      if (h[c * 8])
-        fprintf(stderr, "[gather3 %s] ctas=%llu mean cycles: list=%llu first=%llu walk=%llu "
-                "store=%llu  rois/cta=%.2f  warp0: wait-in-walk=%llu stages=%.2f\n",
-                c ? "busy " : "empty", h[c * 8],
-                h[c * 8 + 1] / h[c * 8], h[c * 8 + 2] / h[c * 8], h[c * 8 + 3] / h[c * 8],
-                h[c * 8 + 4] / h[c * 8], (double)h[c * 8 + 5] / h[c * 8], h[c * 8 + 6] / h[c * 8],
-                (double)h[c * 8 + 7] / h[c * 8]);
-  }
-#else
-  roi_bwd_gather3_kernel<<<grid, B3_THREADS, smem, stream>>>(ba, bucket_rec, bucket, bucket_cnt,
-                                                            tile_cnt, R, tab, gt);
-#endif
+  roi_bwd_gather5_kernel<<<grid, B5_THREADS, B5_RING_BYTES, stream>>>(
+      ba, (const int32_t*)(ws + w.tile_r), (const RoiBwdRec*)(ws + w.tile_rec), tile_cnt,
+      bucket_rec, bucket, bucket_cnt, R, tab, gt);
   g_launch_count_add(1);
   BRCNN_CUDA_CHECK_LAST();
   return BRCNN_OK;

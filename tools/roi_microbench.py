@@ -4,7 +4,6 @@ captured alone in a CUDA graph, L2 flushed before every repetition.
 
   python tools/roi_microbench.py --cfg utdac --batch 16            # configs[1] RoIs (256 / img)
   python tools/roi_microbench.py --cfg coco --batch 2 --train      # configs[2] RoIs (512 / img)
-  BRCNN_ROI_BWD=v2 python tools/roi_microbench.py ...              # previous gather kernel
 
 Prints one JSON line; `union_bytes` is the number of distinct feature bytes the RoIs touch
 (bitmap union of the footprints per (image, level)), `algo_*` = output bytes + union bytes."""
@@ -80,7 +79,7 @@ def main():
     if args.dump_rois:
         np.save(args.dump_rois, rois.cpu().numpy())
     out = {'cfg': args.cfg, 'batch': B, 'rois': int(R), 'live': int((rois[:, 0] >= 0).sum()),
-           'bwd_env': os.environ.get('BRCNN_ROI_BWD', 'default')}
+           }
     with torch.no_grad():
         for name, cl in (('fwd_nchw', False), ('fwd_hwc', True)):
             out[name + '_ms'] = graph_time(
