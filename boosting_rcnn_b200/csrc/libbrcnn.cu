@@ -359,6 +359,44 @@ static int rcnn_ws(const brcnn_rcnn_params* p, RcnnWsInternal* w) {
 
 using namespace brcnn;
 
+// clusters of CS rpn_nms_image_kernel CTAs that can be resident at once on this device
+// (cudaOccupancyMaxActiveClusters; cached per cluster size, shared-memory size and device)
+template <int CS>
+static int rpn_nms_max_clusters(int L, int max_out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, int> cache;
+  const RpnNmsImageSmem lay = rpn_nms_image_smem(L, max_out, CS);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find({dev, lay.total});
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  if (lay.total <= 160 * 1024) {
+    if (lay.total > 32 * 1024 &&
+        ensure_dyn_smem((const void*)rpn_nms_image_kernel<CS>, lay.total) != cudaSuccess)
+      n = 0;
+    else {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(CS * 64);
+      cfg.blockDim = dim3(RNI_THREADS);
+      cfg.dynamicSmemBytes = (size_t)lay.total;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&n, rpn_nms_image_kernel<CS>, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        n = 0;
+      }
+    }
+  }
+  cache[{dev, lay.total}] = n;
+  return n;
+}
+
 extern "C" {
 
 const char* brcnn_version(void) { return "libbrcnn 0.1 sm_100a"; }
@@ -477,7 +515,22 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
       if (e && e[0] == 'i' && strchr(e, '1')) return 1;     // single CTA per image
       return 2;                                             // cluster
     }();
-    const int cs = (mode == 2) ? RNI_CLUSTER : 1;
+    // Cluster size: 8 CTAs per image unless the batch's clusters would not be co-resident (a
+    // 512-thread, 123-register CTA fills an SM and a cluster must sit inside one GPC: B200 holds
+    // fewer than 16 clusters of 8 at once, so batch 16 ran as two waves = twice the latency);
+    // then 4 CTAs per image, all resident.
+    int cs = 1;
+    if (mode == 2) {
+      cs = RNI_CLUSTER;
+      if (p->batch > rpn_nms_max_clusters<RNI_CLUSTER>(p->num_levels, p->max_per_img) &&
+          p->batch <= rpn_nms_max_clusters<4>(p->num_levels, p->max_per_img))
+        cs = 4;
+      static const int forced_cs = [] {
+        const char* e = getenv("BRCNN_RNI_CS");       // developer knob: 1 | 2 | 4 | 8
+        return e ? atoi(e) : 0;
+      }();
+      if (forced_cs == 1 || forced_cs == 2 || forced_cs == 4 || forced_cs == 8) cs = forced_cs;
+    }
     const RpnNmsImageSmem lay = rpn_nms_image_smem(p->num_levels, p->max_per_img, cs);
     if (mode != 0 && lay.total <= 160 * 1024 && lay.kp <= 65535) {
       cudaLaunchConfig_t cfg;
@@ -506,29 +559,24 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
 #else
       long long* dbg = nullptr;
 #endif
-      if (cs > 1) {
-        if (lay.total > 32 * 1024) {
-          e = ensure_dyn_smem((const void*)rpn_nms_image_kernel<RNI_CLUSTER>, lay.total);
-          if (e != cudaSuccess) return (int)e;
-        }
-        e = cudaLaunchKernelEx(&cfg, rpn_nms_image_kernel<RNI_CLUSTER>,
-                               (const float4*)cand_boxes, (const u64*)cand_key,
-                               (const uint8_t*)cand_valid, (const int32_t*)cand_count,
-                               (int)p->num_levels, (int)d.Kc, p->iou_threshold, maxc_f,
-                               (int)p->max_per_img, proposals, num_proposals, lay, dbg,
-                               (const int32_t*)nullptr, 0.0f, (int64_t*)nullptr);
-      } else {
-        if (lay.total > 32 * 1024) {
-          e = ensure_dyn_smem((const void*)rpn_nms_image_kernel<1>, lay.total);
-          if (e != cudaSuccess) return (int)e;
-        }
-        e = cudaLaunchKernelEx(&cfg, rpn_nms_image_kernel<1>,
-                               (const float4*)cand_boxes, (const u64*)cand_key,
-                               (const uint8_t*)cand_valid, (const int32_t*)cand_count,
-                               (int)p->num_levels, (int)d.Kc, p->iou_threshold, maxc_f,
-                               (int)p->max_per_img, proposals, num_proposals, lay, dbg,
-                               (const int32_t*)nullptr, 0.0f, (int64_t*)nullptr);
-      }
+#define BRCNN_LAUNCH_RNI(CSV)                                                                     \
+      do {                                                                                        \
+        if (lay.total > 32 * 1024) {                                                              \
+          e = ensure_dyn_smem((const void*)rpn_nms_image_kernel<CSV>, lay.total);                 \
+          if (e != cudaSuccess) return (int)e;                                                    \
+        }                                                                                         \
+        e = cudaLaunchKernelEx(&cfg, rpn_nms_image_kernel<CSV>, (const float4*)cand_boxes,        \
+                               (const u64*)cand_key, (const uint8_t*)cand_valid,                  \
+                               (const int32_t*)cand_count, (int)p->num_levels, (int)d.Kc,         \
+                               p->iou_threshold, maxc_f, (int)p->max_per_img, proposals,          \
+                               num_proposals, lay, dbg, (const int32_t*)nullptr, 0.0f,            \
+                               (int64_t*)nullptr);                                                \
+      } while (0)
+      if (cs == RNI_CLUSTER) BRCNN_LAUNCH_RNI(RNI_CLUSTER);
+      else if (cs == 4) BRCNN_LAUNCH_RNI(4);
+      else if (cs == 2) BRCNN_LAUNCH_RNI(2);
+      else BRCNN_LAUNCH_RNI(1);
+#undef BRCNN_LAUNCH_RNI
       if (e != cudaSuccess) return (int)e;
 #ifdef BRCNN_DEBUG_TIMING
       if (dbg != nullptr) {
@@ -536,7 +584,8 @@ int brcnn_rpn_get_bboxes(const brcnn_rpn_params* p,
         cudaStreamSynchronize(stream);
         cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[rpn_nms_image cs=%d] rounds=%lld cycles: windows=%lld rank=%lld pull+diag=%lld "
-                "combine=%lld resolve=%lld\n", cs, h[5], h[0], h[1], h[2], h[3], h[4]);
+                "combine=%lld resolve=%lld | prologue=%lld total=%lld\n", cs, h[5], h[0], h[1], h[2],
+                h[3], h[4], h[7], h[6]);
       }
 #endif
       g_launch_count_add(1);

@@ -92,6 +92,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
   __shared__ int s_nkept;                    // GLOBAL kept count (same in every CTA)
   __shared__ int s_lkept;                    // LOCAL kept count (all levels)
 
+  const long long t_entry = dbg != nullptr ? clock64() : 0;
   const int crank = (CS > 1) ? (int)cg::this_cluster().block_rank() : 0;
   const int b = blockIdx.x / CS;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -124,7 +125,7 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
   long long t_prev = 0, t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int n_rounds = 0;
 #define RNI_MARK(i) do { if (dbg != nullptr && tid == 0) { const long long t_now = clock64(); t_acc[i] += t_now - t_prev; t_prev = t_now; } } while (0)
-  if (dbg != nullptr && tid == 0) t_prev = clock64();
+  if (dbg != nullptr && tid == 0) { t_prev = clock64(); t_acc[7] = t_prev - t_entry; }
   for (int round = 0;; ++round) {
     ++n_rounds;
     // ---- 1. windows: registers -> smem ----
@@ -348,6 +349,8 @@ rpn_nms_image_kernel(const float4* __restrict__ cand_boxes, const u64* __restric
   if (dbg != nullptr && tid == 0 && blockIdx.x == 0) {
     for (int i = 0; i < 5; ++i) dbg[i] = t_acc[i];
     dbg[5] = n_rounds;
+    dbg[6] = clock64() - t_entry;     // kernel entry -> here (CTA 0)
+    dbg[7] = t_acc[7];                // prologue
   }
   // nobody leaves while a peer may still read its hit masks
   if (CS > 1) cg::this_cluster().sync();
