@@ -274,6 +274,7 @@ roi_bwd_gather5_kernel(const __grid_constant__ RoiBwd3Args ba,
           const uint32_t cq = (uint32_t)(C >> 2);
           // B5_NSLOT - 1 trailing copies of the last step: the prefetch below never needs a
           // bounds test (the copies land in slots nobody reads any more)
+          __syncwarp();                      // the last step was written by another lane
           if (total > 0 && lane < B5_NSLOT - 1) s_steps[wid][total + lane] = s_steps[wid][total - 1];
           __syncwarp();
           // ---- walk: private cp.async ring, B5_NSLOT - 1 steps in flight ----
