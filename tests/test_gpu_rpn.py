@@ -175,7 +175,8 @@ def test_rpn_determinism(cuda):
 
 def test_rpn_image_kernel_equals_segment_path(cuda):
     """BRCNN_RPN_NMS=segments (per-level NMS to completion + merge) vs image1 (one CTA
-    per image, global score order, early stop) vs the default 8-CTA cluster version:
+    per image, global score order, early stop) vs the cluster version with 8, 4 and 2 CTAs per
+    image (the launcher drops to 4 when a batch's 8-CTA clusters cannot all be resident):
     identical proposals."""
     import os
     import subprocess
@@ -203,10 +204,13 @@ np.save(sys.argv[1], np.concatenate(res))
 ''' % (os.path.dirname(here), here)
     outs = []
     with tempfile.TemporaryDirectory() as d:
-        for mode in ('segments', 'image1', 'cluster'):
-            path = os.path.join(d, mode + '.npy')
-            subprocess.run([sys.executable, '-c', code, path], check=True,
-                           env=dict(os.environ, BRCNN_RPN_NMS=mode))
+        for mode, cs in (('segments', ''), ('image1', ''), ('cluster', '8'), ('cluster', '4'),
+                         ('cluster', '2')):
+            path = os.path.join(d, mode + cs + '.npy')
+            env = dict(os.environ, BRCNN_RPN_NMS=mode)
+            if cs:
+                env['BRCNN_RNI_CS'] = cs
+            subprocess.run([sys.executable, '-c', code, path], check=True, env=env)
             outs.append(np.load(path))
-    np.testing.assert_array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
-    np.testing.assert_array_equal(outs[0].view(np.uint32), outs[2].view(np.uint32))
+    for o in outs[1:]:
+        np.testing.assert_array_equal(outs[0].view(np.uint32), o.view(np.uint32))
