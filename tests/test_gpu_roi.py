@@ -245,7 +245,7 @@ def test_roi_backward_channel_slabs_and_long_lists(cuda, C, n):
 
 # ---------------------------------------------------------------------------
 # (R,7,7,C) feature hand-off: persistent forward kernel (roi_align_fwd3.cuh) and the
-# TMA-staged backward gather reading bin-major gradients (roi_align_bwd3.cuh)
+# backward gather reading bin-major gradients (roi_align_bwd5.cuh)
 # ---------------------------------------------------------------------------
 @pytest.mark.parametrize('pad_hw,C,n,clustered', [
     ((256, 320), 64, 50, False), ((800, 1344), 256, 256, True), ((256, 320), 4, 30, False),
