@@ -137,6 +137,24 @@ def test_rpn_scores_clustered_on_histogram_bin_edges(cuda):
               max_per_img=300, iou_thr=0.7, seed=32, mutate=on_edges)
 
 
+def test_rpn_extreme_logits(cuda):
+    """Saturated and infinite logits: the approximate pre-selection score and the pinned score
+    must agree on 0 / 1 and on everything in between (exp overflow, denormal sigmoids)."""
+    def extreme(cls, iou):
+        rng = np.random.RandomState(91)
+        vals = np.array([np.inf, -np.inf, 95.0, -95.0, 88.5, -88.5, 40.0, -40.0, 17.0, -17.0],
+                        dtype=np.float32)
+        for c, u in zip(cls, iou):
+            m = rng.rand(*c.shape) < 0.03
+            c[m] = vals[rng.randint(0, len(vals), int(m.sum()))]
+            m = rng.rand(*u.shape) < 0.03
+            u[m] = vals[rng.randint(0, len(vals), int(m.sum()))]
+    _run_case(cuda, batch=2, pad_hw=(256, 320), img_hw=(250, 317), nms_pre=300,
+              max_per_img=100, iou_thr=0.7, seed=41, mutate=extreme)
+    _run_case(cuda, batch=1, pad_hw=(512, 640), img_hw=(500, 600), nms_pre=1000,
+              max_per_img=300, iou_thr=0.7, seed=42, mutate=extreme)
+
+
 def test_rpn_single_anchor_voc_like(cuda):
     _run_case(cuda, batch=2, pad_hw=(608, 1024), img_hw=(600, 1000), nms_pre=1000,
               max_per_img=256, iou_thr=0.7, seed=3, num_scales=1, ratios=(1.0,))
