@@ -200,3 +200,39 @@ def test_register_into_mmdet_against_a_stub_registry(monkeypatch):
     assert plugin.REGISTERED == ('ProbRoIHead', 'SingleRoIExtractor')
     assert set(heads.module_dict) == {'ProbRoIHead'}
     sys.modules.pop('boosting_rcnn_b200.mmdet_plugin', None)
+
+
+def test_two_phase_topk_selection_is_a_superset():
+    """The RPN top-k pre-selects on an APPROXIMATE score (|error| <= eps << 1/2048) and ranks the
+    survivors on the pinned one (csrc/rpn.cuh: rpn_score_kernel / rpn_collect_kernel).  Model of
+    that rule in numpy: with d = the 1/2048-wide value bin holding the k-th best approximate
+    score, the elements whose approximate score lies in a bin >= d - 1 must contain the exact
+    top-k (ties included) for ANY perturbation within eps — random, adversarial around the
+    threshold, and with the scores piled onto bin edges."""
+    rng = np.random.RandomState(5)
+    eps = 2e-5
+    for trial in range(60):
+        n = int(rng.choice([500, 3000, 40000]))
+        k = int(rng.choice([1, 100, 300, n - 1]))
+        mode = trial % 3
+        if mode == 0:
+            s = rng.rand(n)
+        elif mode == 1:        # piled onto bin edges
+            s = rng.randint(0, 2049, n) / 2048.0 + rng.randint(-3, 4, n) * 6e-8
+        else:                  # narrow spread around one edge
+            s = 0.5 + rng.randn(n) * 3e-5
+        s = np.clip(s, 0.0, 1.0).astype(np.float64)
+        if trial % 2:          # adversarial: push the true top-k down, everything else up
+            thr = np.sort(s)[::-1][k - 1]
+            noise = np.where(s >= thr, -eps, eps)
+        else:
+            noise = rng.uniform(-eps, eps, n)
+        sa = np.clip(s + noise, 0.0, None)
+        bins = np.minimum((sa * 2048).astype(np.int64), 2047)
+        hist = np.bincount(bins, minlength=2048)
+        ge = np.cumsum(hist[::-1])[::-1]                   # count(bin >= d)
+        d = int(np.max(np.nonzero(ge >= k)[0]))            # #(bins > d) < k <= #(bins >= d)
+        assert (ge[d + 1] if d + 1 < 2048 else 0) < k <= ge[d]
+        picked = bins >= max(d - 1, 0)
+        kth = np.sort(s)[::-1][k - 1]
+        assert picked[s >= kth].all(), (trial, n, k, d)
