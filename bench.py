@@ -604,14 +604,26 @@ def bench_stress(args, rank, world, local_rank):
         d_sc = [torch.from_numpy(x).to(dev) for x in sc]
         d_lv = [torch.from_numpy(x).to(dev) for x in lv]
 
+        # mmcv batched_nms per image, ids = pyramid level (no host sync).  The images are
+        # independent: one stream each, so the per-image cluster kernels (8 SMs each) run side by
+        # side instead of one after the other (forked from / joined to the calling stream, which
+        # is also how the calls are captured into the step's CUDA graph)
+        side = [torch.cuda.Stream(device=dev) for _ in range(B)]
+
         @torch.no_grad()
         def proposals():
+            cur = torch.cuda.current_stream()
             boxes = torch.zeros((B, M, 5), dtype=torch.float32, device=dev)
-            nums = []
-            for b in range(B):   # mmcv batched_nms per image, ids = pyramid level (no host sync)
-                dets, _, num = ops._nms_raw(d_bx[b], d_sc[b], d_lv[b], 0.7, 0, num_ids=5, max_num=M)
-                boxes[b] = dets[:M]
-                nums.append(num)
+            nums = [None] * B
+            for b in range(B):
+                side[b].wait_stream(cur)
+                with torch.cuda.stream(side[b]):
+                    dets, _, num = ops._nms_raw(d_bx[b], d_sc[b], d_lv[b], 0.7, 0, num_ids=5,
+                                                max_num=M)
+                    boxes[b] = dets[:M]
+                    nums[b] = num
+            for st in side:
+                cur.wait_stream(st)
             return boxes, torch.cat(nums).clamp_(max=M)
 
     @torch.no_grad()
