@@ -149,9 +149,11 @@ nms_rank_scatter_kernel(const float* __restrict__ boxes,
 constexpr int NMS_RANK_JSPLIT = 2048;   // boxes j per CTA row
 __global__ void __launch_bounds__(256)
 nms_id_rank_count_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idxs, int K,
-                         int32_t* __restrict__ lt_out, int32_t* __restrict__ rank_out) {
+                         int32_t* __restrict__ lt_out, int32_t* __restrict__ rank_out,
+                         const int32_t* __restrict__ gate) {
   __shared__ u64 t_key[256];
   __shared__ int t_id[256];
+  if (gate != nullptr && *gate == 0) return;     // the fast id sort already did the job
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   u64 mine = 0;
   int my_id = 0;
@@ -185,9 +187,11 @@ nms_id_scatter_kernel(const float* __restrict__ boxes, const float* __restrict__
                       const int64_t* __restrict__ idxs, int K, int num_ids,
                       const int32_t* __restrict__ lt_in, const int32_t* __restrict__ rank_in,
                       float4* __restrict__ sorted_boxes, u64* __restrict__ sorted_key,
-                      int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_count) {
+                      int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_count,
+                      const int32_t* __restrict__ gate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K) return;
+  if (gate != nullptr && *gate == 0) return;     // the fast id sort already did the job
   const int my_id = idxs != nullptr ? (int)idxs[i] : 0;
   if (my_id < 0 || my_id >= num_ids) return;
   const int lt = lt_in[i], rank = rank_in[i];
@@ -195,7 +199,84 @@ nms_id_scatter_kernel(const float* __restrict__ boxes, const float* __restrict__
   sorted_boxes[pos] = reinterpret_cast<const float4*>(boxes)[i];
   sorted_key[pos] = ((u64)ordered_bits(scores[i]) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)i);
   if (rank == 0) seg_start[my_id] = lt;     // the best box of the id
-  atomicAdd(seg_count + my_id, 1);
+  if (gate == nullptr) atomicAdd(seg_count + my_id, 1);   // (gated: counted by nms_id_count_kernel)
+}
+
+// Fast form of the same sort when every id's list fits one CTA's shared memory: the ids are
+// counted (nms_id_count_kernel), then one CTA per id gathers its boxes' keys, sorts them with the
+// shared-memory bitonic network and writes its segment at the prefix sum of the counts.  An id
+// with more than NMS_IDSORT_CAP boxes raises `overflow`; the counting kernels above then redo
+// the whole sort (they return at once when the flag is clear).  K = 20 000 / 5 ids: 183 us of
+// rank counting -> ~20 us.
+constexpr int NMS_IDSORT_CAP = 8192;
+__global__ void __launch_bounds__(256)
+nms_id_count_kernel(const int64_t* __restrict__ idxs, int K, int num_ids,
+                    int32_t* __restrict__ seg_count) {
+  extern __shared__ int s_hist[];
+  for (int i = threadIdx.x; i < num_ids; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
+    const int id = (int)idxs[i];
+    if (id >= 0 && id < num_ids) atomicAdd(&s_hist[id], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < num_ids; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(seg_count + i, s_hist[i]);
+}
+// grid num_ids, block 1024, dynamic smem NMS_IDSORT_CAP * 8
+__global__ void __launch_bounds__(1024)
+nms_id_sort_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                   const int64_t* __restrict__ idxs, int K, int num_ids,
+                   const int32_t* __restrict__ seg_count, int32_t* __restrict__ seg_start,
+                   float4* __restrict__ sorted_boxes, u64* __restrict__ sorted_key,
+                   int32_t* __restrict__ overflow) {
+  extern __shared__ __align__(16) u64 s_keys[];
+  __shared__ int s_part[32];
+  __shared__ int s_n;
+  const int id = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // start of this id's segment: sum of the counts of the smaller ids
+  int part = 0;
+  for (int j = tid; j < id; j += blockDim.x) part += seg_count[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) s_part[wid] = part;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  int start = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) start += s_part[w];
+  const int n = seg_count[id];
+  if (tid == 0) seg_start[id] = start;
+  if (n == 0) return;
+  if (n > NMS_IDSORT_CAP) {
+    if (tid == 0) atomicExch(overflow, 1);
+    return;
+  }
+  // gather (arbitrary order: sorted next), warp-aggregated slots
+  for (int i0 = 0; i0 < K; i0 += blockDim.x) {
+    const int i = i0 + tid;
+    const bool mine = i < K && (int)idxs[i] == id;
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    if (m) {
+      int base = 0;
+      const int leader = __ffs(m) - 1;
+      if (lane == leader) base = atomicAdd(&s_n, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (mine)
+        s_keys[base + __popc(m & ((1u << lane) - 1u))] =
+            ((u64)ordered_bits(scores[i]) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)i);
+    }
+  }
+  __syncthreads();
+  int np = 1;
+  while (np < n) np <<= 1;
+  for (int i = n + tid; i < np; i += blockDim.x) s_keys[i] = 0ull;
+  bitonic_sort_desc_u64(s_keys, np);
+  for (int r = tid; r < n; r += blockDim.x) {
+    const u64 key = s_keys[r];
+    const uint32_t src = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+    sorted_key[start + r] = key;
+    sorted_boxes[start + r] = reinterpret_cast<const float4*>(boxes)[src];
+  }
 }
 
 __global__ void nms_finalize_kernel(const float* __restrict__ boxes,
@@ -779,18 +860,41 @@ struct OpMergeEpilogue {
 // (id asc, score desc, index asc) counting sort; lt / rank scratch = order + kept_pos arrays
 static int launch_id_sort(const float* boxes, const float* scores, const int64_t* idxs, int K,
                           int num_ids, int32_t* lt, int32_t* rank, float4* sboxes, u64* skey,
-                          int32_t* seg_start, int32_t* seg_count, cudaStream_t stream) {
+                          int32_t* seg_start, int32_t* seg_count, int32_t* gate,
+                          cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(lt, 0, (size_t)K * 4, stream);
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(rank, 0, (size_t)K * 4, stream);
   if (e != cudaSuccess) return (int)e;
+  // fast path: count the ids, one sorting CTA per id (seg_count must be zero on entry); the
+  // rank-counting kernels below only run when an id's list overflowed a CTA's shared memory
+  // (below ~8k boxes the K x K counting costs less than the two extra launches)
+  const bool fast = idxs != nullptr && gate != nullptr && num_ids >= 1 && num_ids <= NMS_MAX_IDS &&
+                    K >= 8192;
+  if (fast) {
+    e = cudaMemsetAsync(gate, 0, 4, stream);
+    if (e != cudaSuccess) return (int)e;
+    int cb = (K + 256 * 8 - 1) / (256 * 8);
+    if (cb > 2 * sm_count()) cb = 2 * sm_count();
+    nms_id_count_kernel<<<cb, 256, (size_t)num_ids * 4, stream>>>(idxs, K, num_ids, seg_count);
+    g_launch_count_add(1);
+    BRCNN_CUDA_CHECK_LAST();
+    const size_t sm = (size_t)NMS_IDSORT_CAP * 8;
+    e = ensure_dyn_smem((const void*)nms_id_sort_kernel, sm);
+    if (e != cudaSuccess) return (int)e;
+    nms_id_sort_kernel<<<num_ids, 1024, sm, stream>>>(boxes, scores, idxs, K, num_ids, seg_count,
+                                                      seg_start, sboxes, skey, gate);
+    g_launch_count_add(1);
+    BRCNN_CUDA_CHECK_LAST();
+  }
   dim3 grid((K + 255) / 256, (K + NMS_RANK_JSPLIT - 1) / NMS_RANK_JSPLIT);
-  nms_id_rank_count_kernel<<<grid, 256, 0, stream>>>(scores, idxs, K, lt, rank);
+  nms_id_rank_count_kernel<<<grid, 256, 0, stream>>>(scores, idxs, K, lt, rank,
+                                                    fast ? gate : nullptr);
   g_launch_count_add(1);
   BRCNN_CUDA_CHECK_LAST();
   nms_id_scatter_kernel<<<(K + 255) / 256, 256, 0, stream>>>(boxes, scores, idxs, K, num_ids, lt,
                                                             rank, sboxes, skey, seg_start,
-                                                            seg_count);
+                                                            seg_count, fast ? gate : nullptr);
   g_launch_count_add(1);
   BRCNN_CUDA_CHECK_LAST();
   return BRCNN_OK;
@@ -850,7 +954,7 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
       cudaError_t e = cudaMemsetAsync(seg_start, 0, 2 * BRCNN_MAX_LEVELS * 4, stream);
       if (e != cudaSuccess) return (int)e;
       const int rcs = launch_id_sort(boxes, scores, idxs, K, L, order, kept_pos, sboxes, skey,
-                                     seg_start, seg_count, stream);
+                                     seg_start, seg_count, (int32_t*)(ws + w.count) + 1, stream);
       if (rcs) return rcs;
       if (lay.total > 32 * 1024) {
         e = ensure_dyn_smem((const void*)rpn_nms_image_kernel<RNI_CLUSTER>, lay.total);
@@ -908,7 +1012,7 @@ int brcnn_batched_nms(const float* boxes, const float* scores, const int64_t* id
       if (e != cudaSuccess) return (int)e;
       const int rcs = launch_id_sort(boxes, scores, idxs, K, num_ids, order,
                                      (int32_t*)(ws + w.mask), sboxes, skey, seg_start, seg_count,
-                                     stream);
+                                     (int32_t*)(ws + w.count) + 1, stream);
       if (rcs) return rcs;
       const size_t smem = (size_t)keep_pad * 20;
       if (smem > 48 * 1024) {

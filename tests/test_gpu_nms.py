@@ -137,16 +137,19 @@ def test_batched_nms_coco_scale_many_ids(cuda, n, nid, clustered):
         np.testing.assert_array_equal(dets.cpu().numpy()[:, 4], scores[ref])
 
 
-def test_batched_nms_one_id_with_more_keeps_than_shared_memory(cuda):
-    """One id keeps > 8192 boxes (its kept list spills from shared to global memory inside the
-    per-id kernel); ids > 8 so that the per-id path is taken."""
+@pytest.mark.parametrize('nid', [12, 4])
+def test_batched_nms_one_id_with_more_keeps_than_shared_memory(cuda, nid):
+    """One id holds 9000 boxes and keeps them all: its list overflows the per-id sorting CTA
+    (> 8192: the operator falls back to the rank-counting sort) and, with more than 8 ids (the
+    per-id NMS path), its kept list spills from shared to global memory inside the kernel; with
+    4 ids the clustered walk is taken."""
     rng = np.random.RandomState(3)
     n0 = 9000                     # a 100 x 90 lattice of disjoint 6x6 boxes: all kept
     gx, gy = np.meshgrid(np.arange(100) * 10.0, np.arange(90) * 8.0)
     b0 = np.stack([gx.ravel(), gy.ravel(), gx.ravel() + 6, gy.ravel() + 6], 1)
     b1 = synth.random_boxes(3000, 800, 1333, seed=11, clustered=True)
     boxes = np.concatenate([b0, b1]).astype(np.float32)
-    ids = np.concatenate([np.zeros(n0), rng.randint(1, 12, 3000)]).astype(np.int64)
+    ids = np.concatenate([np.zeros(n0), rng.randint(1, nid, 3000)]).astype(np.int64)
     scores = rng.permutation(len(boxes)).astype(np.float32) / len(boxes)
     t = lambda a: torch.from_numpy(a).to(cuda)
     dets, keep = ops.batched_nms(t(boxes), t(scores), t(ids), dict(type='nms', iou_threshold=0.5))
