@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument('--strong-total', type=int, default=16,
                     help='images of the strong-scaling sub-record (sharded over the GPUs)')
     ap.add_argument('--no-graph', action='store_true', help='launch kernels one by one')
+    ap.add_argument('--train-eager', action='store_true',
+                    help='training record without the captured R-CNN half (RcnnTrainGraph)')
     ap.add_argument('--rpn-max-per-img', type=int, default=0,
                     help='override test_cfg.rpn.max_per_img (BASELINE configs[3]: VOC at 1000)')
     return ap.parse_args()
@@ -375,10 +377,14 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
             f.grad = None
         # RPN loss on the head outputs (anchor targets, focal / IoU / MSE / BCE, gradients): its
         # two reduce_mean normalisers are one fused device-side all-reduce inside ops.rpn_loss
-        rpn_losses = rpn_head.loss(cls, box, iou, gts, metas)
+        # Order: proposals and the R-CNN assignment are launched first, the RPN loss is queued
+        # behind them, and only then does the host wait (an event) for the two candidate
+        # counts the reference's CPU randperm needs: the GPU works on the RPN loss meanwhile.
         with torch.no_grad():   # padded proposals stay on the device (no sync)
             plist = rpn_head.get_bboxes_padded(cls, box, iou, metas, cfg=prop_cfg)
-        losses = roi_head.forward_train(feats, metas, plist, gts, labels)
+        pending = roi_head.assign_async(plist, gts, labels)
+        rpn_losses = rpn_head.loss(cls, box, iou, gts, metas)
+        losses = roi_head.forward_train(feats, metas, plist, gts, labels, assigned=pending)
         total = losses['loss_cls'] + losses['loss_bbox']
         for v in rpn_losses.values():
             total = total + torch.stack(v).sum()
@@ -402,9 +408,34 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
         else:
             scal.update({k: v.detach() for k, v in losses.items()})
 
+    # the captured R-CNN half must reproduce the eager one bit for bit (same kernels, same
+    # CPU RNG stream): one step each way from the same seed, losses and every gradient compared
+    graph_check = None
+    roi_head.train_graph = False
+    if not getattr(args, 'train_eager', False):
+        def snapshot():
+            torch.cuda.synchronize()
+            return ([p.grad.clone() for p in params] + [f.grad.clone() for f in feats + cls + box + iou]
+                    + [scal[k].clone() for k in sorted(scal)])
+        torch.manual_seed(1234)
+        step(False)
+        ref = snapshot()
+        roi_head.train_graph = True
+        torch.manual_seed(1234)
+        step(False)
+        got = snapshot()
+        captured = any(bool(g) for g in roi_head._train_graphs.values())
+        graph_check = {'captured': captured,
+                       'bit_identical_to_eager': all(torch.equal(a, b) for a, b in zip(ref, got))}
+        if not captured:
+            roi_head.train_graph = False
+        del ref, got
+    graphs = [g for g in roi_head._train_graphs.values() if g]
     l0 = lib.brcnn_launch_count()
     ms = _timed_steps(step, K, W, world, dist, dev)
     launches = (lib.brcnn_launch_count() - l0) * K // (K + W)
+    if graphs:   # kernels inside the replayed graphs are not seen by the launch counter
+        launches += graphs[0].launches_per_step * K
     ms_comm = 0.0
     if comm_events:
         torch.cuda.synchronize()
@@ -452,7 +483,12 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
                         'NCCL all-reduce of the head gradients (one flat fp32 bucket) + one fused '
                         'scalar all-reduce of the logged losses'),
         'gpu_launches_per_step': int(launches // max(K, 1)),
-        'launch_mode': 'eager (one host sync per step: the reference\'s CPU randperm)',
+        'launch_mode': ('RPN loss / proposals / R-CNN assignment eager, then one event wait for '
+                        'the reference\'s CPU randperm, then the R-CNN half (sample + targets, '
+                        'RoIAlign, 2-fc head, boost loss, backward) as two CUDA-graph replays'
+                        if graphs else
+                        'eager (one event wait per step: the reference\'s CPU randperm)'),
+        'train_graph_check': graph_check,
         'losses': {k: float(v) for k, v in scal.items()},
     }
     if with_stages:
@@ -527,7 +563,8 @@ def bench_train(args, rank, world, local_rank):
             'roofline': rec.get('roofline'), 'stages_ms': rec.get('stages_ms'),
             'ms_allreduce': rec['ms_allreduce'], 'ms_per_step_no_comm': rec['ms_per_step_no_comm'],
             'ms_allreduce_collective_only': rec.get('ms_allreduce_collective_only'),
-            'losses': rec['losses'],
+            'losses': rec['losses'], 'launch_mode': rec['launch_mode'],
+            'train_graph_check': rec['train_graph_check'],
         }
         print(json.dumps(out))
     if dist:

@@ -249,4 +249,6 @@ class ProbConvFCBBoxHead(nn.Module):
             cls_score, bbox_pred, labels, label_weights, prior, bbox_targets, bbox_weights,
             self.num_classes, self.reg_class_agnostic, gamma, alpha,
             self.loss_cls.loss_weight, self.loss_bbox.loss_weight, reg_norm == 'mean')
-        return dict(loss_cls=loss_cls, acc=acc, loss_bbox=loss_bbox)
+        # acc is a view of the kernel's scalar block: detached, so that it does not inherit
+        # requires_grad from its (differentiable) base
+        return dict(loss_cls=loss_cls, acc=acc.detach(), loss_bbox=loss_bbox)

@@ -12,9 +12,12 @@ counters), so it captures into one CUDA graph:
 copy stream so that the H2D of step i+1 overlaps the compute of step i; this
 is the end-to-end entry point for callers whose inputs live in host memory.
 """
-import torch
+import warnings
 
-from . import _lib
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
 from .registry import ConfigDict
 
 
@@ -158,3 +161,116 @@ class HostPipeline:
             if s['busy']:
                 s['done'].synchronize()
                 s['busy'] = False
+
+
+class _RcnnTrainBody(nn.Module):
+    """The sync-free tail of ``ProbRoIHead.forward_train`` on static inputs: sample + targets
+    + prior (one launch) -> RoI extraction -> 2-fc head -> boost loss."""
+
+    def __init__(self, roi_head, static, num_rows):
+        super().__init__()
+        self.roi_head = roi_head          # its parameters are this module's parameters
+        self.static, self.num_rows = static, num_rows
+
+    def forward(self, *feats):
+        st, rh = self.static, self.roi_head
+        h = rh.bbox_head
+        rois, labels, label_weights, bbox_targets, bbox_weights, prior = ops.rcnn_sample_targets(
+            st['proposals'], st['num_props'], st['gtb'], st['gtl'], st['num_gt'], st['gt_inds'],
+            st['plan'], st['perm_pos'], st['perm_neg'], self.num_rows, h.num_classes,
+            h.bbox_coder.means, h.bbox_coder.stds, rh.train_cfg.pos_weight)
+        res = rh._bbox_forward(feats, rois)
+        out = h.boost_loss(res['cls_score'], res['bbox_pred'], labels, label_weights,
+                           bbox_targets, bbox_weights, prior, rh.gamma, rh.alpha, rh.reg_norm)
+        return out['loss_cls'], out['loss_bbox'], out['acc']
+
+
+class RcnnTrainGraph:
+    """CUDA-graph replay of the R-CNN half of the training step (prob_roi_head.py:66-149 after
+    the sampler's CPU ``randperm``): forward and backward are one graph each
+    (``torch.cuda.make_graphed_callables``), so the ~45 eager launches of sample/targets,
+    layout hand-off, RoIAlign, the 2-fc head, the boost loss and their backward become two
+    replays.  The result is an ordinary autograd node: ``loss.backward()`` of the caller
+    replays the backward graph, accumulates the head's parameter gradients and hands the
+    gradients of the FPN maps on to the neck.
+
+    Static shapes: a graph is keyed by (rows N, proposal capacity, GT capacity, feature-map
+    shapes); ``ProbRoIHead`` pads the GT tensors to a multiple of 32 in this mode.  Any other
+    combination builds another graph (or, if capture fails, the eager path runs).  Enabled
+    with ``roi_head.train_graph = True``."""
+
+    _NAMES = ('proposals', 'num_props', 'gtb', 'gtl', 'num_gt', 'gt_inds')
+
+    def __init__(self, roi_head, feats, assigned, plan, perm_pos, perm_neg, num_rows):
+        dev = assigned.proposals.device
+        self.static = {k: getattr(assigned, k).clone() for k in self._NAMES}
+        B, cap = perm_pos.shape
+        # plan + both permutations cross the bus as ONE pinned buffer
+        self._host = torch.empty((B * 5 + 2 * B * cap,), dtype=torch.int32).pin_memory()
+        self._dev = torch.empty_like(self._host, device=dev)
+        self._cuts = (B * 5, B * 5 + B * cap)
+        a, b = self._cuts
+        self.static.update(plan=self._dev[:a].view(B, 5), perm_pos=self._dev[a:b].view(B, cap),
+                           perm_neg=self._dev[b:].view(B, cap))
+        self._fill(assigned, plan, perm_pos, perm_neg, first=True)
+        self.body = _RcnnTrainBody(roi_head, self.static, int(num_rows))
+        # An autograd graph of an earlier eager step that is still alive (kept by a reference
+        # cycle somewhere in the caller) pins the parameters' AccumulateGrad nodes to the
+        # stream that step ran on; autograd would then synchronise the capturing stream with
+        # it — illegal for the default stream, the capture is invalidated.  Collect first.
+        import gc
+        gc.collect()
+        lib = _lib.load()
+        l0 = lib.brcnn_launch_count()
+        torch.cuda.make_graphed_callables(self.body, tuple(feats), num_warmup_iters=3,
+                                          allow_unused_input=True)
+        # kernels of the library inside one forward + backward replay (3 warm-up passes + 1
+        # capture were recorded)
+        self.launches_per_step = int(lib.brcnn_launch_count() - l0) // 4
+
+    def _fill(self, assigned, plan, perm_pos, perm_neg, first=False):
+        a, b = self._cuts
+        h = self._host
+        h[:a] = plan.reshape(-1)
+        h[a:b] = perm_pos.reshape(-1)
+        h[b:] = perm_neg.reshape(-1)
+        self._dev.copy_(h, non_blocking=True)
+        if not first:
+            torch._foreach_copy_([self.static[k] for k in self._NAMES],
+                                 [getattr(assigned, k) for k in self._NAMES])
+
+    @staticmethod
+    def _key(feats, assigned, perm_pos, num_rows):
+        return (int(num_rows), tuple(assigned.proposals.shape), int(assigned.gtb.size(1)),
+                tuple(perm_pos.shape), str(assigned.proposals.device),
+                tuple((tuple(f.shape), tuple(f.stride()), bool(f.requires_grad)) for f in feats))
+
+    @classmethod
+    def run(cls, roi_head, feats, assigned, plan, perm_pos, perm_neg, num_rows):
+        """Losses of this step through the graph matching its shapes (built on first use);
+        None when there is nothing to replay (no rows, capture failed): the caller then runs
+        the eager path."""
+        if num_rows <= 0 or not torch.is_grad_enabled():
+            return None
+        feats = tuple(feats[:roi_head.bbox_roi_extractor.num_inputs])
+        key = cls._key(feats, assigned, perm_pos, num_rows)
+        g = roi_head._train_graphs.get(key)
+        if g is False:
+            return None
+        if g is None:
+            try:
+                g = cls(roi_head, feats, assigned, plan, perm_pos, perm_neg, num_rows)
+            except Exception as e:  # noqa: BLE001 - capture is an optimisation, never fatal
+                warnings.warn(f'RcnnTrainGraph: capture failed ({type(e).__name__}: {e}); '
+                              f'the eager training path runs instead')
+                roi_head._train_graphs[key] = False
+                return None
+            roi_head._train_graphs[key] = g
+        else:
+            # the previous step's copies out of the pinned buffer must have left the host
+            g._copied.synchronize()
+            g._fill(assigned, plan, perm_pos, perm_neg)
+        g._copied = torch.cuda.Event()
+        g._copied.record()
+        loss_cls, loss_bbox, acc = g.body(*feats)
+        return dict(loss_cls=loss_cls, acc=acc, loss_bbox=loss_bbox)

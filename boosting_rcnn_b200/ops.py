@@ -77,11 +77,22 @@ def _first_cuda_tensor(args):
     return None
 
 
+def _check_same_device(xs, device, name):
+    for a in xs:
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda and a.device != device:
+                raise RuntimeError(f'{name}: tensors on {a.device} and {device}')
+        elif isinstance(a, (list, tuple)):
+            _check_same_device(a, device, name)
+
+
 def _device_guard(fn):
     """Run ``fn`` with the device of its first CUDA tensor argument current (like the mmcv ops'
     device guard): launches, cudaFuncSetAttribute and ``_stream()`` then refer to the GPU the
     tensors live on even when the caller never called ``torch.cuda.set_device``; all CUDA
-    tensor arguments must share that device."""
+    tensor arguments must share that device.  (No closures over the arguments: a recursive
+    local function would form a reference cycle that keeps the first tensor — and the
+    autograd graph behind it — alive until the cyclic GC runs.)"""
     import functools
 
     @functools.wraps(fn)
@@ -91,19 +102,13 @@ def _device_guard(fn):
             t = _first_cuda_tensor(tuple(kwargs.values()))
         if t is None:
             return fn(*args, **kwargs)
-
-        def check_same(xs):
-            for a in xs:
-                if isinstance(a, torch.Tensor):
-                    if a.is_cuda and a.device != t.device:
-                        raise RuntimeError(f'{fn.__name__}: tensors on {a.device} and {t.device}')
-                elif isinstance(a, (list, tuple)):
-                    check_same(a)
-        check_same(args)
-        check_same(tuple(kwargs.values()))
-        if t.device.index == torch.cuda.current_device():
+        dev = t.device
+        del t
+        _check_same_device(args, dev, fn.__name__)
+        _check_same_device(tuple(kwargs.values()), dev, fn.__name__)
+        if dev.index == torch.cuda.current_device():
             return fn(*args, **kwargs)
-        with torch.cuda.device(t.device):
+        with torch.cuda.device(dev):
             return fn(*args, **kwargs)
     return wrapper
 
@@ -686,14 +691,12 @@ def sample_plan(counts, num, pos_fraction, neg_pos_ub=-1):
     B = len(counts)
     n_exp_pos = int(num * pos_fraction)
     cap = max(1, num)
-    plan = torch.zeros((B, 5), dtype=torch.int32)
-    perm_pos = torch.zeros((B, cap), dtype=torch.int32)
-    perm_neg = torch.zeros((B, cap), dtype=torch.int32)
-    rows, base = [], 0
+    perms = torch.zeros((2, B, cap), dtype=torch.int32)
+    plan_rows, rows, base = [], [], 0
     for b in range(B):
         n_pos_c, n_neg_c = int(counts[b][0]), int(counts[b][1])
         if n_pos_c > n_exp_pos:
-            perm_pos[b, :n_exp_pos] = torch.randperm(n_pos_c)[:n_exp_pos].to(torch.int32)
+            perms[0, b, :n_exp_pos] = torch.randperm(n_pos_c)[:n_exp_pos]
             n_pos, use_p = n_exp_pos, 1
         else:
             n_pos, use_p = n_pos_c, 0
@@ -701,30 +704,47 @@ def sample_plan(counts, num, pos_fraction, neg_pos_ub=-1):
         if neg_pos_ub >= 0:
             n_exp_neg = min(n_exp_neg, int(neg_pos_ub * max(1, n_pos)))
         if n_neg_c > n_exp_neg:
-            perm_neg[b, :n_exp_neg] = torch.randperm(n_neg_c)[:n_exp_neg].to(torch.int32)
+            perms[1, b, :n_exp_neg] = torch.randperm(n_neg_c)[:n_exp_neg]
             n_neg, use_n = n_exp_neg, 1
         else:
             n_neg, use_n = n_neg_c, 0
-        plan[b] = torch.tensor([n_pos, n_neg, base, use_p, use_n], dtype=torch.int32)
+        plan_rows.append([n_pos, n_neg, base, use_p, use_n])
         rows.append(n_pos + n_neg)
         base += n_pos + n_neg
-    return plan, perm_pos, perm_neg, rows
+    return torch.tensor(plan_rows, dtype=torch.int32).reshape(B, 5), perms[0], perms[1], rows
+
+
+class RcnnAssigned:
+    """Result of ``rcnn_assign``: the device-side state ``rcnn_sample_targets`` consumes plus
+    the per-image (positive, negative) candidate counts on their way to the host.  The counts
+    are copied into pinned memory behind an event, so a caller can keep queueing unrelated
+    GPU work (the RPN loss) between ``rcnn_assign`` and the first ``counts()`` call — the
+    reference's CPU ``randperm`` then runs while the GPU is busy instead of behind a drained
+    stream."""
+
+    def __init__(self, proposals, num_props, gtb, gtl, num_gt, gt_inds, counts_dev, num_gts_host):
+        self.proposals, self.num_props = proposals, num_props
+        self.gtb, self.gtl, self.num_gt, self.gt_inds = gtb, gtl, num_gt, gt_inds
+        self.num_gts_host = list(num_gts_host)
+        self._counts_host = torch.empty(counts_dev.shape, dtype=counts_dev.dtype, pin_memory=True)
+        self._counts_host.copy_(counts_dev, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(counts_dev.device))
+        self._counts_dev = counts_dev          # keeps the source alive until the copy is done
+
+    def counts(self):
+        """[[n_pos_candidates, n_neg_candidates]] per image: the one host sync of the
+        training front-end (an event wait, not a stream drain)."""
+        self._event.synchronize()
+        return self._counts_host.tolist()
 
 
 @_device_guard
-def rcnn_assign_sample(proposals, num_props, gt_bboxes, gt_labels, num_classes,
-                       pos_iou_thr, neg_iou_thr, min_pos_iou=0., num=512, pos_fraction=0.25,
-                       neg_pos_ub=-1, means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.),
-                       pos_weight=-1):
-    """MaxIoUAssigner(match_low_quality=False) + RandomSampler(add_gt_as_proposals=True) +
-    BBoxHead.get_targets + the ProbRoIHead prior vector for a whole batch.
-
-    proposals (B,M,5) padded + num_props (B,) int32 (the layout of rpn_get_bboxes);
-    gt_bboxes / gt_labels: per-image lists of (G_b,4) / (G_b,) device tensors.
-    The permutations are drawn with torch.randperm on the CPU generator in the
-    reference's order (random_sampler.py:58): per image positives, then negatives.
-    Returns rois (N,5), labels (N,), label_weights (N,), bbox_targets (N,4),
-    bbox_weights (N,4), prior (N,), rows_per_image (list)."""
+def rcnn_assign(proposals, num_props, gt_bboxes, gt_labels, pos_iou_thr, neg_iou_thr,
+                min_pos_iou=0., max_gts=None):
+    """MaxIoUAssigner(match_low_quality=False) over ``cat[gt_bboxes, proposals]`` for a whole
+    batch (max_iou_assigner.py:61-212 + assign_result.py:191-205 ``add_gt_``): one launch.
+    ``max_gts`` pads the GT tensors to a fixed capacity (static shapes for a captured step)."""
     lib = _lib.load()
     proposals = _f32c(proposals, 'proposals')
     assert proposals.dim() == 3 and proposals.size(2) == 5
@@ -733,6 +753,9 @@ def rcnn_assign_sample(proposals, num_props, gt_bboxes, gt_labels, num_classes,
     num_props = num_props.to(torch.int32).contiguous()
     Gs = [int(g.size(0)) for g in gt_bboxes]
     Gmax = max(1, max(Gs))
+    if max_gts is not None:
+        assert max_gts >= Gmax
+        Gmax = int(max_gts)
     gtb = torch.zeros((B, Gmax, 4), dtype=torch.float32, device=dev)
     gtl = torch.zeros((B, Gmax), dtype=torch.int64, device=dev)
     for b in range(B):
@@ -746,13 +769,23 @@ def rcnn_assign_sample(proposals, num_props, gt_bboxes, gt_labels, num_classes,
     check(lib.brcnn_rcnn_assign(ap, proposals.data_ptr(), num_props.data_ptr(), gtb.data_ptr(),
                                 num_gt.data_ptr(), gt_inds.data_ptr(), counts.data_ptr(),
                                 _stream()), 'brcnn_rcnn_assign')
-    cnt = counts.cpu().tolist()          # the one host sync of the training front-end
-    plan, perm_pos, perm_neg, rows = sample_plan(cnt, num, pos_fraction, neg_pos_ub)
+    return RcnnAssigned(proposals, num_props, gtb, gtl, num_gt, gt_inds, counts, Gs)
+
+
+@_device_guard
+def rcnn_sample_targets(proposals, num_props, gtb, gtl, num_gt, gt_inds, plan, perm_pos,
+                        perm_neg, N, num_classes, means=(0., 0., 0., 0.),
+                        stds=(1., 1., 1., 1.), pos_weight=-1):
+    """RandomSampler row selection + BBoxHead.get_targets + the ProbRoIHead prior vector for a
+    whole batch from device-resident inputs only (one launch, no host sync: capturable).
+    plan (B,5) / perm_pos / perm_neg (B,cap) int32 come from ``sample_plan``; N = total rows.
+    Returns rois (N,5), labels (N,), label_weights (N,), bbox_targets (N,4),
+    bbox_weights (N,4), prior (N,)."""
+    lib = _lib.load()
+    dev = proposals.device
+    B, M = proposals.shape[:2]
+    Gmax = gtb.size(1)
     cap = perm_pos.size(1)
-    base = sum(rows)
-    N = base
-    to = lambda t: t.to(dev, non_blocking=True)
-    plan_d, pp_d, pn_d = to(plan), to(perm_pos), to(perm_neg)
     rois = torch.empty((N, 5), dtype=torch.float32, device=dev)
     labels = torch.empty((N,), dtype=torch.int64, device=dev)
     label_weights = torch.empty((N,), dtype=torch.float32, device=dev)
@@ -768,11 +801,37 @@ def rcnn_assign_sample(proposals, num_props, gt_bboxes, gt_labels, num_classes,
         sp.pos_weight = 1.0 if pos_weight <= 0 else float(pos_weight)
         check(lib.brcnn_rcnn_sample_targets(
             sp, proposals.data_ptr(), num_props.data_ptr(), gtb.data_ptr(), gtl.data_ptr(),
-            num_gt.data_ptr(), gt_inds.data_ptr(), plan_d.data_ptr(), pp_d.data_ptr(),
-            pn_d.data_ptr(), rois.data_ptr(), labels.data_ptr(), label_weights.data_ptr(),
+            num_gt.data_ptr(), gt_inds.data_ptr(), plan.data_ptr(), perm_pos.data_ptr(),
+            perm_neg.data_ptr(), rois.data_ptr(), labels.data_ptr(), label_weights.data_ptr(),
             bbox_targets.data_ptr(), bbox_weights.data_ptr(), prior.data_ptr(), _stream()),
             'brcnn_rcnn_sample_targets')
-    return rois, labels, label_weights, bbox_targets, bbox_weights, prior, rows
+    return rois, labels, label_weights, bbox_targets, bbox_weights, prior
+
+
+def rcnn_assign_sample(proposals, num_props, gt_bboxes, gt_labels, num_classes,
+                       pos_iou_thr, neg_iou_thr, min_pos_iou=0., num=512, pos_fraction=0.25,
+                       neg_pos_ub=-1, means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.),
+                       pos_weight=-1, assigned=None):
+    """MaxIoUAssigner(match_low_quality=False) + RandomSampler(add_gt_as_proposals=True) +
+    BBoxHead.get_targets + the ProbRoIHead prior vector for a whole batch.
+
+    proposals (B,M,5) padded + num_props (B,) int32 (the layout of rpn_get_bboxes);
+    gt_bboxes / gt_labels: per-image lists of (G_b,4) / (G_b,) device tensors.
+    The permutations are drawn with torch.randperm on the CPU generator in the
+    reference's order (random_sampler.py:58): per image positives, then negatives.
+    ``assigned``: the result of an earlier ``rcnn_assign`` on the same inputs.
+    Returns rois (N,5), labels (N,), label_weights (N,), bbox_targets (N,4),
+    bbox_weights (N,4), prior (N,), rows_per_image (list)."""
+    a = assigned if assigned is not None else rcnn_assign(
+        proposals, num_props, gt_bboxes, gt_labels, pos_iou_thr, neg_iou_thr, min_pos_iou)
+    dev = a.proposals.device
+    cnt = a.counts()                     # the one host sync of the training front-end
+    plan, perm_pos, perm_neg, rows = sample_plan(cnt, num, pos_fraction, neg_pos_ub)
+    to = lambda t: t.to(dev, non_blocking=True)
+    out = rcnn_sample_targets(a.proposals, a.num_props, a.gtb, a.gtl, a.num_gt, a.gt_inds,
+                              to(plan), to(perm_pos), to(perm_neg), sum(rows), num_classes,
+                              means, stds, pos_weight)
+    return (*out, rows)
 
 
 # --------------------------------------------------------------------------

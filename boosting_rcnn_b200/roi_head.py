@@ -95,6 +95,10 @@ class ProbRoIHead(nn.Module):
             self.bbox_assigner = build_assigner(self.train_cfg.assigner)
             self.bbox_sampler = build_sampler(self.train_cfg.sampler, context=self)
         self._hw_cache = {}
+        #: opt-in: replay the sync-free tail of the training step (sample + targets, RoIAlign,
+        #: head, boost loss and their backward) as CUDA graphs (graph.RcnnTrainGraph)
+        self.train_graph = False
+        self._train_graphs = {}
 
     with_bbox, with_mask, with_shared_head = True, False, False
 
@@ -106,8 +110,12 @@ class ProbRoIHead(nn.Module):
 
     # --------------------------------------------------------------- train
     def forward_train(self, x, img_metas, proposal_list, gt_bboxes, gt_labels,
-                      gt_bboxes_ignore=None, gt_masks=None):
+                      gt_bboxes_ignore=None, gt_masks=None, assigned=None):
+        """prob_roi_head.py:23-105.  ``assigned`` (optional, not in the reference): the handle
+        of an earlier ``assign_async`` call on the same proposals / GTs."""
         num_imgs = len(img_metas)
+        if assigned is not None:
+            return self._forward_train_fused(x, proposal_list, gt_bboxes, gt_labels, assigned)
         if gt_bboxes_ignore is None:
             gt_bboxes_ignore = [None for _ in range(num_imgs)]
         if self._fused_train_prep_ok(gt_bboxes_ignore):
@@ -150,27 +158,65 @@ class ProbRoIHead(nn.Module):
                 and s.add_gt_as_proposals and all(g is None for g in gt_bboxes_ignore)
                 and not getattr(self, 'force_python_train_prep', False))
 
-    @staticmethod
-    def _fused_train_prep_fits(num_props_cap, gt_bboxes, num):
+    def _fused_train_prep_fits(self, num_props_cap, gt_bboxes, num):
         """Limits of the fused kernels: <= 2048 GTs per image (brcnn_rcnn_assign) and a
         candidate list + selection buffer within 200 KB of shared memory
         (brcnn_rcnn_sample_targets); crowded images take the torch fallback instead of
         raising in the middle of training."""
         gmax = max([int(g.size(0)) for g in gt_bboxes] + [1])
+        if self.train_graph:
+            gmax = (gmax + 31) // 32 * 32      # _gt_capacity
         sel = 1
         while sel < max(1, num):
             sel <<= 1
         return gmax <= 2048 and sel * 8 + (gmax + num_props_cap) * 4 <= 200 * 1024
 
-    def _forward_train_fused(self, x, proposal_list, gt_bboxes, gt_labels):
+    def assign_async(self, proposal_list, gt_bboxes, gt_labels, gt_bboxes_ignore=None):
+        """Optional first half of ``forward_train``: launch the batch-wide MaxIoU assignment
+        now and return a handle for ``forward_train(..., assigned=handle)``.  GPU work queued
+        between the two calls (the RPN loss) overlaps the reference's CPU ``randperm``.
+        Returns None when the fused path does not cover the settings (``forward_train`` then
+        does everything itself)."""
+        ignore = gt_bboxes_ignore if gt_bboxes_ignore is not None else [None] * len(gt_bboxes)
+        if not self._fused_train_prep_ok(ignore):
+            return None
         props = proposal_list if isinstance(proposal_list, PaddedProposals) \
             else pad_proposals(proposal_list)
+        if not self._fused_train_prep_fits(props.boxes.size(1), gt_bboxes, self.bbox_sampler.num):
+            return None
+        a = self.bbox_assigner
+        return ops.rcnn_assign(props.boxes, props.num, gt_bboxes, gt_labels, a.pos_iou_thr,
+                               a.neg_iou_thr, a.min_pos_iou, max_gts=self._gt_capacity(gt_bboxes))
+
+    def _gt_capacity(self, gt_bboxes):
+        """GT capacity of the assignment tensors: the batch maximum, or (captured training
+        step) the next multiple of 32 so that the graph's shapes repeat from step to step."""
+        if not self.train_graph:
+            return None
+        g = max([int(t.size(0)) for t in gt_bboxes] + [1])
+        return (g + 31) // 32 * 32
+
+    def _forward_train_fused(self, x, proposal_list, gt_bboxes, gt_labels, assigned=None):
         a, s, h = self.bbox_assigner, self.bbox_sampler, self.bbox_head
-        rois, labels, label_weights, bbox_targets, bbox_weights, prior, _ = \
-            ops.rcnn_assign_sample(
-                props.boxes, props.num, gt_bboxes, gt_labels, h.num_classes, a.pos_iou_thr,
-                a.neg_iou_thr, a.min_pos_iou, s.num, s.pos_fraction, s.neg_pos_ub,
-                h.bbox_coder.means, h.bbox_coder.stds, self.train_cfg.pos_weight)
+        if assigned is None:
+            props = proposal_list if isinstance(proposal_list, PaddedProposals) \
+                else pad_proposals(proposal_list)
+            assigned = ops.rcnn_assign(props.boxes, props.num, gt_bboxes, gt_labels,
+                                       a.pos_iou_thr, a.neg_iou_thr, a.min_pos_iou,
+                                       max_gts=self._gt_capacity(gt_bboxes))
+        plan, perm_pos, perm_neg, rows = ops.sample_plan(assigned.counts(), s.num,
+                                                         s.pos_fraction, s.neg_pos_ub)
+        if self.train_graph:
+            from .graph import RcnnTrainGraph
+            out = RcnnTrainGraph.run(self, x, assigned, plan, perm_pos, perm_neg, sum(rows))
+            if out is not None:
+                return out
+        dev = assigned.proposals.device
+        to = lambda t: t.to(dev, non_blocking=True)
+        rois, labels, label_weights, bbox_targets, bbox_weights, prior = ops.rcnn_sample_targets(
+            assigned.proposals, assigned.num_props, assigned.gtb, assigned.gtl, assigned.num_gt,
+            assigned.gt_inds, to(plan), to(perm_pos), to(perm_neg), sum(rows), h.num_classes,
+            h.bbox_coder.means, h.bbox_coder.stds, self.train_cfg.pos_weight)
         bbox_results = self._bbox_forward(x, rois)
         return h.boost_loss(bbox_results['cls_score'], bbox_results['bbox_pred'], labels,
                             label_weights, bbox_targets, bbox_weights, prior, self.gamma,

@@ -315,6 +315,63 @@ def test_fused_assign_sample_targets_equals_executed_reference(cuda, case):
         assert torch.allclose(out[0][k], out[1][k], rtol=1e-6, atol=1e-7), k
 
 
+def test_train_graph_and_assign_async_match_eager(cuda):
+    """roi_head.train_graph (graph.py::RcnnTrainGraph: the R-CNN half of the training step as
+    a forward and a backward CUDA graph) and ``assign_async`` + ``forward_train(assigned=)``
+    give the losses and every gradient of the plain eager ``forward_train`` (bit for bit
+    without the graph, <= 1e-5 of the largest element with it), step after step with different proposals / permutations through the SAME captured graphs."""
+    torch.manual_seed(5)
+    _, roi, m = configs.build_hot_path('coco', train=True)
+    roi = roi.to(cuda).train()
+    sizes = synth.featmap_sizes(256, 320)
+    params = [p for p in roi.parameters() if p.requires_grad]
+
+    def run(case, seed, mode):
+        gts_h, labels_h, plist_h = synth.rcnn_train_case(case)
+        B = len(plist_h)
+        gts = [torch.from_numpy(g).to(cuda) for g in gts_h]
+        labels = [torch.from_numpy(l).to(cuda) for l in labels_h]
+        plist = [torch.from_numpy(p).to(cuda) for p in plist_h]
+        feats = [torch.from_numpy(f).to(cuda).requires_grad_(True)
+                 for f in synth.fpn_feats(B, 256, sizes, seed=seed)]
+        for p in params:
+            p.grad = None
+        roi.train_graph = mode == 'graph'
+        torch.manual_seed(seed)
+        if mode == 'eager':
+            out = roi.forward_train(feats, _metas(B), plist, gts, labels)
+        else:
+            pending = roi.assign_async(plist, gts, labels)
+            assert pending is not None
+            torch.zeros(1 << 20, device=cuda).sum()           # unrelated work in between
+            out = roi.forward_train(feats, _metas(B), plist, gts, labels, assigned=pending)
+        (out['loss_cls'] + 3 * out['loss_bbox']).backward()
+        torch.cuda.synchronize()
+        return ([out[k].detach().clone() for k in ('loss_cls', 'loss_bbox', 'acc')]
+                + [p.grad.clone() for p in params] + [f.grad.clone() for f in feats])
+
+    cases = [c for c in synth.RCNN_TRAIN_CASES]
+    seen = 0
+    for step, case in enumerate(cases + cases[:1]):
+        ref = run(case, 100 + step, 'eager')
+        for mode in ('async', 'graph'):
+            got = run(case, 100 + step, mode)
+            assert len(ref) == len(got)
+            for i, (a, b) in enumerate(zip(ref, got)):
+                if mode == 'async':      # same launches in the same order
+                    assert torch.equal(a, b), (case, mode, i)
+                else:                    # cuBLAS may pick another algorithm under capture
+                    err = (a.float() - b.float()).abs().max().item()
+                    assert err <= 1e-5 * a.float().abs().max().item() + 1e-12, (case, mode, i, err)
+        seen += 1
+    graphs = [g for g in roi._train_graphs.values() if g]
+    assert graphs and all(roi._train_graphs.values()), 'capture failed: eager fallback ran'
+    # the repeated case replayed an existing graph instead of capturing another one
+    assert len(roi._train_graphs) <= len(cases)
+    assert graphs[0].launches_per_step >= 5
+    roi.train_graph = False
+
+
 def test_dual_stream_runner_matches_single_graph(cuda):
     """graph.py::DualStreamRunner: two graphs replayed alternately on two streams give the
     same detections as one graph, for any interleaving."""

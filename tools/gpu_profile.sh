@@ -11,12 +11,12 @@ FAST="--no-train-record --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 80 --csv \
     --log-file $out/${tag}_launches_infer.csv python bench.py --steps 2 --warmup 3 --no-graph $FAST > $out/${tag}_infer_under_ncu.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv \
-    --log-file $out/${tag}_launches_train.csv python bench.py --mode train --cfg coco --batch 2 --steps 1 --warmup 3 > $out/${tag}_train_under_ncu.log 2>&1
+    --log-file $out/${tag}_launches_train.csv python bench.py --mode train --train-eager --cfg coco --batch 2 --steps 1 --warmup 3 > $out/${tag}_train_under_ncu.log 2>&1
 # full captures of our kernels, one step after 3 warm-up steps
 ncu --set full --clock-control none --import-source on -k "$K" -s 30 -c 10 -o $out/${tag}_full_infer \
     python bench.py --steps 1 --warmup 3 --no-graph $FAST > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k "$K" -s 54 -c 18 -o $out/${tag}_full_train \
-    python bench.py --mode train --cfg coco --batch 2 --steps 1 --warmup 3 > /dev/null 2>&1
+    python bench.py --mode train --train-eager --cfg coco --batch 2 --steps 1 --warmup 3 > /dev/null 2>&1
 # clean bench lines (not under a profiler)
 python bench.py --steps 100 --warmup 5 > $out/${tag}_bench_infer.json 2> $out/${tag}_bench_infer.err
 python bench.py --mode train --cfg coco --batch 2 --steps 20 --warmup 3 > $out/${tag}_bench_train.json 2>/dev/null
