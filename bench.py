@@ -464,6 +464,10 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_coll = float(t.item())
         del flat
+    n_graphs = len(graphs)
+    launches_in_graphs = graphs[0].launches_per_step if graphs else 0
+    del graphs
+    roi_head._train_graphs.clear()     # graph <-> head reference cycle: release the pools now
     if rank != 0:
         return None
     rec = {
@@ -486,8 +490,9 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
         'launch_mode': ('RPN loss / proposals / R-CNN assignment eager, then one event wait for '
                         'the reference\'s CPU randperm, then the R-CNN half (sample + targets, '
                         'RoIAlign, 2-fc head, boost loss, backward) as two CUDA-graph replays'
-                        if graphs else
+                        if n_graphs else
                         'eager (one event wait per step: the reference\'s CPU randperm)'),
+        'gpu_launches_per_step_inside_graphs': launches_in_graphs,
         'train_graph_check': graph_check,
         'losses': {k: float(v) for k, v in scal.items()},
     }
