@@ -385,11 +385,12 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
         pending = roi_head.assign_async(plist, gts, labels)
         rpn_losses = rpn_head.loss(cls, box, iou, gts, metas)
         losses = roi_head.forward_train(feats, metas, plist, gts, labels, assigned=pending)
+        rpn_sums = {k: torch.stack(v).sum() for k, v in rpn_losses.items()}
         total = losses['loss_cls'] + losses['loss_bbox']
-        for v in rpn_losses.values():
-            total = total + torch.stack(v).sum()
+        for v in rpn_sums.values():
+            total = total + v
         total.backward()
-        losses = dict(losses, **{k: torch.stack(v).sum() for k, v in rpn_losses.items()})
+        losses = dict(losses, **rpn_sums)
         if world > 1 and comm:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -464,6 +465,14 @@ def train_record(args, rank, world, local_rank, dist, cfg_name='coco', B=2, K=20
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_coll = float(t.item())
         del flat
+    if os.environ.get('BENCH_TRAIN_TRACE') and world == 1:
+        # developer aid: chrome trace of three steps (kernels + host ranges) for gap analysis
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step(False)
+            torch.cuda.synchronize()
+        prof.export_chrome_trace(os.environ['BENCH_TRAIN_TRACE'])
     n_graphs = len(graphs)
     launches_in_graphs = graphs[0].launches_per_step if graphs else 0
     del graphs

@@ -203,7 +203,10 @@ class RcnnTrainGraph:
 
     def __init__(self, roi_head, feats, assigned, plan, perm_pos, perm_neg, num_rows):
         dev = assigned.proposals.device
-        self.static = {k: getattr(assigned, k).clone() for k in self._NAMES}
+        # the head's reusable assignment buffers are the graph's inputs as they are; anything
+        # else is cloned and refilled by copies before every replay
+        self.static = {k: (getattr(assigned, k) if assigned.is_static
+                           else getattr(assigned, k).clone()) for k in self._NAMES}
         B, cap = perm_pos.shape
         # plan + both permutations cross the bus as ONE pinned buffer
         self._host = torch.empty((B * 5 + 2 * B * cap,), dtype=torch.int32).pin_memory()
@@ -236,12 +239,16 @@ class RcnnTrainGraph:
         h[b:] = perm_neg.reshape(-1)
         self._dev.copy_(h, non_blocking=True)
         if not first:
-            torch._foreach_copy_([self.static[k] for k in self._NAMES],
-                                 [getattr(assigned, k) for k in self._NAMES])
+            todo = [k for k in self._NAMES
+                    if getattr(assigned, k).data_ptr() != self.static[k].data_ptr()]
+            if todo:
+                torch._foreach_copy_([self.static[k] for k in todo],
+                                     [getattr(assigned, k) for k in todo])
 
     @staticmethod
     def _key(feats, assigned, perm_pos, num_rows):
         return (int(num_rows), tuple(assigned.proposals.shape), int(assigned.gtb.size(1)),
+                assigned.proposals.data_ptr() if assigned.is_static else 0,
                 tuple(perm_pos.shape), str(assigned.proposals.device),
                 tuple((tuple(f.shape), tuple(f.stride()), bool(f.requires_grad)) for f in feats))
 

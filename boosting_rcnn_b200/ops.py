@@ -113,6 +113,21 @@ def _device_guard(fn):
     return wrapper
 
 
+def host_to_device(data, dtype, device):
+    """Small host list / CPU tensor -> device through PINNED staging memory.  A copy from
+    pageable memory (``torch.tensor(x).to(dev)``, ``torch.tensor(x, device=dev)``) makes the
+    host wait until the stream has drained up to the copy — a hidden synchronisation that
+    stops the host from queueing work ahead of the GPU.  The caching host allocator keeps the
+    staging block alive until the copy has executed."""
+    if torch.device(device).type != 'cuda':
+        return torch.as_tensor(data, dtype=dtype).to(device)
+    if isinstance(data, torch.Tensor):
+        t = data.to(dtype).pin_memory()
+    else:
+        t = torch.tensor(data, dtype=dtype, pin_memory=True)
+    return t.to(device, non_blocking=True)
+
+
 def _f32c(t, name):
     if not t.is_cuda:
         raise RuntimeError(
@@ -722,10 +737,12 @@ class RcnnAssigned:
     reference's CPU ``randperm`` then runs while the GPU is busy instead of behind a drained
     stream."""
 
-    def __init__(self, proposals, num_props, gtb, gtl, num_gt, gt_inds, counts_dev, num_gts_host):
+    def __init__(self, proposals, num_props, gtb, gtl, num_gt, gt_inds, counts_dev, num_gts_host,
+                 is_static=False):
         self.proposals, self.num_props = proposals, num_props
         self.gtb, self.gtl, self.num_gt, self.gt_inds = gtb, gtl, num_gt, gt_inds
         self.num_gts_host = list(num_gts_host)
+        self.is_static = is_static      # the tensors are a caller-owned, reused buffer set
         self._counts_host = torch.empty(counts_dev.shape, dtype=counts_dev.dtype, pin_memory=True)
         self._counts_host.copy_(counts_dev, non_blocking=True)
         self._event = torch.cuda.Event()
@@ -739,12 +756,25 @@ class RcnnAssigned:
         return self._counts_host.tolist()
 
 
+def rcnn_assign_buffers(batch, max_props, max_gts, device):
+    """A reusable buffer set for ``rcnn_assign(..., static=...)``: the inputs of the captured
+    training step live at fixed addresses, so nothing has to be copied between the assignment
+    and the graph replay."""
+    z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
+    return dict(proposals=z((batch, max_props, 5), torch.float32),
+                num_props=z((batch,), torch.int32), gtb=z((batch, max_gts, 4), torch.float32),
+                gtl=z((batch, max_gts), torch.int64), num_gt=z((batch,), torch.int32),
+                gt_inds=z((batch, max_gts + max_props), torch.int32))
+
+
 @_device_guard
 def rcnn_assign(proposals, num_props, gt_bboxes, gt_labels, pos_iou_thr, neg_iou_thr,
-                min_pos_iou=0., max_gts=None):
+                min_pos_iou=0., max_gts=None, static=None):
     """MaxIoUAssigner(match_low_quality=False) over ``cat[gt_bboxes, proposals]`` for a whole
     batch (max_iou_assigner.py:61-212 + assign_result.py:191-205 ``add_gt_``): one launch.
-    ``max_gts`` pads the GT tensors to a fixed capacity (static shapes for a captured step)."""
+    ``max_gts`` pads the GT tensors to a fixed capacity (static shapes for a captured step);
+    ``static``: a ``rcnn_assign_buffers`` set of exactly these shapes to work in (the proposals
+    are copied into it; GT rows beyond an image's count keep stale values nobody reads)."""
     lib = _lib.load()
     proposals = _f32c(proposals, 'proposals')
     assert proposals.dim() == 3 and proposals.size(2) == 5
@@ -756,20 +786,30 @@ def rcnn_assign(proposals, num_props, gt_bboxes, gt_labels, pos_iou_thr, neg_iou
     if max_gts is not None:
         assert max_gts >= Gmax
         Gmax = int(max_gts)
-    gtb = torch.zeros((B, Gmax, 4), dtype=torch.float32, device=dev)
-    gtl = torch.zeros((B, Gmax), dtype=torch.int64, device=dev)
+    if static is not None:
+        assert tuple(static['proposals'].shape) == (B, M, 5) and static['gtb'].size(1) == Gmax
+        static['proposals'].copy_(proposals)
+        static['num_props'].copy_(num_props)
+        proposals, num_props = static['proposals'], static['num_props']
+        gtb, gtl, gt_inds = static['gtb'], static['gtl'], static['gt_inds']
+        num_gt = static['num_gt']
+        num_gt.copy_(torch.tensor(Gs, dtype=torch.int32, pin_memory=True), non_blocking=True)
+    else:
+        gtb = torch.zeros((B, Gmax, 4), dtype=torch.float32, device=dev)
+        gtl = torch.zeros((B, Gmax), dtype=torch.int64, device=dev)
+        num_gt = host_to_device(Gs, torch.int32, dev)
+        gt_inds = torch.empty((B, Gmax + M), dtype=torch.int32, device=dev)
     for b in range(B):
         if Gs[b]:
             gtb[b, :Gs[b]] = gt_bboxes[b].float()
             gtl[b, :Gs[b]] = gt_labels[b].long()
-    num_gt = torch.tensor(Gs, dtype=torch.int32).to(dev)
-    gt_inds = torch.empty((B, Gmax + M), dtype=torch.int32, device=dev)
     counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
     ap = AssignParams(B, M, Gmax, float(pos_iou_thr), float(neg_iou_thr), float(min_pos_iou), 0)
     check(lib.brcnn_rcnn_assign(ap, proposals.data_ptr(), num_props.data_ptr(), gtb.data_ptr(),
                                 num_gt.data_ptr(), gt_inds.data_ptr(), counts.data_ptr(),
                                 _stream()), 'brcnn_rcnn_assign')
-    return RcnnAssigned(proposals, num_props, gtb, gtl, num_gt, gt_inds, counts, Gs)
+    return RcnnAssigned(proposals, num_props, gtb, gtl, num_gt, gt_inds, counts, Gs,
+                        is_static=static is not None)
 
 
 @_device_guard
@@ -827,7 +867,7 @@ def rcnn_assign_sample(proposals, num_props, gt_bboxes, gt_labels, num_classes,
     dev = a.proposals.device
     cnt = a.counts()                     # the one host sync of the training front-end
     plan, perm_pos, perm_neg, rows = sample_plan(cnt, num, pos_fraction, neg_pos_ub)
-    to = lambda t: t.to(dev, non_blocking=True)
+    to = lambda t: host_to_device(t, torch.int32, dev)
     out = rcnn_sample_targets(a.proposals, a.num_props, a.gtb, a.gtl, a.num_gt, a.gt_inds,
                               to(plan), to(perm_pos), to(perm_neg), sum(rows), num_classes,
                               means, stds, pos_weight)

@@ -58,7 +58,7 @@ def pad_proposals(proposal_list):
             boxes[b, :n, :4] = p[:, :4]
             # the reference takes boxes[:, -1] as the prior, whatever it is
             boxes[b, :n, 4] = p[:, -1]
-    num = torch.tensor([p.size(0) for p in proposal_list], dtype=torch.int32, device=dev)
+    num = ops.host_to_device([p.size(0) for p in proposal_list], torch.int32, dev)
     return PaddedProposals(boxes, num)
 
 
@@ -99,6 +99,7 @@ class ProbRoIHead(nn.Module):
         #: head, boost loss and their backward) as CUDA graphs (graph.RcnnTrainGraph)
         self.train_graph = False
         self._train_graphs = {}
+        self._train_buffers = {}
 
     with_bbox, with_mask, with_shared_head = True, False, False
 
@@ -184,26 +185,31 @@ class ProbRoIHead(nn.Module):
             else pad_proposals(proposal_list)
         if not self._fused_train_prep_fits(props.boxes.size(1), gt_bboxes, self.bbox_sampler.num):
             return None
-        a = self.bbox_assigner
-        return ops.rcnn_assign(props.boxes, props.num, gt_bboxes, gt_labels, a.pos_iou_thr,
-                               a.neg_iou_thr, a.min_pos_iou, max_gts=self._gt_capacity(gt_bboxes))
+        return self._assign(props, gt_bboxes, gt_labels)
 
-    def _gt_capacity(self, gt_bboxes):
-        """GT capacity of the assignment tensors: the batch maximum, or (captured training
-        step) the next multiple of 32 so that the graph's shapes repeat from step to step."""
-        if not self.train_graph:
-            return None
-        g = max([int(t.size(0)) for t in gt_bboxes] + [1])
-        return (g + 31) // 32 * 32
+    def _assign(self, props, gt_bboxes, gt_labels):
+        """Batch-wide assignment.  Captured training step: the GT capacity is the next multiple
+        of 32 (the graph's shapes repeat from step to step) and the kernels work in a buffer
+        set at fixed addresses (nothing is copied between the assignment and the replay)."""
+        a = self.bbox_assigner
+        cap, static = None, None
+        if self.train_graph:
+            g = max([int(t.size(0)) for t in gt_bboxes] + [1])
+            cap = (g + 31) // 32 * 32
+            key = (tuple(props.boxes.shape[:2]), cap, str(props.boxes.device))
+            static = self._train_buffers.get(key)
+            if static is None:
+                static = self._train_buffers[key] = ops.rcnn_assign_buffers(
+                    props.boxes.size(0), props.boxes.size(1), cap, props.boxes.device)
+        return ops.rcnn_assign(props.boxes, props.num, gt_bboxes, gt_labels, a.pos_iou_thr,
+                               a.neg_iou_thr, a.min_pos_iou, max_gts=cap, static=static)
 
     def _forward_train_fused(self, x, proposal_list, gt_bboxes, gt_labels, assigned=None):
         a, s, h = self.bbox_assigner, self.bbox_sampler, self.bbox_head
         if assigned is None:
             props = proposal_list if isinstance(proposal_list, PaddedProposals) \
                 else pad_proposals(proposal_list)
-            assigned = ops.rcnn_assign(props.boxes, props.num, gt_bboxes, gt_labels,
-                                       a.pos_iou_thr, a.neg_iou_thr, a.min_pos_iou,
-                                       max_gts=self._gt_capacity(gt_bboxes))
+            assigned = self._assign(props, gt_bboxes, gt_labels)
         plan, perm_pos, perm_neg, rows = ops.sample_plan(assigned.counts(), s.num,
                                                          s.pos_fraction, s.neg_pos_ub)
         if self.train_graph:
@@ -212,7 +218,7 @@ class ProbRoIHead(nn.Module):
             if out is not None:
                 return out
         dev = assigned.proposals.device
-        to = lambda t: t.to(dev, non_blocking=True)
+        to = lambda t: ops.host_to_device(t, torch.int32, dev)
         rois, labels, label_weights, bbox_targets, bbox_weights, prior = ops.rcnn_sample_targets(
             assigned.proposals, assigned.num_props, assigned.gtb, assigned.gtl, assigned.num_gt,
             assigned.gt_inds, to(plan), to(perm_pos), to(perm_neg), sum(rows), h.num_classes,

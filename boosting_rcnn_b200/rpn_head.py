@@ -275,9 +275,9 @@ class ATSSRPNHead(nn.Module):
         for b in range(B):
             if Gs[b]:
                 gtb[b, :Gs[b]] = gt_bboxes[b][:, :4].float()
-        num_gt = torch.tensor(Gs, dtype=torch.int32).to(dev, non_blocking=True)
-        pad_hw = torch.tensor([[m['pad_shape'][0], m['pad_shape'][1]] for m in img_metas],
-                              dtype=torch.float32).to(dev, non_blocking=True)
+        num_gt = ops.host_to_device(Gs, torch.int32, dev)
+        pad_hw = ops.host_to_device([[m['pad_shape'][0], m['pad_shape'][1]] for m in img_metas],
+                                    torch.float32, dev)
         a = self.train_cfg.assigner
         varifocal = type(self.loss_cls).__name__ == 'VarifocalLoss'
         p = ops.make_rpn_loss_params(
