@@ -73,3 +73,54 @@ def test_single_process_paths_are_identity():
     det = torch.arange(2 * 3 * 5, dtype=torch.float32).reshape(2, 3, 5)
     col = bdist.collect_detections(det, torch.tensor([[1, 2, 3], [4, 5, 6]]), torch.tensor([2, 0]))
     assert [tuple(c.shape) for c in col] == [(2, 6), (0, 6)] and col[0][1, 5] == 2
+
+
+RESULTS_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                            'reference_golden_results.npz')
+
+
+def _wire_worker(rank, world, port, out):
+    import numpy as np
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    g = np.load(RESULTS_GOLD)
+    mine = g['shards'][rank]                        # DistributedSampler shard (round-robin, padded)
+    det = torch.from_numpy(g['det'][mine])
+    lab = torch.from_numpy(g['lab'][mine])
+    num = torch.from_numpy(g['num'][mine])
+    col = bdist.collect_detections(det, lab, num, size=int(g['det'].shape[0]), interleaved=True)
+    out.put((rank, None if col is None else [c.numpy() for c in col]))
+    dist.destroy_process_group()
+
+
+def test_result_wire_equals_executed_reference():
+    """``dist.collect_detections(interleaved=True)`` + ``bbox2result`` give,
+    on rank 0, exactly what the reference's ``collect_results_cpu`` (mmdet/apis/test.py:273-313)
+    returns for the same per-rank ``bbox2result`` lists (transforms.py:100-117) — golden produced
+    by executing both reference functions (tests/golden/make_golden_results.py): dataset order
+    restored from the round-robin shards, the sampler's padding image dropped, per-class arrays
+    bit-identical (incl. an image without detections)."""
+    import numpy as np
+    from boosting_rcnn_b200.roi_head import bbox2result
+    g = np.load(RESULTS_GOLD)
+    world, C = int(g['world']), int(g['num_classes'])
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_wire_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(res[r] is None for r in range(1, world))
+    col = res[0]
+    assert len(col) == g['det'].shape[0]
+    for i, rows in enumerate(col):
+        per_class = bbox2result(rows[:, :5], rows[:, 5].astype(np.int64), C)
+        assert len(per_class) == C
+        for c in range(C):
+            ref = g[f'out/{i}/{c}']
+            assert per_class[c].shape == ref.shape, (i, c)
+            np.testing.assert_array_equal(per_class[c].view(np.uint32), ref.view(np.uint32))
