@@ -816,9 +816,14 @@ def main():
     train = None
     if not args.no_train_record:
         import torch.distributed as tdist
-        train = train_record(args, rank, world, local_rank, tdist if world > 1 else None,
-                             cfg_name='coco', B=2, K=min(max(args.steps, 10), 20), W=3,
-                             with_stages=(rank == 0))
+        try:
+            train = train_record(args, rank, world, local_rank, tdist if world > 1 else None,
+                                 cfg_name='coco', B=2, K=min(max(args.steps, 10), 20), W=3,
+                                 with_stages=(rank == 0))
+        except Exception as e:  # noqa: BLE001 - the sub-record must not take the headline down
+            import traceback
+            traceback.print_exc()
+            train = {'error': f'{type(e).__name__}: {e}'} if rank == 0 else None
         torch.cuda.empty_cache()
     rpn_head, roi_head = rpn_head.to(dev).eval(), roi_head.to(dev).eval()
     sizes, h_feats, h_cls, h_box, h_iou = make_inputs(B, pad_hw, A, C, seed=1234 + rank, pin=True)
