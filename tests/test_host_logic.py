@@ -236,3 +236,49 @@ def test_two_phase_topk_selection_is_a_superset():
         picked = bins >= max(d - 1, 0)
         kth = np.sort(s)[::-1][k - 1]
         assert picked[s >= kth].all(), (trial, n, k, d)
+
+
+def test_device_guard_builds_no_reference_cycles(monkeypatch):
+    """ops._device_guard must not leave garbage behind: a recursive local closure over the
+    first tensor argument once kept every eager step's autograd graph alive until the cyclic
+    GC ran, which pinned the parameters' AccumulateGrad nodes to the default stream and broke
+    the capture of the training-step graphs."""
+    import gc
+    import weakref
+
+    # make the guard take its CUDA branch on this CPU-only machine
+    def first_tensor(args):
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                return a
+            if isinstance(a, (list, tuple)):
+                t = first_tensor(a)
+                if t is not None:
+                    return t
+        return None
+    monkeypatch.setattr(ops, '_first_cuda_tensor', first_tensor)
+    monkeypatch.setattr(torch.cuda, 'current_device', lambda: None)   # == cpu device index
+
+    @ops._device_guard
+    def op(x, ys, k=None):
+        return x.sum() + ys[0].sum()
+
+    gc.collect()
+    gc.disable()
+    try:
+        w = torch.ones(4, requires_grad=True)
+        x = w * 2
+        out = op(x, [torch.ones(2)], k=(torch.zeros(1),))
+        ref = weakref.ref(x)
+        del x, out
+        assert ref() is None, 'the first tensor argument outlived its last user reference'
+        assert gc.collect() == 0
+    finally:
+        gc.enable()
+
+
+def test_host_to_device_without_cuda_is_a_plain_copy():
+    t = ops.host_to_device([3, 4], torch.int32, 'cpu')
+    assert t.dtype == torch.int32 and t.tolist() == [3, 4]
+    t = ops.host_to_device(torch.tensor([1.5]), torch.float32, torch.device('cpu'))
+    assert t.tolist() == [1.5]
