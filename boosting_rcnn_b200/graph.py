@@ -268,6 +268,9 @@ class RcnnTrainGraph:
             try:
                 g = cls(roi_head, feats, assigned, plan, perm_pos, perm_neg, num_rows)
             except Exception as e:  # noqa: BLE001 - capture is an optimisation, never fatal
+                # (a failure in the warm-up passes is harmless; one inside the stream capture
+                # itself can leave torch's CUDA generator registered with the dead capture, and
+                # later random ops then raise — treat this warning as a bug report)
                 warnings.warn(f'RcnnTrainGraph: capture failed ({type(e).__name__}: {e}); '
                               f'the eager training path runs instead')
                 roi_head._train_graphs[key] = False
