@@ -297,9 +297,15 @@ class ATSSRPNHead(nn.Module):
 
     def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None,
                       proposal_cfg=None, **kwargs):
-        """atss_rpn_head.py:270-294: losses, and proposals when ``proposal_cfg`` is given."""
+        """atss_rpn_head.py:270-294: losses, and proposals when ``proposal_cfg`` is given.
+        With ``self.padded_proposals = True`` (opt-in, default off) the proposals are returned
+        as device-resident ``PaddedProposals`` — what ``ProbRoIHead.forward_train`` of this
+        package consumes directly — instead of the reference's per-image list, whose lengths
+        cost a host read per step."""
         outs = self(x)
         losses = self.loss(*outs, gt_bboxes, img_metas, gt_bboxes_ignore=gt_bboxes_ignore)
         if proposal_cfg is None:
             return losses
+        if getattr(self, 'padded_proposals', False):
+            return losses, self.get_bboxes_padded(*outs, img_metas, cfg=proposal_cfg)
         return losses, self.get_bboxes(*outs, img_metas, cfg=proposal_cfg)
